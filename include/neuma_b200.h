@@ -1,0 +1,201 @@
+/*
+ * neuma_b200.h -- C ABI of libneuma_b200.so
+ *
+ * B200-native (sm_100a) replacement for the one hot path of XJay18/NeuMA: the
+ * differentiable MLS-MPM substep, the neural constitutive law, the
+ * particle->Gaussian binding, and the Particle-GS tile rasterizer.
+ *
+ * The reference has NO native interface for this path: its kernels are Warp-DSL
+ * Python JIT-compiled at run time (modules/nclaw/sim/mpm.py:321-498,
+ * modules/nclaw/warp/svd.py:59-96, modules/d3gs/utils/simulation_utils.py:25-48)
+ * and an external CUDA extension (diff_gaussian_rasterization, call site
+ * modules/tune/utils.py:385-419).  Each entry point below names the reference
+ * symbol it replaces; INTEGRATION.md shows the ctypes stub a maintainer adds on
+ * the reference side.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - all arrays are fp32 / int32, C-contiguous, in the reference's layouts:
+ *       x,v [Np,3]; C,F,stress [Np,3,3] row-major; vol,rho,clip_bound [Np];
+ *       enabled int32[Np]; packed covariances [K,6] = xx,xy,xz,yy,yz,zz;
+ *   - the caller owns every array; the library owns only the ctx workspace
+ *     (grid, sort buffers), grown lazily and never returned;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no
+ *     entry point synchronises the device unless documented;
+ *   - every entry returns 0 on success, non-zero on failure; the message is
+ *     available from neuma_last_error(ctx).  No exceptions cross the ABI;
+ *   - a ctx is bound to one device and is not thread-safe (the reference is
+ *     single-threaded, experiments/finetune.py:507).
+ */
+#ifndef NEUMA_B200_H
+#define NEUMA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct neuma_ctx neuma_ctx;
+
+/* MPMConstant, modules/nclaw/sim/mpm.py:158-167 (+ bc from :545-550).
+ * z_off / nz describe the z-slab of the grid this ctx holds: grid planes
+ * [z_off, z_off + nz).  Single GPU: z_off = 0, nz = num_grids. */
+typedef struct {
+  int32_t num_grids;
+  float dt;
+  int32_t bound;
+  float gravity[3];
+  float dx;
+  float inv_dx;
+  float eps;
+  int32_t bc;    /* 0 = noslip (mpm.py:402-429), 1 = freeslip (mpm.py:373-400) */
+  int32_t z_off; /* first grid plane held by this ctx */
+  int32_t nz;    /* number of grid planes held by this ctx */
+} neuma_mpm_const;
+
+/* GaussianRasterizationSettings, modules/d3gs/gaussian_renderer/__init__.py:103-116.
+ * viewmatrix / projmatrix are the reference's transposed (row-vector) 4x4s
+ * (modules/d3gs/scene/cameras.py:54-56), flattened row-major, HOST arrays. */
+typedef struct {
+  int32_t image_height;
+  int32_t image_width;
+  float tanfovx;
+  float tanfovy;
+  float bg[3];
+  float scale_modifier;
+  float viewmatrix[16];
+  float projmatrix[16];
+  int32_t sh_degree;
+  float campos[3];
+  int32_t prefiltered;
+  int32_t debug;
+} neuma_raster_settings;
+
+/* ---- context ---------------------------------------------------------- */
+int neuma_ctx_create(int device, neuma_ctx** out);
+int neuma_ctx_destroy(neuma_ctx* ctx);
+const char* neuma_last_error(neuma_ctx* ctx);
+int neuma_version(void);
+/* number of kernels this ctx has launched since creation (bench.py gpu_launches) */
+long long neuma_launch_count(neuma_ctx* ctx);
+
+/* ---- MPM substep: modules/nclaw/sim/mpm.py ---------------------------- */
+/* grid.clear(), mpm.py:147-150 / :290 */
+int neuma_mpm_grid_clear(neuma_ctx* ctx, const neuma_mpm_const* c, void* stream);
+/* p2g, mpm.py:321-371 (accumulates into the ctx grid) */
+int neuma_mpm_p2g(neuma_ctx* ctx, const neuma_mpm_const* c, int n,
+                  const float* x, const float* v, const float* C, const float* stress,
+                  const float* vol, const float* rho, const int32_t* enabled, void* stream);
+/* grid_op_noslip / grid_op_freeslip, mpm.py:373-429 (dense sweep, writes grid.v) */
+int neuma_mpm_grid_op(neuma_ctx* ctx, const neuma_mpm_const* c, void* stream);
+/* g2p, mpm.py:432-498.  In-place safe (x2 may alias x, F2 may alias F), as
+ * MPMForwardSim requires (modules/nclaw/sim/interface.py:133).
+ * lazy_grid_op != 0: evaluate the grid_op arithmetic per gathered node from
+ * (mv, m) instead of reading grid.v (no dense sweep needed). */
+int neuma_mpm_g2p(neuma_ctx* ctx, const neuma_mpm_const* c, int n,
+                  const float* x, const float* F, const float* clip_bound, const int32_t* enabled,
+                  float* x2, float* v2, float* C2, float* F2, int lazy_grid_op, void* stream);
+/* copies the ctx grid out in the reference's layout (mpm.py:131-142): mv, v
+ * [G,G,nz,3] and m [G,G,nz], index [ix][iy][iz - z_off]; any pointer may be NULL. */
+int neuma_mpm_grid_export(neuma_ctx* ctx, const neuma_mpm_const* c,
+                          float* mv, float* m, float* v, void* stream);
+/* adds (dir=+1) / overwrites (dir=0) `nplanes` z-planes of the packed (mv,m)
+ * grid starting at plane z (global index) from/to a contiguous buffer of
+ * nplanes*G*G*4 floats: the slab-halo pack/unpack. */
+int neuma_mpm_halo_pack(neuma_ctx* ctx, const neuma_mpm_const* c, int z, int nplanes,
+                        float* buf, void* stream);
+int neuma_mpm_halo_unpack_add(neuma_ctx* ctx, const neuma_mpm_const* c, int z, int nplanes,
+                              const float* buf, void* stream);
+
+/* MPMModel.forward, mpm.py:279-297: clear + p2g + grid_op + g2p, fused
+ * (clear, p2g, g2p with lazy grid_op). */
+int neuma_mpm_substep_fwd(neuma_ctx* ctx, const neuma_mpm_const* c, int n,
+                          const float* x, const float* v, const float* C, const float* F,
+                          const float* stress,
+                          const float* vol, const float* rho, const float* clip_bound,
+                          const int32_t* enabled,
+                          float* x2, float* v2, float* C2, float* F2, void* stream);
+/* MPMModel.backward, mpm.py:299-319 + MPMSimFunction.backward,
+ * modules/nclaw/sim/interface.py:39-76: recompute p2g + grid_op, then
+ * adj(g2p), adj(grid_op), adj(p2g); NaN/Inf in the results are replaced by 0
+ * (interface.py:65-74).  Any output gradient pointer may be NULL
+ * (the reference returns None for inputs without requires_grad, mpm.py:198-204).
+ * v2 is the v' the forward produced (the reference keeps it in state_next): it
+ * decides which components of x' = clamp(x + dt v') were clamped. */
+int neuma_mpm_substep_bwd(neuma_ctx* ctx, const neuma_mpm_const* c, int n,
+                          const float* x, const float* v, const float* C, const float* F,
+                          const float* stress,
+                          const float* vol, const float* rho, const float* clip_bound,
+                          const int32_t* enabled,
+                          const float* v2 /* the forward's v output */,
+                          const float* gx2, const float* gv2, const float* gC2, const float* gF2,
+                          float* gx, float* gv, float* gC, float* gF, float* gstress,
+                          void* stream);
+
+/* ---- SVD: modules/nclaw/warp/svd.py:59-96 ------------------------------ */
+/* batch_svd incl. the det<0 sign fix; outputs U [n,3,3], sigma [n,3], Vh [n,3,3] */
+int neuma_svd3_fwd(neuma_ctx* ctx, int n, const float* A, float* U, float* sigma, float* Vh,
+                   void* stream);
+/* adjoint of the above given dL/dU, dL/dsigma, dL/dVh (any may be NULL = 0) */
+int neuma_svd3_bwd(neuma_ctx* ctx, int n, const float* U, const float* sigma, const float* Vh,
+                   const float* gU, const float* gsigma, const float* gVh, float* gA,
+                   void* stream);
+
+/* ---- neural constitutive law: modules/nclaw/material/meta.py ----------- */
+/* kind 0: InvariantFullMetaElasticity.forward (meta.py:196-221), out = Kirchhoff
+ *         stress  R sym(MLP(feat)) F^T
+ * kind 1: InvariantFullMetaPlasticity.forward (meta.py:468-489), out = F + alpha R sym(MLP(feat))
+ * W0 [H,13], W1 [H,H], W2 [9,H]: bias-free Linear weights (H = hidden = 64),
+ * with any LoRA adaptor already merged (W + scaling * B A, loralib.py:216-224);
+ * the host wrapper un-merges the weight gradients. */
+int neuma_constitutive_fwd(neuma_ctx* ctx, int kind, int n, int hidden,
+                           const float* F, const float* W0, const float* W1, const float* W2,
+                           float alpha, float* out, void* stream);
+/* gW* are [same shapes], ACCUMULATED into (caller zero-fills); may be NULL to skip
+ * parameter gradients.  gF is overwritten. */
+int neuma_constitutive_bwd(neuma_ctx* ctx, int kind, int n, int hidden,
+                           const float* F, const float* W0, const float* W1, const float* W2,
+                           float alpha, const float* gout,
+                           float* gF, float* gW0, float* gW1, float* gW2, void* stream);
+
+/* ---- particle -> Gaussian binding: modules/tune/utils.py:424-472 ------- */
+/* out[K,ncol] = B in[Np,ncol] (transpose=0) or out[Np,ncol] = B^T in[K,ncol]
+ * (transpose=1, the backward), B in CSR (rowptr[K+1], col[nnz], w[nnz]). */
+int neuma_bind_spmm(neuma_ctx* ctx, int K, int Np, const int32_t* rowptr, const int32_t* col,
+                    const float* w, int ncol, const float* in, float* out, int transpose,
+                    void* stream);
+/* deform_cov_by_F, modules/d3gs/utils/simulation_utils.py:25-48 */
+int neuma_deform_cov(neuma_ctx* ctx, int K, const float* cov6, const float* F, float* out6,
+                     void* stream);
+
+/* ---- Gaussian rasterizer: diff_gaussian_rasterization (external), call site
+ *      modules/tune/utils.py:385-419 ------------------------------------- */
+/* shs [K,M,3] (M >= (deg+1)^2) or colors_precomp [K,3] (exactly one non-NULL);
+ * opacities [K]; cov6 [K,6]; image [3,H,W]; radii int32[K].
+ * Keeps per-call state in the ctx for the matching backward. */
+int neuma_raster_fwd(neuma_ctx* ctx, const neuma_raster_settings* s, int K, int M,
+                     const float* means3D, const float* shs, const float* colors_precomp,
+                     const float* opacities, const float* cov6,
+                     float* image, int32_t* radii, void* stream);
+/* dL/dimage [3,H,W] -> dL/dmeans3D [K,3], dL/dmeans2D [K,3] (z = 0); optional
+ * (may be NULL) dL/dcov6 [K,6], dL/dopacity [K], dL/dcolors or dL/dshs. */
+int neuma_raster_bwd(neuma_ctx* ctx, const neuma_raster_settings* s, int K, int M,
+                     const float* means3D, const float* shs, const float* colors_precomp,
+                     const float* opacities, const float* cov6, const int32_t* radii,
+                     const float* dL_dimage,
+                     float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dcov6,
+                     float* dL_dopacity, float* dL_dcolor_or_sh, void* stream);
+/* introspection for the bit-exact tile/sort parity tests: number of
+ * (tile, gaussian) instances of the last forward, then the sorted 64-bit keys
+ * (tile << 32 | depth bits), Gaussian ids, and per-tile [start,end) ranges.
+ * Synchronises `stream`. */
+int neuma_raster_num_rendered(neuma_ctx* ctx, void* stream, int* out_host);
+int neuma_raster_export_binning(neuma_ctx* ctx, uint64_t* keys, int32_t* gaussian_ids,
+                                int32_t* tile_ranges /* [tiles,2] */, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NEUMA_B200_H */

@@ -1,0 +1,247 @@
+"""Thin torch-tensor front end of the C ABI (include/neuma_b200.h).
+
+Every function here takes CUDA fp32 tensors, hands their device pointers and the
+current torch stream to libneuma_b200.so, and returns torch tensors.  torch is
+used for memory and streams only; there is no torch (or CPU) compute fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from ._lib import Context, MPMConstC, RasterSettingsC, NeumaError, ptr
+
+BC_CODES = {"noslip": 0, "freeslip": 1}
+
+
+def _ctx(t: torch.Tensor) -> Context:
+    if not t.is_cuda:
+        raise NeumaError("neuma_b200 ops need CUDA tensors (sm_100a); there is no CPU fallback")
+    return Context.get(t.device.index if t.device.index is not None else torch.cuda.current_device())
+
+
+def _stream(t: torch.Tensor) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _f32(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        raise NeumaError(f"expected float32, got {t.dtype}")
+    return t.contiguous()
+
+
+def mpm_const(num_grids: int, dt: float, bound: int, gravity: Sequence[float], eps: float, bc: str,
+              z_off: int = 0, nz: Optional[int] = None) -> MPMConstC:
+    """MPMConstant (mpm.py:158-167, dx/inv_dx as mpm.py:516-517)."""
+    if bc not in BC_CODES:
+        raise ValueError("invalid boundary condition: {}".format(bc))  # mpm.py:550
+    c = MPMConstC()
+    c.num_grids = int(num_grids)
+    c.dt = float(dt)
+    c.bound = int(bound)
+    c.gravity[0], c.gravity[1], c.gravity[2] = [float(g) for g in gravity]
+    c.dx = 1 / num_grids
+    c.inv_dx = float(num_grids)
+    c.eps = float(eps)
+    c.bc = BC_CODES[bc]
+    c.z_off = int(z_off)
+    c.nz = int(num_grids if nz is None else nz)
+    return c
+
+
+# --------------------------------------------------------------------- MPM
+def mpm_grid_clear(c: MPMConstC, like: torch.Tensor) -> None:
+    _ctx(like).call("neuma_mpm_grid_clear", C.byref(c), _stream(like))
+
+
+def mpm_p2g(c: MPMConstC, x, v, Cm, stress, vol, rho, enabled) -> None:
+    x, v, Cm, stress, vol, rho = map(_f32, (x, v, Cm, stress, vol, rho))
+    _ctx(x).call("neuma_mpm_p2g", C.byref(c), x.shape[0], ptr(x), ptr(v), ptr(Cm), ptr(stress),
+                 ptr(vol), ptr(rho), ptr(enabled), _stream(x))
+
+
+def mpm_grid_op(c: MPMConstC, like: torch.Tensor) -> None:
+    _ctx(like).call("neuma_mpm_grid_op", C.byref(c), _stream(like))
+
+
+def mpm_g2p(c: MPMConstC, x, F, clip_bound, enabled, out=None, lazy_grid_op: bool = True):
+    x, F, clip_bound = map(_f32, (x, F, clip_bound))
+    n = x.shape[0]
+    if out is None:
+        out = (torch.empty_like(x), torch.empty_like(x), torch.empty_like(F), torch.empty_like(F))
+    x2, v2, C2, F2 = out
+    _ctx(x).call("neuma_mpm_g2p", C.byref(c), n, ptr(x), ptr(F), ptr(clip_bound), ptr(enabled),
+                 ptr(x2), ptr(v2), ptr(C2), ptr(F2), int(lazy_grid_op), _stream(x))
+    return x2, v2, C2, F2
+
+
+def mpm_grid_export(c: MPMConstC, like: torch.Tensor, want_v: bool = False):
+    G, nz = c.num_grids, c.nz
+    mv = torch.empty(G, G, nz, 3, device=like.device, dtype=torch.float32)
+    m = torch.empty(G, G, nz, device=like.device, dtype=torch.float32)
+    v = torch.empty(G, G, nz, 3, device=like.device, dtype=torch.float32) if want_v else None
+    _ctx(like).call("neuma_mpm_grid_export", C.byref(c), ptr(mv), ptr(m), ptr(v), _stream(like))
+    return mv, m, v
+
+
+def mpm_halo_pack(c: MPMConstC, z: int, nplanes: int, buf: torch.Tensor) -> None:
+    _ctx(buf).call("neuma_mpm_halo_pack", C.byref(c), int(z), int(nplanes), ptr(buf), _stream(buf))
+
+
+def mpm_halo_unpack_add(c: MPMConstC, z: int, nplanes: int, buf: torch.Tensor) -> None:
+    _ctx(buf).call("neuma_mpm_halo_unpack_add", C.byref(c), int(z), int(nplanes), ptr(buf), _stream(buf))
+
+
+def mpm_substep_fwd(c: MPMConstC, x, v, Cm, F, stress, vol, rho, clip_bound, enabled, out=None):
+    x, v, Cm, F, stress, vol, rho, clip_bound = map(_f32, (x, v, Cm, F, stress, vol, rho, clip_bound))
+    if out is None:
+        out = (torch.empty_like(x), torch.empty_like(v), torch.empty_like(Cm), torch.empty_like(F))
+    x2, v2, C2, F2 = out
+    _ctx(x).call("neuma_mpm_substep_fwd", C.byref(c), x.shape[0], ptr(x), ptr(v), ptr(Cm), ptr(F),
+                 ptr(stress), ptr(vol), ptr(rho), ptr(clip_bound), ptr(enabled),
+                 ptr(x2), ptr(v2), ptr(C2), ptr(F2), _stream(x))
+    return x2, v2, C2, F2
+
+
+def mpm_substep_bwd(c: MPMConstC, x, v, Cm, F, stress, vol, rho, clip_bound, enabled, v2,
+                    gx2, gv2, gC2, gF2, need: Sequence[bool] = (True,) * 5):
+    x, v, Cm, F, stress, vol, rho, clip_bound, v2 = map(
+        _f32, (x, v, Cm, F, stress, vol, rho, clip_bound, v2))
+    gx2, gv2, gC2, gF2 = map(_f32, (gx2, gv2, gC2, gF2))
+    outs = [torch.empty_like(t) if nd else None for t, nd in zip((x, v, Cm, F, stress), need)]
+    _ctx(x).call("neuma_mpm_substep_bwd", C.byref(c), x.shape[0], ptr(x), ptr(v), ptr(Cm), ptr(F),
+                 ptr(stress), ptr(vol), ptr(rho), ptr(clip_bound), ptr(enabled), ptr(v2),
+                 ptr(gx2), ptr(gv2), ptr(gC2), ptr(gF2), *[ptr(o) for o in outs], _stream(x))
+    return tuple(outs)
+
+
+# --------------------------------------------------------------------- SVD / constitutive
+def svd3_fwd(A: torch.Tensor):
+    A = _f32(A)
+    n = A.shape[0]
+    U = torch.empty_like(A)
+    s = torch.empty(n, 3, device=A.device, dtype=torch.float32)
+    Vh = torch.empty_like(A)
+    _ctx(A).call("neuma_svd3_fwd", n, ptr(A), ptr(U), ptr(s), ptr(Vh), _stream(A))
+    return U, s, Vh
+
+
+def svd3_bwd(U, s, Vh, gU, gs, gVh):
+    U, s, Vh = map(_f32, (U, s, Vh))
+    gU, gs, gVh = [None if g is None else _f32(g) for g in (gU, gs, gVh)]
+    gA = torch.empty_like(U)
+    _ctx(U).call("neuma_svd3_bwd", U.shape[0], ptr(U), ptr(s), ptr(Vh), ptr(gU), ptr(gs), ptr(gVh),
+                 ptr(gA), _stream(U))
+    return gA
+
+
+KIND_ELASTIC, KIND_PLASTIC, KIND_ELASTIC_RAW = 0, 1, 2
+
+
+def constitutive_fwd(kind: int, F, W0, W1, W2, alpha: float = 0.0):
+    F, W0, W1, W2 = map(_f32, (F, W0, W1, W2))
+    out = torch.empty_like(F)
+    _ctx(F).call("neuma_constitutive_fwd", int(kind), F.shape[0], W1.shape[0], ptr(F), ptr(W0),
+                 ptr(W1), ptr(W2), C.c_float(alpha), ptr(out), _stream(F))
+    return out
+
+
+def constitutive_bwd(kind: int, F, W0, W1, W2, alpha: float, gout, want_wgrad: bool = True):
+    F, W0, W1, W2, gout = map(_f32, (F, W0, W1, W2, gout))
+    gF = torch.empty_like(F)
+    gW = [torch.zeros_like(w) for w in (W0, W1, W2)] if want_wgrad else [None, None, None]
+    _ctx(F).call("neuma_constitutive_bwd", int(kind), F.shape[0], W1.shape[0], ptr(F), ptr(W0),
+                 ptr(W1), ptr(W2), C.c_float(alpha), ptr(gout), ptr(gF), ptr(gW[0]), ptr(gW[1]),
+                 ptr(gW[2]), _stream(F))
+    return gF, gW[0], gW[1], gW[2]
+
+
+# --------------------------------------------------------------------- bindings
+def bind_spmm(rowptr, col, w, dense: torch.Tensor, n_particles: int, transpose: bool = False):
+    dense = _f32(dense)
+    K = rowptr.shape[0] - 1
+    ncol = dense.shape[1]
+    rows = n_particles if transpose else K
+    out = torch.empty(rows, ncol, device=dense.device, dtype=torch.float32)
+    _ctx(dense).call("neuma_bind_spmm", K, int(n_particles), ptr(rowptr), ptr(col), ptr(w), ncol,
+                     ptr(dense), ptr(out), int(transpose), _stream(dense))
+    return out
+
+
+def deform_cov(cov6: torch.Tensor, F: torch.Tensor):
+    cov6, F = _f32(cov6), _f32(F)
+    out = torch.empty_like(cov6)
+    _ctx(cov6).call("neuma_deform_cov", cov6.shape[0], ptr(cov6), ptr(F), ptr(out), _stream(cov6))
+    return out
+
+
+# --------------------------------------------------------------------- rasterizer
+def raster_settings(image_height, image_width, tanfovx, tanfovy, bg, scale_modifier, viewmatrix,
+                    projmatrix, sh_degree, campos, prefiltered=False, debug=False) -> RasterSettingsC:
+    s = RasterSettingsC()
+    s.image_height, s.image_width = int(image_height), int(image_width)
+    s.tanfovx, s.tanfovy = float(tanfovx), float(tanfovy)
+    bgl = [float(b) for b in (bg.detach().cpu().tolist() if torch.is_tensor(bg) else bg)]
+    s.bg[0], s.bg[1], s.bg[2] = bgl
+    s.scale_modifier = float(scale_modifier)
+    vm = viewmatrix.detach().cpu().reshape(-1).tolist() if torch.is_tensor(viewmatrix) else list(viewmatrix)
+    pm = projmatrix.detach().cpu().reshape(-1).tolist() if torch.is_tensor(projmatrix) else list(projmatrix)
+    for i in range(16):
+        s.viewmatrix[i] = float(vm[i])
+        s.projmatrix[i] = float(pm[i])
+    s.sh_degree = int(sh_degree)
+    cp = campos.detach().cpu().tolist() if torch.is_tensor(campos) else list(campos)
+    s.campos[0], s.campos[1], s.campos[2] = [float(v) for v in cp]
+    s.prefiltered, s.debug = int(bool(prefiltered)), int(bool(debug))
+    return s
+
+
+def raster_fwd(s: RasterSettingsC, means3D, shs, colors_precomp, opacities, cov6):
+    means3D, opacities, cov6 = map(_f32, (means3D, opacities, cov6))
+    shs = None if shs is None else _f32(shs)
+    colors_precomp = None if colors_precomp is None else _f32(colors_precomp)
+    K = means3D.shape[0]
+    M = 0 if shs is None else shs.shape[1]
+    image = torch.empty(3, s.image_height, s.image_width, device=means3D.device, dtype=torch.float32)
+    radii = torch.empty(K, device=means3D.device, dtype=torch.int32)
+    _ctx(means3D).call("neuma_raster_fwd", C.byref(s), K, M, ptr(means3D), ptr(shs),
+                       ptr(colors_precomp), ptr(opacities), ptr(cov6), ptr(image), ptr(radii),
+                       _stream(means3D))
+    return image, radii
+
+
+def raster_bwd(s: RasterSettingsC, means3D, shs, colors_precomp, opacities, cov6, radii, dL_dimage,
+               want_cov=False, want_opacity=False, want_color=False):
+    means3D, opacities, cov6, dL_dimage = map(_f32, (means3D, opacities, cov6, dL_dimage))
+    shs = None if shs is None else _f32(shs)
+    colors_precomp = None if colors_precomp is None else _f32(colors_precomp)
+    K = means3D.shape[0]
+    M = 0 if shs is None else shs.shape[1]
+    dev = means3D.device
+    g3 = torch.empty(K, 3, device=dev, dtype=torch.float32)
+    g2 = torch.empty(K, 3, device=dev, dtype=torch.float32)
+    gcov = torch.empty(K, 6, device=dev, dtype=torch.float32) if want_cov else None
+    gop = torch.empty_like(opacities) if want_opacity else None
+    gcol = None
+    if want_color:
+        gcol = torch.empty_like(shs if shs is not None else colors_precomp)
+    _ctx(means3D).call("neuma_raster_bwd", C.byref(s), K, M, ptr(means3D), ptr(shs),
+                       ptr(colors_precomp), ptr(opacities), ptr(cov6), ptr(radii), ptr(dL_dimage),
+                       ptr(g3), ptr(g2), ptr(gcov), ptr(gop), ptr(gcol), _stream(means3D))
+    return g3, g2, gcov, gop, gcol
+
+
+def raster_binning(like: torch.Tensor, tiles: int):
+    """Sorted instance keys / Gaussian ids / tile ranges of the last forward."""
+    ctx = _ctx(like)
+    n = C.c_int(0)
+    ctx.call("neuma_raster_num_rendered", _stream(like), C.byref(n))
+    L = n.value
+    keys = torch.empty(L, device=like.device, dtype=torch.int64)
+    ids = torch.empty(L, device=like.device, dtype=torch.int32)
+    ranges = torch.empty(tiles, 2, device=like.device, dtype=torch.int32)
+    ctx.call("neuma_raster_export_binning", ptr(keys), ptr(ids), ptr(ranges), _stream(like))
+    return keys, ids, ranges

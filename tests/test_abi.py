@@ -1,0 +1,50 @@
+"""The C-ABI library builds, loads, and exports every symbol include/neuma_b200.h declares."""
+import ctypes
+import os
+import re
+
+from neuma_b200 import build, _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "neuma_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(neuma_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_exported():
+    build.build()
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    names = _declared()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in neuma_b200.h but not exported"
+
+
+def test_bindings_cover_header():
+    assert sorted(_lib.SIGNATURES) == _declared()
+
+
+def test_load_and_version():
+    lib = _lib.load()
+    assert lib.neuma_version() >= 100
+
+
+def test_no_gpu_is_loud():
+    import torch
+    import pytest
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(_lib.NeumaError):
+        _lib.Context(0)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "neuma_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh")):
+                src = open(os.path.join(dp, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
