@@ -29,16 +29,37 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+EXTRA_FLAGS = {"raster_pre.cu": ["-fmad=false"]}
+
+
+def _compile_one(args):
+    nvcc, src, obj, verbose = args
+    flags = [f for f in NVCC_FLAGS if f != "-shared"] + EXTRA_FLAGS.get(os.path.basename(src), [])
+    cmd = [nvcc] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    return src, r.returncode, r.stdout + r.stderr
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile every csrc/*.cu for sm_100a (one nvcc per file, in parallel) and link."""
     if not force and not needs_build():
         return OUT
+    from concurrent.futures import ThreadPoolExecutor
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + sources()
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    jobs = [(nvcc, s, os.path.join(objdir, os.path.basename(s)[:-3] + ".o"), verbose) for s in sources()]
+    with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
+        results = list(ex.map(_compile_one, jobs))
+    for src, rc, log in results:
+        if verbose:
+            print(log)
+        if rc != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n{log}")
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT] + [j[2] for j in jobs]
     r = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose:
-        print(r.stderr)
     if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+        raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
     return OUT
 
 

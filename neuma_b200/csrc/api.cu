@@ -6,8 +6,6 @@ void neuma_raster_state_free(RasterState* s);  // raster.cu
 
 int neuma_ensure_grid(neuma_ctx* ctx, size_t nodes) {
   if (nodes <= ctx->grid_nodes) return 0;
-  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-  (void)cs;
   if (ctx->grid_mvm) cudaFree(ctx->grid_mvm);
   if (ctx->grid_v) cudaFree(ctx->grid_v);
   if (ctx->grid_adj) cudaFree(ctx->grid_adj);

@@ -17,42 +17,8 @@
 // backward reduces the per-Gaussian gradient contributions of a warp's 32 pixels
 // with shuffles before one atomic per warp (instead of 32), and the per-Gaussian
 // records are read as 128-bit vectors.
-#include "common.cuh"
+#include "raster_common.cuh"
 #include <cub/cub.cuh>
-
-namespace {
-constexpr int BX = 16, BY = 16, BLOCK = BX * BY;
-}
-
-struct RasterState {
-  // per Gaussian
-  int capK = 0;
-  float* depths = nullptr;
-  float2* xy = nullptr;
-  float4* conic_o = nullptr;
-  float* rgb = nullptr;
-  unsigned char* clamped = nullptr;
-  uint32_t* tiles_touched = nullptr;
-  uint32_t* offsets = nullptr;
-  float4* dconic = nullptr;  // backward: dL/d(A,B,C) of the conic, .w = dL/dopacity
-  float* dcolor = nullptr;   // backward: dL/drgb [K,3]
-  // per instance
-  size_t capD = 0;
-  uint64_t *keys_a = nullptr, *keys_b = nullptr;
-  uint32_t *vals_a = nullptr, *vals_b = nullptr;
-  // per tile / pixel
-  int capT = 0;
-  uint2* ranges = nullptr;
-  int capPix = 0;
-  float* final_T = nullptr;
-  uint32_t* n_contrib = nullptr;
-  // cub temp
-  void* temp = nullptr;
-  size_t temp_bytes = 0;
-  // last forward
-  int num_rendered = 0, K = 0, tiles_x = 0, tiles_y = 0, W = 0, Himg = 0;
-  int* num_rendered_pinned = nullptr;
-};
 
 void neuma_raster_state_free(RasterState* s) {
   if (!s) return;
@@ -66,220 +32,6 @@ void neuma_raster_state_free(RasterState* s) {
 }
 
 namespace {
-
-struct Cam {
-  float view[16], proj[16];
-  float cam[3], bg[3];
-  float tanx, tany, fx, fy;
-  int W, H, tiles_x, tiles_y, deg;
-};
-
-Cam make_cam(const neuma_raster_settings* s) {
-  Cam c;
-  memcpy(c.view, s->viewmatrix, sizeof(c.view));
-  memcpy(c.proj, s->projmatrix, sizeof(c.proj));
-  memcpy(c.cam, s->campos, sizeof(c.cam));
-  memcpy(c.bg, s->bg, sizeof(c.bg));
-  c.tanx = s->tanfovx; c.tany = s->tanfovy;
-  c.W = s->image_width; c.H = s->image_height;
-  c.fx = c.W / (2.0f * c.tanx);
-  c.fy = c.H / (2.0f * c.tany);
-  c.tiles_x = (c.W + BX - 1) / BX;
-  c.tiles_y = (c.H + BY - 1) / BY;
-  c.deg = s->sh_degree;
-  return c;
-}
-
-__device__ __forceinline__ void xform43(const float* m, const float p[3], float o[3]) {
-  o[0] = m[0] * p[0] + m[4] * p[1] + m[8] * p[2] + m[12];
-  o[1] = m[1] * p[0] + m[5] * p[1] + m[9] * p[2] + m[13];
-  o[2] = m[2] * p[0] + m[6] * p[1] + m[10] * p[2] + m[14];
-}
-__device__ __forceinline__ void xform44(const float* m, const float p[3], float o[4]) {
-  o[0] = m[0] * p[0] + m[4] * p[1] + m[8] * p[2] + m[12];
-  o[1] = m[1] * p[0] + m[5] * p[1] + m[9] * p[2] + m[13];
-  o[2] = m[2] * p[0] + m[6] * p[1] + m[10] * p[2] + m[14];
-  o[3] = m[3] * p[0] + m[7] * p[1] + m[11] * p[2] + m[15];
-}
-__device__ __forceinline__ float ndc2pix(float v, int S) { return ((v + 1.0f) * S - 1.0f) * 0.5f; }
-
-// real SH basis (degree <= 3) and its gradient wrt the unit direction
-#define SH_C0 0.28209479177387814f
-#define SH_C1 0.4886025119029199f
-__device__ __forceinline__ void sh_basis(int deg, float x, float y, float z, float b[16],
-                                         float gx[16], float gy[16], float gz[16]) {
-  const float C2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
-                       -1.0925484305920792f, 0.5462742152960396f};
-  const float C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f,
-                       0.3731763325901154f, -0.4570457994644658f, 1.445305721320277f,
-                       -0.5900435899266435f};
-#pragma unroll
-  for (int i = 0; i < 16; ++i) { b[i] = 0.f; gx[i] = 0.f; gy[i] = 0.f; gz[i] = 0.f; }
-  b[0] = SH_C0;
-  if (deg > 0) {
-    b[1] = -SH_C1 * y; gy[1] = -SH_C1;
-    b[2] = SH_C1 * z;  gz[2] = SH_C1;
-    b[3] = -SH_C1 * x; gx[3] = -SH_C1;
-    if (deg > 1) {
-      const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-      b[4] = C2[0] * xy; gx[4] = C2[0] * y; gy[4] = C2[0] * x;
-      b[5] = C2[1] * yz; gy[5] = C2[1] * z; gz[5] = C2[1] * y;
-      b[6] = C2[2] * (2.0f * zz - xx - yy);
-      gx[6] = C2[2] * -2.0f * x; gy[6] = C2[2] * -2.0f * y; gz[6] = C2[2] * 4.0f * z;
-      b[7] = C2[3] * xz; gx[7] = C2[3] * z; gz[7] = C2[3] * x;
-      b[8] = C2[4] * (xx - yy); gx[8] = C2[4] * 2.0f * x; gy[8] = C2[4] * -2.0f * y;
-      if (deg > 2) {
-        b[9] = C3[0] * y * (3.0f * xx - yy);
-        gx[9] = C3[0] * 6.0f * xy; gy[9] = C3[0] * (3.0f * xx - 3.0f * yy);
-        b[10] = C3[1] * xy * z;
-        gx[10] = C3[1] * yz; gy[10] = C3[1] * xz; gz[10] = C3[1] * xy;
-        b[11] = C3[2] * y * (4.0f * zz - xx - yy);
-        gx[11] = C3[2] * -2.0f * xy; gy[11] = C3[2] * (4.0f * zz - xx - 3.0f * yy);
-        gz[11] = C3[2] * 8.0f * yz;
-        b[12] = C3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy);
-        gx[12] = C3[3] * -6.0f * xz; gy[12] = C3[3] * -6.0f * yz;
-        gz[12] = C3[3] * (6.0f * zz - 3.0f * xx - 3.0f * yy);
-        b[13] = C3[4] * x * (4.0f * zz - xx - yy);
-        gx[13] = C3[4] * (4.0f * zz - 3.0f * xx - yy); gy[13] = C3[4] * -2.0f * xy;
-        gz[13] = C3[4] * 8.0f * xz;
-        b[14] = C3[5] * z * (xx - yy);
-        gx[14] = C3[5] * 2.0f * xz; gy[14] = C3[5] * -2.0f * yz; gz[14] = C3[5] * (xx - yy);
-        b[15] = C3[6] * x * (xx - 3.0f * yy);
-        gx[15] = C3[6] * (3.0f * xx - 3.0f * yy); gy[15] = C3[6] * -6.0f * xy;
-      }
-    }
-  }
-}
-
-// EWA projection of a packed-6 covariance; returns cov2D (a, b, c) incl. the 0.3
-// low-pass, plus the intermediates the backward needs.
-struct Cov2D {
-  float a, b, c;
-  float T[2][3];   // T = J W  (rows 0,1; row 2 of J is zero)
-  float t[3];      // clamped view-space mean
-  float xmul, ymul;
-};
-__device__ __forceinline__ Cov2D cov2d(const Cam& cam, const float p[3], const float* cv) {
-  Cov2D r;
-  float t[3];
-  xform43(cam.view, p, t);
-  const float limx = 1.3f * cam.tanx, limy = 1.3f * cam.tany;
-  const float txtz = t[0] / t[2], tytz = t[1] / t[2];
-  r.xmul = (txtz < -limx || txtz > limx) ? 0.f : 1.f;
-  r.ymul = (tytz < -limy || tytz > limy) ? 0.f : 1.f;
-  t[0] = fminf(limx, fmaxf(-limx, txtz)) * t[2];
-  t[1] = fminf(limy, fmaxf(-limy, tytz)) * t[2];
-  r.t[0] = t[0]; r.t[1] = t[1]; r.t[2] = t[2];
-  const float J00 = cam.fx / t[2], J02 = -(cam.fx * t[0]) / (t[2] * t[2]);
-  const float J11 = cam.fy / t[2], J12 = -(cam.fy * t[1]) / (t[2] * t[2]);
-  // Wr[i][j]: view = Wr p + trans ; Wr[i][j] = view[4*j + i]
-#pragma unroll
-  for (int j = 0; j < 3; ++j) {
-    r.T[0][j] = J00 * cam.view[4 * j + 0] + J02 * cam.view[4 * j + 2];
-    r.T[1][j] = J11 * cam.view[4 * j + 1] + J12 * cam.view[4 * j + 2];
-  }
-  const float S[3][3] = {{cv[0], cv[1], cv[2]}, {cv[1], cv[3], cv[4]}, {cv[2], cv[4], cv[5]}};
-  float TS[2][3];
-#pragma unroll
-  for (int i = 0; i < 2; ++i)
-#pragma unroll
-    for (int j = 0; j < 3; ++j)
-      TS[i][j] = r.T[i][0] * S[0][j] + r.T[i][1] * S[1][j] + r.T[i][2] * S[2][j];
-  r.a = TS[0][0] * r.T[0][0] + TS[0][1] * r.T[0][1] + TS[0][2] * r.T[0][2] + 0.3f;
-  r.b = TS[0][0] * r.T[1][0] + TS[0][1] * r.T[1][1] + TS[0][2] * r.T[1][2];
-  r.c = TS[1][0] * r.T[1][0] + TS[1][1] * r.T[1][1] + TS[1][2] * r.T[1][2] + 0.3f;
-  return r;
-}
-
-__device__ __forceinline__ void tile_rect(const Cam& cam, float px, float py, int radius,
-                                          int& x0, int& y0, int& x1, int& y1) {
-  x0 = min(cam.tiles_x, max(0, (int)((px - radius) / BX)));
-  y0 = min(cam.tiles_y, max(0, (int)((py - radius) / BY)));
-  x1 = min(cam.tiles_x, max(0, (int)((px + radius + BX - 1) / BX)));
-  y1 = min(cam.tiles_y, max(0, (int)((py + radius + BY - 1) / BY)));
-}
-
-// ---------------------------------------------------------------- preprocess
-__global__ void __launch_bounds__(256)
-preprocess_kernel(Cam cam, int K, int M, const float* __restrict__ means,
-                  const float* __restrict__ shs, const float* __restrict__ colors_precomp,
-                  const float* __restrict__ opac, const float* __restrict__ cov6,
-                  int* __restrict__ radii, float* __restrict__ depths, float2* __restrict__ xy,
-                  float4* __restrict__ conic_o, float* __restrict__ rgb,
-                  unsigned char* __restrict__ clamped, uint32_t* __restrict__ tiles_touched) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= K) return;
-  radii[i] = 0;
-  tiles_touched[i] = 0;
-  const float p[3] = {means[3 * i], means[3 * i + 1], means[3 * i + 2]};
-  float pv[3];
-  xform43(cam.view, p, pv);
-  if (pv[2] <= 0.2f) return;  // near-plane cull
-  float ph[4];
-  xform44(cam.proj, p, ph);
-  const float pw = 1.0f / (ph[3] + 0.0000001f);
-  const float pp[2] = {ph[0] * pw, ph[1] * pw};
-  const Cov2D cv = cov2d(cam, p, cov6 + (size_t)i * 6);
-  const float det = cv.a * cv.c - cv.b * cv.b;
-  if (det == 0.0f) return;
-  const float di = 1.0f / det;
-  const float mid = 0.5f * (cv.a + cv.c);
-  const float l1 = mid + sqrtf(fmaxf(0.1f, mid * mid - det));
-  const float l2 = mid - sqrtf(fmaxf(0.1f, mid * mid - det));
-  const int radius = (int)ceilf(3.0f * sqrtf(fmaxf(l1, l2)));
-  const float px = ndc2pix(pp[0], cam.W), py = ndc2pix(pp[1], cam.H);
-  int x0, y0, x1, y1;
-  tile_rect(cam, px, py, radius, x0, y0, x1, y1);
-  if ((x1 - x0) * (y1 - y0) == 0) return;
-  if (colors_precomp) {
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      rgb[3 * i + c] = colors_precomp[3 * i + c];
-      clamped[3 * i + c] = 0;
-    }
-  } else {
-    float d[3] = {p[0] - cam.cam[0], p[1] - cam.cam[1], p[2] - cam.cam[2]};
-    const float il = 1.0f / sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
-    d[0] *= il; d[1] *= il; d[2] *= il;
-    float b[16], gx[16], gy[16], gz[16];
-    sh_basis(cam.deg, d[0], d[1], d[2], b, gx, gy, gz);
-    const int nb = (cam.deg + 1) * (cam.deg + 1);
-    const float* sh = shs + (size_t)i * M * 3;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      float r = 0.f;
-      for (int k = 0; k < nb; ++k) r += b[k] * sh[3 * k + c];
-      r += 0.5f;
-      clamped[3 * i + c] = r < 0.f;
-      rgb[3 * i + c] = fmaxf(r, 0.f);
-    }
-  }
-  depths[i] = pv[2];
-  radii[i] = radius;
-  xy[i] = make_float2(px, py);
-  conic_o[i] = make_float4(cv.c * di, -cv.b * di, cv.a * di, opac[i]);
-  tiles_touched[i] = (uint32_t)((x1 - x0) * (y1 - y0));
-}
-
-__global__ void __launch_bounds__(256)
-duplicate_kernel(Cam cam, int K, const float2* __restrict__ xy, const float* __restrict__ depths,
-                 const uint32_t* __restrict__ offsets, const int* __restrict__ radii,
-                 uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= K) return;
-  if (radii[i] <= 0) return;
-  uint32_t off = (i == 0) ? 0 : offsets[i - 1];
-  int x0, y0, x1, y1;
-  tile_rect(cam, xy[i].x, xy[i].y, radii[i], x0, y0, x1, y1);
-  const uint32_t dbits = __float_as_uint(depths[i]);
-  for (int y = y0; y < y1; ++y)
-    for (int x = x0; x < x1; ++x) {
-      const uint64_t key = ((uint64_t)(y * cam.tiles_x + x) << 32) | dbits;
-      keys[off] = key;
-      vals[off] = (uint32_t)i;
-      ++off;
-    }
-}
 
 __global__ void __launch_bounds__(256)
 tile_ranges_kernel(int L, const uint64_t* __restrict__ keys, uint2* __restrict__ ranges) {
@@ -297,6 +49,7 @@ tile_ranges_kernel(int L, const uint64_t* __restrict__ keys, uint2* __restrict__
   }
   if (i == L - 1) ranges[t].y = L;
 }
+
 
 // ---------------------------------------------------------------- render fwd
 __global__ void __launch_bounds__(BLOCK)
@@ -689,10 +442,7 @@ int neuma_raster_fwd(neuma_ctx* ctx, const neuma_raster_settings* set, int K, in
   s->num_rendered = 0;
   NEUMA_CUDA(ctx, cudaMemsetAsync(s->ranges, 0, (size_t)tiles * sizeof(uint2), st));
   if (K > 0) {
-    preprocess_kernel<<<(K + 255) / 256, 256, 0, st>>>(cam, K, M, means3D, shs, colors_precomp,
-                                                       opacities, cov6, radii, s->depths, s->xy,
-                                                       s->conic_o, s->rgb, s->clamped,
-                                                       s->tiles_touched);
+    neuma_launch_preprocess(cam, K, M, means3D, shs, colors_precomp, opacities, cov6, radii, s, st);
     NEUMA_LAUNCH_CHECK(ctx, "preprocess_kernel");
     size_t tb = 0;
     cub::DeviceScan::InclusiveSum(nullptr, tb, s->tiles_touched, s->offsets, K, st);
@@ -715,8 +465,7 @@ int neuma_raster_fwd(neuma_ctx* ctx, const neuma_raster_settings* set, int K, in
         return 1;
       s->capD = cap;
     }
-    duplicate_kernel<<<(K + 255) / 256, 256, 0, st>>>(cam, K, s->xy, s->depths, s->offsets, radii,
-                                                      s->keys_a, s->vals_a);
+    neuma_launch_duplicate(cam, K, radii, s, st);
     NEUMA_LAUNCH_CHECK(ctx, "duplicate_kernel");
     int tile_bits = 0;
     while ((1 << tile_bits) < tiles) ++tile_bits;

@@ -1,0 +1,105 @@
+// Per-Gaussian preprocess + instance duplication of the rasterizer forward.
+// Compiled with -fmad=false: every fp32 operation below rounds separately, in the
+// order written, exactly like oracle/raster_oracle.py::bin_np (numpy fp32), so the
+// depth bits, radii, tile rectangles -- and hence the sorted (tile << 32 | depth)
+// instance keys -- are bit-exact against the oracle.
+#include "raster_common.cuh"
+
+namespace {
+
+// ---------------------------------------------------------------- preprocess
+__global__ void __launch_bounds__(256)
+preprocess_kernel(Cam cam, int K, int M, const float* __restrict__ means,
+                  const float* __restrict__ shs, const float* __restrict__ colors_precomp,
+                  const float* __restrict__ opac, const float* __restrict__ cov6,
+                  int* __restrict__ radii, float* __restrict__ depths, float2* __restrict__ xy,
+                  float4* __restrict__ conic_o, float* __restrict__ rgb,
+                  unsigned char* __restrict__ clamped, uint32_t* __restrict__ tiles_touched) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= K) return;
+  radii[i] = 0;
+  tiles_touched[i] = 0;
+  const float p[3] = {means[3 * i], means[3 * i + 1], means[3 * i + 2]};
+  float pv[3];
+  xform43(cam.view, p, pv);
+  if (pv[2] <= 0.2f) return;  // near-plane cull
+  float ph[4];
+  xform44(cam.proj, p, ph);
+  const float pw = 1.0f / (ph[3] + 0.0000001f);
+  const float pp[2] = {ph[0] * pw, ph[1] * pw};
+  const Cov2D cv = cov2d(cam, p, cov6 + (size_t)i * 6);
+  const float det = cv.a * cv.c - cv.b * cv.b;
+  if (det == 0.0f) return;
+  const float di = 1.0f / det;
+  const float mid = 0.5f * (cv.a + cv.c);
+  const float l1 = mid + sqrtf(fmaxf(0.1f, mid * mid - det));
+  const float l2 = mid - sqrtf(fmaxf(0.1f, mid * mid - det));
+  const int radius = (int)ceilf(3.0f * sqrtf(fmaxf(l1, l2)));
+  const float px = ndc2pix(pp[0], cam.W), py = ndc2pix(pp[1], cam.H);
+  int x0, y0, x1, y1;
+  tile_rect(cam, px, py, radius, x0, y0, x1, y1);
+  if ((x1 - x0) * (y1 - y0) == 0) return;
+  if (colors_precomp) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      rgb[3 * i + c] = colors_precomp[3 * i + c];
+      clamped[3 * i + c] = 0;
+    }
+  } else {
+    float d[3] = {p[0] - cam.cam[0], p[1] - cam.cam[1], p[2] - cam.cam[2]};
+    const float il = 1.0f / sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+    d[0] *= il; d[1] *= il; d[2] *= il;
+    float b[16], gx[16], gy[16], gz[16];
+    sh_basis(cam.deg, d[0], d[1], d[2], b, gx, gy, gz);
+    const int nb = (cam.deg + 1) * (cam.deg + 1);
+    const float* sh = shs + (size_t)i * M * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float r = 0.f;
+      for (int k = 0; k < nb; ++k) r += b[k] * sh[3 * k + c];
+      r += 0.5f;
+      clamped[3 * i + c] = r < 0.f;
+      rgb[3 * i + c] = fmaxf(r, 0.f);
+    }
+  }
+  depths[i] = pv[2];
+  radii[i] = radius;
+  xy[i] = make_float2(px, py);
+  conic_o[i] = make_float4(cv.c * di, -cv.b * di, cv.a * di, opac[i]);
+  tiles_touched[i] = (uint32_t)((x1 - x0) * (y1 - y0));
+}
+
+__global__ void __launch_bounds__(256)
+duplicate_kernel(Cam cam, int K, const float2* __restrict__ xy, const float* __restrict__ depths,
+                 const uint32_t* __restrict__ offsets, const int* __restrict__ radii,
+                 uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= K) return;
+  if (radii[i] <= 0) return;
+  uint32_t off = (i == 0) ? 0 : offsets[i - 1];
+  int x0, y0, x1, y1;
+  tile_rect(cam, xy[i].x, xy[i].y, radii[i], x0, y0, x1, y1);
+  const uint32_t dbits = __float_as_uint(depths[i]);
+  for (int y = y0; y < y1; ++y)
+    for (int x = x0; x < x1; ++x) {
+      const uint64_t key = ((uint64_t)(y * cam.tiles_x + x) << 32) | dbits;
+      keys[off] = key;
+      vals[off] = (uint32_t)i;
+      ++off;
+    }
+}
+
+}  // namespace
+
+void neuma_launch_preprocess(const Cam& cam, int K, int M, const float* means, const float* shs,
+                             const float* colors_precomp, const float* opac, const float* cov6,
+                             int* radii, RasterState* s, cudaStream_t st) {
+  preprocess_kernel<<<(K + 255) / 256, 256, 0, st>>>(cam, K, M, means, shs, colors_precomp, opac,
+                                                     cov6, radii, s->depths, s->xy, s->conic_o,
+                                                     s->rgb, s->clamped, s->tiles_touched);
+}
+
+void neuma_launch_duplicate(const Cam& cam, int K, const int* radii, RasterState* s, cudaStream_t st) {
+  duplicate_kernel<<<(K + 255) / 256, 256, 0, st>>>(cam, K, s->xy, s->depths, s->offsets, radii,
+                                                    s->keys_a, s->vals_a);
+}
