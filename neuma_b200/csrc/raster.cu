@@ -429,9 +429,9 @@ int neuma_raster_fwd(neuma_ctx* ctx, const neuma_raster_settings* set, int K, in
                      const float* opacities, const float* cov6, float* image, int32_t* radii,
                      void* stream) {
   if (int r = check_settings(ctx, set, K, M)) return r;
-  if ((shs == nullptr) == (colors_precomp == nullptr))
+  if (K > 0 && (shs == nullptr) == (colors_precomp == nullptr))
     return neuma_fail_msg(ctx, "raster: provide exactly one of shs / colors_precomp");
-  if (shs && M < (set->sh_degree + 1) * (set->sh_degree + 1))
+  if (K > 0 && shs && M < (set->sh_degree + 1) * (set->sh_degree + 1))
     return neuma_fail_msg(ctx, "raster: shs has fewer coefficients than sh_degree needs");
   const Cam cam = make_cam(set);
   cudaStream_t st = (cudaStream_t)stream;

@@ -38,14 +38,15 @@ struct RasterState {
 };
 
 
-namespace {
-
 struct Cam {
   float view[16], proj[16];
   float cam[3], bg[3];
   float tanx, tany, fx, fy;
   int W, H, tiles_x, tiles_y, deg;
 };
+
+namespace {
+
 
 Cam make_cam(const neuma_raster_settings* s) {
   Cam c;

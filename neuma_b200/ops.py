@@ -10,6 +10,7 @@ import ctypes as C
 from dataclasses import dataclass, field
 from typing import Optional, Sequence, Tuple
 
+import numpy as np
 import torch
 
 from ._lib import Context, MPMConstC, RasterSettingsC, NeumaError, ptr
@@ -184,17 +185,19 @@ def raster_settings(image_height, image_width, tanfovx, tanfovy, bg, scale_modif
     s = RasterSettingsC()
     s.image_height, s.image_width = int(image_height), int(image_width)
     s.tanfovx, s.tanfovy = float(tanfovx), float(tanfovy)
-    bgl = [float(b) for b in (bg.detach().cpu().tolist() if torch.is_tensor(bg) else bg)]
-    s.bg[0], s.bg[1], s.bg[2] = bgl
+    def flat(a):
+        if torch.is_tensor(a):
+            a = a.detach().cpu().numpy()
+        return [float(v) for v in np.asarray(a, dtype=np.float64).reshape(-1)]
+
+    s.bg[0], s.bg[1], s.bg[2] = flat(bg)
     s.scale_modifier = float(scale_modifier)
-    vm = viewmatrix.detach().cpu().reshape(-1).tolist() if torch.is_tensor(viewmatrix) else list(viewmatrix)
-    pm = projmatrix.detach().cpu().reshape(-1).tolist() if torch.is_tensor(projmatrix) else list(projmatrix)
+    vm, pm = flat(viewmatrix), flat(projmatrix)
     for i in range(16):
-        s.viewmatrix[i] = float(vm[i])
-        s.projmatrix[i] = float(pm[i])
+        s.viewmatrix[i] = vm[i]
+        s.projmatrix[i] = pm[i]
     s.sh_degree = int(sh_degree)
-    cp = campos.detach().cpu().tolist() if torch.is_tensor(campos) else list(campos)
-    s.campos[0], s.campos[1], s.campos[2] = [float(v) for v in cp]
+    s.campos[0], s.campos[1], s.campos[2] = flat(campos)
     s.prefiltered, s.debug = int(bool(prefiltered)), int(bool(debug))
     return s
 

@@ -314,7 +314,7 @@ def render_torch(s: Settings, binning, means3D, shs, colors_precomp, opacities, 
         if return_aux:
             with torch.no_grad():
                 live = ~stopped | stop
-                near = ((alpha - 1.0 / 255.0).abs() < 2e-5) | ((T_incl - 0.0001).abs() < 2e-6) | (power.abs() < 1e-6)
+                near = ((alpha - 1.0 / 255.0).abs() < 5e-6) | ((T_incl - 0.0001).abs() < 5e-7) | (power.abs() < 1e-6)
                 borderline[gy.reshape(-1), gx.reshape(-1)] = (near & live).any(dim=1)
     if return_aux:
         return img, dict(n_contrib=n_contrib, final_T=final_T, borderline=borderline, pre=pre)
