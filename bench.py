@@ -1,0 +1,414 @@
+#!/usr/bin/env python
+"""bench.py -- sim+render fwd+bwd frames/s at 100k particles / 128^3 grid (BASELINE.json).
+
+One "step" = one rendered frame of finetune.py's loop (experiments/finetune.py:360-414):
+S MPM substeps (elasticity -> P2G/grid/G2P -> plasticity), particle->Gaussian binding,
+covariance deformation, one 800x800 rasterised view, l2 loss against a fixed GT image,
+and the complete reverse pass down to dL/dW (LoRA-merged weights) and dL/d(state at
+frame start).  Workload: SURVEY 8d config 3 ("jellyduck-100k-128"), synthetic.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--substeps S] [--impl reference]
+
+Prints ONE JSON line (rank 0).  N > 1: one process per GPU (torchrun), every rank runs
+its own frame stream (the render path replicates; see DESIGN.md "multi-GPU"), weak scaling.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+WORKLOAD = "jellyduck-100k-128"
+IMAGE = 800
+GOLD = os.path.join(ROOT, "tests", "golden", "material_jelly.npz")
+
+
+def load_weights():
+    """Shipped jelly_0300 base weights + a rank-16 LoRA adaptor (fixture made from the
+    reference's own classes, tests/golden/make_golden_material.py), merged: W + s B A."""
+    z = np.load(GOLD)
+    out = {}
+    for tag in ("elastic", "plastic"):
+        Ws = []
+        for l in ("layers.0", "layers.1", "final_layer"):
+            W = torch.from_numpy(z[f"param_{tag}.{l}.fc.weight"]).float()
+            A = torch.from_numpy(z[f"param_{tag}.{l}.fc.lora_A"]).float()
+            B = torch.from_numpy(z[f"param_{tag}.{l}.fc.lora_B"]).float()
+            Ws.append(W + float(z["lora_scaling"]) * (B @ A))
+        out[tag] = Ws
+    out["alpha"] = float(z["alpha"])
+    return out
+
+
+def build_workload(substeps: int, seed: int = 42):
+    from neuma_b200 import synthetic as S
+    torch.manual_seed(seed)                      # finetune.py:496-499
+    spec = S.WORKLOADS[WORKLOAD]
+    p = S.make_particles(spec, seed)
+    g = S.make_gaussians(p["x"], spec["K"], spec["G"], seed + 1)
+    cam = S.make_camera(IMAGE, IMAGE)
+    gt = torch.rand(3, IMAGE, IMAGE, generator=torch.Generator().manual_seed(seed + 2))
+    return dict(spec=spec, p=p, g=g, cam=cam, gt=gt, w=load_weights(), S=substeps)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def event_time_us(fn, iters, warm, flush=None):
+    for _ in range(warm):
+        fn()
+    ts = []
+    for _ in range(iters):
+        if flush is not None:
+            flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        b.synchronize()
+        ts.append(a.elapsed_time(b) * 1e3)
+    return float(np.mean(ts))
+
+
+def run_gpu(args):
+    import torch.distributed as dist
+    from neuma_b200 import ops, build
+    from neuma_b200.pipeline import FusedFrame
+    from neuma_b200.glue import Bindings
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    build.build()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    wl = build_workload(args.substeps)
+    spec, p, g, S = wl["spec"], wl["p"], wl["g"], wl["S"]
+    n, G, K = spec["n"], spec["G"], g["K"]
+    cc = ops.mpm_const(G, spec["dt"], 1, (0.0, -9.8, 0.0), 6e-7, "noslip")
+    d = {k: v.to(dev) for k, v in p.items()}
+    statics = (d["vol"], d["rho"], d["clip"], d["enabled"])
+    We = [w.to(dev) for w in wl["w"]["elastic"]]
+    Wp = [w.to(dev) for w in wl["w"]["plastic"]]
+    bind = Bindings(g["rowptr"].to(dev), g["col"].to(dev), g["w"].to(dev), n)
+    gs = {k: g[k].to(dev) for k in ("cov6", "opac", "shs")}
+    cam = wl["cam"]
+    import math
+    settings = ops.raster_settings(IMAGE, IMAGE, math.tan(cam.FoVx * 0.5), math.tan(cam.FoVy * 0.5),
+                                   [1.0, 1.0, 1.0], 1.0, cam.world_view_transform, cam.full_proj_transform, 3,
+                                   cam.camera_center)
+    # warm-up rollout: 10 substeps so that F is off identity
+    pre = FusedFrame(n, cc, statics, We, Wp, wl["w"]["alpha"], 10, dev, use_graphs=False)
+    pre.load_state(d["x"], d["v"], d["C"], d["F"])
+    x0, v0, C0, F0 = [t.clone() for t in pre.sim_forward()]
+    del pre
+    eng = FusedFrame(n, cc, statics, We, Wp, wl["w"]["alpha"], S, dev, bind=bind, gaussians=gs, settings=settings)
+    eng.load_state(x0, v0, C0, F0)
+    k_prev = g["xyz"].to(dev)
+    de_x_prev = d["x"].clone()
+    gt = wl["gt"].to(dev)
+    ctx = ops._ctx(x0)
+
+    # launches per frame: count one eager (un-graphed) frame with the library's own counter
+    eager = FusedFrame(n, cc, statics, We, Wp, wl["w"]["alpha"], S, dev, bind=bind, gaussians=gs,
+                       settings=settings, use_graphs=False)
+    eager.load_state(x0, v0, C0, F0)
+    l0 = ctx.launches
+    eager.frame_fwd_bwd(gt, de_x_prev, k_prev)
+    torch.cuda.synchronize()
+    launches_per_frame = ctx.launches - l0
+    del eager
+
+    def step():
+        eng.zero_weight_grads()
+        return eng.frame_fwd_bwd(gt, de_x_prev, k_prev)
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    total_ms = 0.0
+    with ClockSampler(local) as clk:
+        for _ in range(args.steps):
+            flush.zero_()                                    # L2 flush between timed iterations
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            loss, g0 = step()
+            b.record()
+            b.synchronize()
+            total_ms += a.elapsed_time(b)
+    torch.cuda.synchronize()
+    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / args.steps
+    value = world * 1000.0 / ms_per_step
+
+    # ---- e2e: same frame through the engine with HOST buffers (pinned), copies inside the timed region
+    hx, hv, hC, hF = [t_.cpu().pin_memory() for t_ in (x0, v0, C0, F0)]
+    hgt = wl["gt"].pin_memory()
+    hloss = torch.empty((), dtype=torch.float32).pin_memory()
+    hgw = [torch.empty_like(w, device="cpu").pin_memory() for w in eng.gWe + eng.gWp]
+    dgt = torch.empty_like(gt)
+
+    def step_e2e():
+        eng.load_state(hx, hv, hC, hF)
+        dgt.copy_(hgt, non_blocking=True)
+        eng.zero_weight_grads()
+        loss_, _ = eng.frame_fwd_bwd(dgt, de_x_prev, k_prev)
+        hloss.copy_(loss_, non_blocking=True)
+        for h_, w_ in zip(hgw, eng.gWe + eng.gWp):
+            h_.copy_(w_, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(3):
+        step_e2e()
+    torch.cuda.synchronize()
+    e2e_ms = 0.0
+    for _ in range(args.steps):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        step_e2e()
+        b.record()
+        b.synchronize()
+        e2e_ms += a.elapsed_time(b)
+    t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms_per_step = float(t.item()) / args.steps
+    h2d = 4 * (hx.numel() + hv.numel() + hC.numel() + hF.numel() + hgt.numel())
+    d2h = 4 * (1 + sum(h_.numel() for h_ in hgw))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- per-kernel durations at the workload's shapes (CUDA events, L2 flushed), for the roofline
+    Ng = G ** 3
+    s0 = eng.S - 1
+    xs, vs, Cs, Fs, st = eng.x[s0], eng.v[s0], eng.C[s0], eng.F[s0], eng.stress[s0]
+    outb = tuple(torch.empty_like(t_) for t_ in (xs, vs, Cs, Fs))
+    gout = [torch.randn_like(t_) for t_ in outb]
+    gF_ = torch.empty_like(Fs)
+    gWt = [torch.zeros_like(w) for w in We]
+    gouts5 = [torch.empty_like(t_) for t_ in (xs, vs, Cs, Fs, st)]
+    it, wm = 20, 3
+    kt = {}
+    kt["grid_clear"] = event_time_us(lambda: ops.mpm_grid_clear(cc, xs), it, wm, flush)
+    kt["p2g"] = event_time_us(lambda: ops.mpm_p2g(cc, xs, vs, Cs, st, *statics[:2], statics[3]), it, wm, flush)
+    kt["g2p"] = event_time_us(lambda: ops.mpm_g2p(cc, xs, Fs, statics[2], statics[3], out=outb), it, wm, flush)
+    kt["mpm_substep_bwd"] = event_time_us(
+        lambda: ops.mpm_substep_bwd_into(cc, xs, vs, Cs, Fs, st, *statics, eng.v[s0 + 1], *gout, *gouts5), it, wm, flush)
+    kt["constitutive_fwd"] = event_time_us(lambda: ops.constitutive_fwd_into(0, Fs, *We, 0.0, gF_), it, wm, flush)
+    kt["constitutive_bwd"] = event_time_us(
+        lambda: ops.constitutive_bwd_into(0, Fs, *We, 0.0, gout[3], gF_, *gWt), it, wm, flush)
+    rs = eng._render_saved
+    kt["raster_fwd"] = event_time_us(lambda: ops.raster_fwd(settings, rs[0], gs["shs"], None, gs["opac"], rs[1]), 10, 2, flush)
+    dimg = torch.randn(3, IMAGE, IMAGE, device=dev)
+    kt["raster_bwd"] = event_time_us(
+        lambda: ops.raster_bwd(settings, rs[0], gs["shs"], None, gs["opac"], rs[1], rs[2], dimg), 10, 2, flush)
+    nr = ops.raster_binning(x0, 50 * 50)[0].shape[0]
+    per_frame_us = {"constitutive_bwd": 2 * S * kt["constitutive_bwd"], "constitutive_fwd": 2 * S * kt["constitutive_fwd"],
+                    "mpm_fwd(clear+p2g+g2p)": S * (kt["grid_clear"] + kt["p2g"] + kt["g2p"]),
+                    "mpm_substep_bwd": S * kt["mpm_substep_bwd"], "raster_fwd": kt["raster_fwd"],
+                    "raster_bwd": kt["raster_bwd"]}
+    peaks = {}
+    pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk_path):
+        peaks = json.load(open(pk_path))
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    tf_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+    p2g_bytes = 108 * n + 44 * Ng                              # clear 28 Ng + P2G 108 Np + 16 Ng
+    p2g_gbs = p2g_bytes / (kt["grid_clear"] + kt["p2g"]) / 1e3
+    fwd_bytes = 260 * n + 84 * Ng
+    mpm_fwd_gbs = fwd_bytes / (kt["grid_clear"] + kt["p2g"] + kt["g2p"]) / 1e3
+    dominant = max(per_frame_us, key=per_frame_us.get)
+    if dominant.startswith("constitutive"):
+        # fused SVD + 13-64-64-9 MLP (+ LoRA merged); bwd = recompute + dgrad + wgrad = 3 x 5504 MAC / particle
+        macs = 5504 * (3 if dominant.endswith("bwd") else 1)
+        achieved = 2.0 * macs * n / (kt[dominant] * 1e-6) / 1e12
+        roof = {"kernel": dominant + "_kernel", "bound": "tensor", "achieved": achieved, "peak": tf_peak,
+                "unit": "TFLOP/s", "frac": achieved / tf_peak, "traffic": None,
+                "note": "fp32 CUDA-core MLP today (0% tensor pipe); peak = sustained bf16 " + peak_src}
+    else:
+        roof = {"kernel": "grid_clear+p2g", "bound": "hbm", "achieved": p2g_gbs, "peak": hbm_peak, "unit": "GB/s",
+                "frac": p2g_gbs / hbm_peak, "traffic": None, "note": "dense-grid algorithmic bytes; peak " + peak_src}
+    line = {
+        "metric": "sim+render fwd+bwd frames/sec at 100k particles/128^3 grid; P2G HBM GB/s",
+        "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "particles": n, "grid": G, "gaussians": K, "image": [IMAGE, IMAGE],
+                   "sh_degree": 3, "substeps_per_frame": S, "views": 1, "instances_rendered": int(nr),
+                   "mode": "fwd+bwd (l2 loss -> dL/dW_eff, dL/dstate0)", "weights": "jelly_0300 + LoRA r16 merged",
+                   "l2": "flushed between timed steps (256 MiB write)", "parallelism": f"replicas x{world}"},
+        "p2g_hbm_gbs": p2g_gbs, "p2g_hbm_frac_of_measured_peak": p2g_gbs / hbm_peak,
+        "mpm_fwd_substep_gbs": mpm_fwd_gbs,
+        "kernel_us": {k: round(v, 2) for k, v in kt.items()},
+        "frame_share_us": {k: round(v, 1) for k, v in per_frame_us.items()},
+        "roofline": roof,
+        "e2e": {"value": world * 1000.0 / e2e_ms_per_step, "unit": "frames/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms_per_step},
+        "gpu_launches": int(launches_per_frame * args.steps),
+        "gpu_launches_per_frame": int(launches_per_frame),
+        "clocks": clk.summary(),
+        "loss": float(loss),
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_sample(wl, x0.cpu(), v0.cpu(), C0.cpu(), F0.cpu())
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------- CPU oracle arm
+def cpu_sample(wl, x0, v0, C0, F0, reps: int = 1):
+    """Times the CPU oracle (a restatement of the reference's mpm.py / meta.py / the published
+    rasterizer -- NOT Warp, which is not installable) on a bounded sample of the workload:
+    ONE substep (elasticity -> sim -> plasticity) fwd+bwd and ONE render fwd+bwd at full
+    size, then frames/s = 1 / (S * t_substep + t_render)."""
+    from oracle import constitutive_oracle as CO, mpm_oracle as MO, raster_oracle as RO
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    spec, p, g, S = wl["spec"], wl["p"], wl["g"], wl["S"]
+    co = MO.MPMConst(num_grids=spec["G"], dt=spec["dt"], bound=1, eps=6e-7, bc="noslip")
+    We = [w.clone().requires_grad_(True) for w in wl["w"]["elastic"]]
+    Wp = [w.clone().requires_grad_(True) for w in wl["w"]["plastic"]]
+    t_sub = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        x = x0.clone().requires_grad_(True)
+        F = F0.clone().requires_grad_(True)
+        stress = CO.elasticity(F, We)
+        x2, v2, C2, F2 = MO.substep_fwd(co, x, v0, C0, F, stress, p["vol"], p["rho"], p["clip"], p["enabled"])
+        F3 = CO.plasticity(F2, Wp, wl["w"]["alpha"])
+        (x2.sum() + v2.sum() + C2.sum() + F3.sum()).backward()
+        t_sub.append(time.perf_counter() - t0)
+    cam = wl["cam"]
+    import math
+    s = RO.Settings(IMAGE, IMAGE, math.tan(cam.FoVx * 0.5), math.tan(cam.FoVy * 0.5), np.ones(3, np.float32),
+                    cam.world_view_transform.numpy(), cam.full_proj_transform.numpy(), 3, cam.camera_center.numpy())
+    B = torch.sparse_csr_tensor(g["rowptr"].long(), g["col"].long(), g["w"], (g["K"], spec["n"])).to_sparse_coo()
+    t0 = time.perf_counter()
+    xx = x0.clone().requires_grad_(True)
+    means3D = g["xyz"] + torch.sparse.mm(B, xx - p["x"])
+    Fk = torch.sparse.mm(B, F0.reshape(-1, 9)).reshape(-1, 3, 3)
+    cov = RO.deform_cov(g["cov6"], Fk).detach()
+    binning = RO.bin_np(s, means3D.detach().numpy(), cov.numpy())
+    img = RO.render_torch(s, binning, means3D, g["shs"], None, g["opac"], cov, dtype=torch.float32)
+    ((img - wl["gt"]) ** 2).mean().backward()
+    t_render = time.perf_counter() - t0
+    ts = float(np.median(t_sub))
+    return {"value": 1.0 / (S * ts + t_render), "unit": "frames/s", "cores": cores, "kind": "port",
+            "sample": f"1 of {S} substeps fwd+bwd ({ts:.2f} s) + 1 render 800x800 fwd+bwd ({t_render:.2f} s), "
+                      f"torch-CPU fp32 oracle, extrapolated to S={S}",
+            "t_substep_s": ts, "t_render_s": t_render}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU path.  warp-lang / diff_gaussian_rasterization are
+    not installable (no network), so this times the oracle port on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    wl = build_workload(args.substeps)
+    p = wl["p"]
+    vals, secs = [], []
+    base = None
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        base = cpu_sample(wl, p["x"], p["v"], p["C"], p["F"] + 0.01 * torch.randn_like(p["F"]))
+        if i >= args.warmup:
+            vals.append(base["value"])
+            secs.append(time.perf_counter() - t0)
+    v = float(np.mean(vals))
+    line = {"impl": "reference", "metric": "sim+render fwd+bwd frames/sec at 100k particles/128^3 grid; P2G HBM GB/s",
+            "value": v, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1000.0 / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "particles": wl["spec"]["n"], "grid": wl["spec"]["G"],
+                       "gaussians": wl["g"]["K"], "image": [IMAGE, IMAGE], "sh_degree": 3,
+                       "substeps_per_frame": wl["S"], "views": 1},
+            "cpu_baseline": {"value": v, "unit": "frames/s", "cores": base["cores"], "kind": "port",
+                             "sample": base["sample"], "wall_s_per_sample": float(np.mean(secs))},
+            "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--substeps", type=int, default=20, help="MPM substeps per rendered frame (S)")
+    ap.add_argument("--impl", default="neuma_b200", choices=["neuma_b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        args.steps = min(args.steps, 5)         # each step is a ~10-20 s CPU sample
+        args.warmup = min(args.warmup, 1)
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

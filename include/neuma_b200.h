@@ -185,8 +185,18 @@ int neuma_raster_bwd(neuma_ctx* ctx, const neuma_raster_settings* s, int K, int 
                      const float* means3D, const float* shs, const float* colors_precomp,
                      const float* opacities, const float* cov6, const int32_t* radii,
                      const float* dL_dimage,
+                     const void* saved_state /* from neuma_raster_state_save, or NULL = the
+                                                ctx's last forward */,
+                     int saved_num_rendered /* instance count of that forward */,
                      float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dcov6,
                      float* dL_dopacity, float* dL_dcolor_or_sh, void* stream);
+/* A rollout runs several forwards before their backwards (finetune.py:360-414), so the
+ * per-call forward state the backward needs (projected means, conics, colours, the sorted
+ * instance list, tile ranges, final transmittance, contributor counts -- upstream's
+ * geomBuffer / binningBuffer / imgBuffer) can be copied out into a caller-owned device
+ * buffer of neuma_raster_state_bytes() bytes and handed back to neuma_raster_bwd. */
+int neuma_raster_state_bytes(neuma_ctx* ctx, size_t* out_host);
+int neuma_raster_state_save(neuma_ctx* ctx, void* dst, void* stream);
 /* introspection for the bit-exact tile/sort parity tests: number of
  * (tile, gaussian) instances of the last forward, then the sorted 64-bit keys
  * (tile << 32 | depth bits), Gaussian ids, and per-tile [start,end) ranges.

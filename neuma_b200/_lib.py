@@ -63,7 +63,9 @@ SIGNATURES = {
     "neuma_bind_spmm": [_P, _I, _I, _P, _P, _P, _I, _P, _P, _I, _P],
     "neuma_deform_cov": [_P, _I, _P, _P, _P, _P],
     "neuma_raster_fwd": [_P, _RP, _I, _I] + [_P] * 8,
-    "neuma_raster_bwd": [_P, _RP, _I, _I] + [_P] * 13,
+    "neuma_raster_bwd": [_P, _RP, _I, _I] + [_P] * 8 + [_I] + [_P] * 6,
+    "neuma_raster_state_bytes": [_P, C.POINTER(C.c_size_t)],
+    "neuma_raster_state_save": [_P, _P, _P],
     "neuma_raster_num_rendered": [_P, _P, C.POINTER(_I)],
     "neuma_raster_export_binning": [_P, _P, _P, _P, _P],
 }

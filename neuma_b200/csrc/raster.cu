@@ -367,6 +367,26 @@ preprocess_bwd_kernel(Cam cam, int K, int M, const float* __restrict__ means,
   }
 }
 
+struct BlobLayout {
+  size_t xy, conic, rgb, clamped, plist, ranges, final_T, n_contrib, total;
+};
+inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+// Forward state needed by the backward, packed for neuma_raster_state_save.
+BlobLayout blob_layout(int K, int L, int tiles, int pix) {
+  BlobLayout b;
+  size_t o = 0;
+  b.xy = o; o = align256(o + (size_t)K * sizeof(float2));
+  b.conic = o; o = align256(o + (size_t)K * sizeof(float4));
+  b.rgb = o; o = align256(o + (size_t)K * 3 * sizeof(float));
+  b.clamped = o; o = align256(o + (size_t)K * 3);
+  b.plist = o; o = align256(o + (size_t)L * sizeof(uint32_t));
+  b.ranges = o; o = align256(o + (size_t)tiles * sizeof(uint2));
+  b.final_T = o; o = align256(o + (size_t)pix * sizeof(float));
+  b.n_contrib = o; o = align256(o + (size_t)pix * sizeof(uint32_t));
+  b.total = o;
+  return b;
+}
+
 template <typename T>
 int grow(neuma_ctx* ctx, T*& ptr, size_t count) {
   if (ptr) cudaFree(ptr);
@@ -488,30 +508,81 @@ int neuma_raster_fwd(neuma_ctx* ctx, const neuma_raster_settings* set, int K, in
 int neuma_raster_bwd(neuma_ctx* ctx, const neuma_raster_settings* set, int K, int M,
                      const float* means3D, const float* shs, const float* colors_precomp,
                      const float* opacities, const float* cov6, const int32_t* radii,
-                     const float* dL_dimage, float* dL_dmeans3D, float* dL_dmeans2D,
+                     const float* dL_dimage, const void* saved_state, int saved_num_rendered,
+                     float* dL_dmeans3D, float* dL_dmeans2D,
                      float* dL_dcov6, float* dL_dopacity, float* dL_dcolor_or_sh, void* stream) {
   if (int r = check_settings(ctx, set, K, M)) return r;
   RasterState* s = ctx->raster;
-  if (!s || s->K != K || s->W != set->image_width || s->Himg != set->image_height)
-    return neuma_fail_msg(ctx, "raster_bwd: no matching forward state in this ctx");
+  if (!s) return neuma_fail_msg(ctx, "raster_bwd: no forward has run in this ctx");
   if (!dL_dmeans3D || !dL_dmeans2D) return neuma_fail_msg(ctx, "raster_bwd: dL_dmeans3D/2D required");
   (void)opacities;
   if (K == 0) return 0;
   const Cam cam = make_cam(set);
+  const int tiles = cam.tiles_x * cam.tiles_y, pix = cam.W * cam.H;
+  // per-call forward state: either the ctx's (last forward) or a blob saved by
+  // neuma_raster_state_save (several forwards before their backwards, as in a rollout)
+  const float2* xy; const float4* conic_o; const float* rgb; const unsigned char* clamped;
+  const uint32_t* plist; const uint2* ranges; const float* final_T; const uint32_t* n_contrib;
+  int L;
+  if (saved_state) {
+    const BlobLayout b = blob_layout(K, saved_num_rendered, tiles, pix);
+    const char* base = (const char*)saved_state;
+    xy = (const float2*)(base + b.xy); conic_o = (const float4*)(base + b.conic);
+    rgb = (const float*)(base + b.rgb); clamped = (const unsigned char*)(base + b.clamped);
+    plist = (const uint32_t*)(base + b.plist); ranges = (const uint2*)(base + b.ranges);
+    final_T = (const float*)(base + b.final_T); n_contrib = (const uint32_t*)(base + b.n_contrib);
+    L = saved_num_rendered;
+    if (K > s->capK) return neuma_fail_msg(ctx, "raster_bwd: saved state larger than the ctx workspace");
+  } else {
+    if (s->K != K || s->W != set->image_width || s->Himg != set->image_height)
+      return neuma_fail_msg(ctx, "raster_bwd: no matching forward state in this ctx");
+    xy = s->xy; conic_o = s->conic_o; rgb = s->rgb; clamped = s->clamped; plist = s->vals_b;
+    ranges = s->ranges; final_T = s->final_T; n_contrib = s->n_contrib; L = s->num_rendered;
+  }
   cudaStream_t st = (cudaStream_t)stream;
   NEUMA_CUDA(ctx, cudaMemsetAsync(dL_dmeans2D, 0, (size_t)K * 3 * sizeof(float), st));
   NEUMA_CUDA(ctx, cudaMemsetAsync(s->dconic, 0, (size_t)K * sizeof(float4), st));
   NEUMA_CUDA(ctx, cudaMemsetAsync(s->dcolor, 0, (size_t)K * 3 * sizeof(float), st));
-  if (s->num_rendered > 0) {
+  if (L > 0) {
     render_bwd_kernel<<<dim3(cam.tiles_x, cam.tiles_y), dim3(BX, BY), 0, st>>>(
-        cam, s->ranges, s->vals_b, s->xy, s->rgb, s->conic_o, s->final_T, s->n_contrib, dL_dimage,
-        dL_dmeans2D, s->dconic, s->dcolor);
+        cam, ranges, plist, xy, rgb, conic_o, final_T, n_contrib, dL_dimage, dL_dmeans2D, s->dconic,
+        s->dcolor);
     NEUMA_LAUNCH_CHECK(ctx, "render_bwd_kernel");
   }
   preprocess_bwd_kernel<<<(K + 255) / 256, 256, 0, st>>>(
-      cam, K, M, means3D, shs, colors_precomp, cov6, radii, s->clamped, dL_dmeans2D, s->dconic,
+      cam, K, M, means3D, shs, colors_precomp, cov6, radii, clamped, dL_dmeans2D, s->dconic,
       s->dcolor, dL_dmeans3D, dL_dcov6, dL_dopacity, dL_dcolor_or_sh);
   NEUMA_LAUNCH_CHECK(ctx, "preprocess_bwd_kernel");
+  return 0;
+}
+
+int neuma_raster_state_bytes(neuma_ctx* ctx, size_t* out_host) {
+  if (!ctx || !out_host) return 2;
+  RasterState* s = ctx->raster;
+  if (!s) return neuma_fail_msg(ctx, "raster_state_bytes: no forward has run in this ctx");
+  *out_host = blob_layout(s->K, s->num_rendered, s->tiles_x * s->tiles_y, s->W * s->Himg).total;
+  return 0;
+}
+
+int neuma_raster_state_save(neuma_ctx* ctx, void* dst, void* stream) {
+  if (!ctx || !dst) return 2;
+  RasterState* s = ctx->raster;
+  if (!s) return neuma_fail_msg(ctx, "raster_state_save: no forward has run in this ctx");
+  const int K = s->K, L = s->num_rendered, tiles = s->tiles_x * s->tiles_y, pix = s->W * s->Himg;
+  const BlobLayout b = blob_layout(K, L, tiles, pix);
+  char* base = (char*)dst;
+  cudaStream_t st = (cudaStream_t)stream;
+  auto cp = [&](size_t off, const void* src, size_t bytes) {
+    return bytes ? cudaMemcpyAsync(base + off, src, bytes, cudaMemcpyDeviceToDevice, st) : cudaSuccess;
+  };
+  NEUMA_CUDA(ctx, cp(b.xy, s->xy, (size_t)K * sizeof(float2)));
+  NEUMA_CUDA(ctx, cp(b.conic, s->conic_o, (size_t)K * sizeof(float4)));
+  NEUMA_CUDA(ctx, cp(b.rgb, s->rgb, (size_t)K * 3 * sizeof(float)));
+  NEUMA_CUDA(ctx, cp(b.clamped, s->clamped, (size_t)K * 3));
+  NEUMA_CUDA(ctx, cp(b.plist, s->vals_b, (size_t)L * sizeof(uint32_t)));
+  NEUMA_CUDA(ctx, cp(b.ranges, s->ranges, (size_t)tiles * sizeof(uint2)));
+  NEUMA_CUDA(ctx, cp(b.final_T, s->final_T, (size_t)pix * sizeof(float)));
+  NEUMA_CUDA(ctx, cp(b.n_contrib, s->n_contrib, (size_t)pix * sizeof(uint32_t)));
   return 0;
 }
 

@@ -216,8 +216,20 @@ def raster_fwd(s: RasterSettingsC, means3D, shs, colors_precomp, opacities, cov6
     return image, radii
 
 
+def raster_save_state(like: torch.Tensor):
+    """Copy the forward state the backward needs out of the ctx (see neuma_b200.h)."""
+    ctx = _ctx(like)
+    nbytes = C.c_size_t(0)
+    ctx.call("neuma_raster_state_bytes", C.byref(nbytes))
+    n = C.c_int(0)
+    ctx.call("neuma_raster_num_rendered", _stream(like), C.byref(n))
+    blob = torch.empty(nbytes.value, dtype=torch.uint8, device=like.device)
+    ctx.call("neuma_raster_state_save", ptr(blob), _stream(like))
+    return blob, n.value
+
+
 def raster_bwd(s: RasterSettingsC, means3D, shs, colors_precomp, opacities, cov6, radii, dL_dimage,
-               want_cov=False, want_opacity=False, want_color=False):
+               want_cov=False, want_opacity=False, want_color=False, saved=None):
     means3D, opacities, cov6, dL_dimage = map(_f32, (means3D, opacities, cov6, dL_dimage))
     shs = None if shs is None else _f32(shs)
     colors_precomp = None if colors_precomp is None else _f32(colors_precomp)
@@ -233,6 +245,7 @@ def raster_bwd(s: RasterSettingsC, means3D, shs, colors_precomp, opacities, cov6
         gcol = torch.empty_like(shs if shs is not None else colors_precomp)
     _ctx(means3D).call("neuma_raster_bwd", C.byref(s), K, M, ptr(means3D), ptr(shs),
                        ptr(colors_precomp), ptr(opacities), ptr(cov6), ptr(radii), ptr(dL_dimage),
+                       ptr(None if saved is None else saved[0]), 0 if saved is None else int(saved[1]),
                        ptr(g3), ptr(g2), ptr(gcov), ptr(gop), ptr(gcol), _stream(means3D))
     return g3, g2, gcov, gop, gcol
 
@@ -248,3 +261,25 @@ def raster_binning(like: torch.Tensor, tiles: int):
     ranges = torch.empty(tiles, 2, device=like.device, dtype=torch.int32)
     ctx.call("neuma_raster_export_binning", ptr(keys), ptr(ids), ptr(ranges), _stream(like))
     return keys, ids, ranges
+
+
+# --------------------------------------------------------------------- allocation-free variants
+# (static buffers: used by neuma_b200.pipeline under CUDA-graph capture)
+def constitutive_fwd_into(kind: int, F, W0, W1, W2, alpha: float, out) -> None:
+    _ctx(F).call("neuma_constitutive_fwd", int(kind), F.shape[0], W1.shape[0], ptr(F), ptr(W0),
+                 ptr(W1), ptr(W2), C.c_float(alpha), ptr(out), _stream(F))
+
+
+def constitutive_bwd_into(kind: int, F, W0, W1, W2, alpha: float, gout, gF, gW0, gW1, gW2) -> None:
+    """gW* are accumulated into (not zeroed)."""
+    _ctx(F).call("neuma_constitutive_bwd", int(kind), F.shape[0], W1.shape[0], ptr(F), ptr(W0),
+                 ptr(W1), ptr(W2), C.c_float(alpha), ptr(gout), ptr(gF), ptr(gW0), ptr(gW1), ptr(gW2),
+                 _stream(F))
+
+
+def mpm_substep_bwd_into(c: MPMConstC, x, v, Cm, F, stress, vol, rho, clip_bound, enabled, v2,
+                         gx2, gv2, gC2, gF2, gx, gv, gC, gF, gstress) -> None:
+    _ctx(x).call("neuma_mpm_substep_bwd", C.byref(c), x.shape[0], ptr(x), ptr(v), ptr(Cm), ptr(F),
+                 ptr(stress), ptr(vol), ptr(rho), ptr(clip_bound), ptr(enabled), ptr(v2),
+                 ptr(gx2), ptr(gv2), ptr(gC2), ptr(gF2), ptr(gx), ptr(gv), ptr(gC), ptr(gF), ptr(gstress),
+                 _stream(x))

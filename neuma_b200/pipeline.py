@@ -1,0 +1,189 @@
+"""Fused frame engine: S MPM substeps (elasticity -> sim -> plasticity), the
+particle->Gaussian binding, covariance deformation, rasterization and the complete
+reverse pass, driven as a handful of CUDA-graph launches instead of autograd nodes.
+
+It computes exactly what the drop-in classes compute for one rendered frame of
+finetune.py's loop (experiments/finetune.py:360-414) -- the per-op modules in
+neuma_b200.sim / .material / .glue remain the reference-shaped API; this engine is
+the same kernels with the Python/autograd overhead removed:
+
+  * per-substep state is kept compactly: x, v, C, F, stress, F_trial = 168 B per
+    particle per substep (the reference's MPMCacheDiffSim pins 528 B,
+    modules/nclaw/sim/interface.py:108-123);
+  * the S-substep forward and the S-substep backward are each captured once into a
+    CUDA graph (static buffers) and replayed;
+  * LoRA is handled by the caller: the engine takes merged weights and returns
+    dL/dW_eff (see neuma_b200.material for the un-merge).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import ops
+from ._lib import RasterSettingsC
+
+
+class FusedFrame:
+    def __init__(self, n: int, cconst, statics, We: Sequence[torch.Tensor], Wp: Sequence[torch.Tensor],
+                 alpha: float, substeps: int, device, bind=None, gaussians=None,
+                 settings: Optional[RasterSettingsC] = None, center=None, size=None,
+                 elastic_kind: int = ops.KIND_ELASTIC, use_graphs: bool = True):
+        self.n, self.S, self.dev = int(n), int(substeps), device
+        self.c = cconst
+        self.vol, self.rho, self.clip, self.enabled = statics
+        self.We = [w.detach().contiguous() for w in We]
+        self.Wp = [w.detach().contiguous() for w in Wp]
+        self.alpha = float(alpha)
+        self.kind_e = elastic_kind
+        self.bind, self.gs, self.settings = bind, gaussians, settings
+        f = dict(device=device, dtype=torch.float32)
+        S = self.S
+        # state[s] = inputs of substep s (s = 0..S-1), state[S] = frame output
+        self.x = torch.empty(S + 1, n, 3, **f)
+        self.v = torch.empty(S + 1, n, 3, **f)
+        self.C = torch.empty(S + 1, n, 3, 3, **f)
+        self.F = torch.empty(S + 1, n, 3, 3, **f)
+        self.stress = torch.empty(S, n, 3, 3, **f)
+        self.Ftrial = torch.empty(S, n, 3, 3, **f)
+        # adjoint buffers (ping-pong) and weight-gradient accumulators
+        self.g = [[torch.zeros(n, 3, **f), torch.zeros(n, 3, **f), torch.zeros(n, 3, 3, **f),
+                   torch.zeros(n, 3, 3, **f)] for _ in range(2)]
+        self.gstress = torch.empty(n, 3, 3, **f)
+        self.gFtrial = torch.empty(n, 3, 3, **f)
+        self.gF_e = torch.empty(n, 3, 3, **f)
+        self.gWe = [torch.zeros_like(w) for w in self.We]
+        self.gWp = [torch.zeros_like(w) for w in self.Wp]
+        self.center = torch.zeros(3, **f) if center is None else center.to(**f)
+        self.size = torch.ones(3, **f) if size is None else size.to(**f)
+        self.use_graphs = use_graphs
+        self._g_fwd = self._g_bwd = None
+        self._ctx = ops._ctx(self.x)
+
+    # ------------------------------------------------------------------ sim
+    def _sim_forward(self) -> None:
+        c = self.c
+        for s in range(self.S):
+            ctx = self._ctx
+            ops.constitutive_fwd_into(self.kind_e, self.F[s], *self.We, 0.0, self.stress[s])
+            ops.mpm_substep_fwd(c, self.x[s], self.v[s], self.C[s], self.F[s], self.stress[s], self.vol, self.rho,
+                                self.clip, self.enabled,
+                                out=(self.x[s + 1], self.v[s + 1], self.C[s + 1], self.Ftrial[s]))
+            ops.constitutive_fwd_into(ops.KIND_PLASTIC, self.Ftrial[s], *self.Wp, self.alpha, self.F[s + 1])
+
+    def _sim_backward(self) -> None:
+        """Consumes self.g[0] = dL/d(state[S]); leaves dL/d(state[0]) in self.g[0]
+        and accumulates dL/dW_eff into gWe / gWp."""
+        c = self.c
+        cur, nxt = 0, 1
+        for s in reversed(range(self.S)):
+            gx2, gv2, gC2, gF_next = self.g[cur]
+            # plasticity: F[s+1] = P(Ftrial[s])
+            ops.constitutive_bwd_into(ops.KIND_PLASTIC, self.Ftrial[s], *self.Wp, self.alpha, gF_next,
+                                      self.gFtrial, *self.gWp)
+            gx, gv, gC, gF = self.g[nxt]
+            ops.mpm_substep_bwd_into(c, self.x[s], self.v[s], self.C[s], self.F[s], self.stress[s], self.vol,
+                                     self.rho, self.clip, self.enabled, self.v[s + 1],
+                                     gx2, gv2, gC2, self.gFtrial, gx, gv, gC, gF, self.gstress)
+            # elasticity: stress[s] = E(F[s]);  dL/dF[s] += E'(F[s])^T gstress
+            ops.constitutive_bwd_into(self.kind_e, self.F[s], *self.We, 0.0, self.gstress, self.gF_e, *self.gWe)
+            gF.add_(self.gF_e)
+            cur, nxt = nxt, cur
+        if cur != 0:
+            for a, b in zip(self.g[0], self.g[1]):
+                a.copy_(b)
+
+    def _capture(self, fn):
+        fn()                                  # warm-up: grows the library workspaces outside capture
+        torch.cuda.synchronize(self.dev)
+        side = torch.cuda.Stream(self.dev)
+        side.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(side):
+            fn()
+        torch.cuda.current_stream(self.dev).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            fn()
+        return graph
+
+    def load_state(self, x, v, C, F) -> None:
+        self.x[0].copy_(x, non_blocking=True)
+        self.v[0].copy_(v, non_blocking=True)
+        self.C[0].copy_(C, non_blocking=True)
+        self.F[0].copy_(F, non_blocking=True)
+
+    def sim_forward(self):
+        if not self.use_graphs:
+            self._sim_forward()
+        else:
+            if self._g_fwd is None:
+                keep = [t[0].clone() for t in (self.x, self.v, self.C, self.F)]
+                self._g_fwd = self._capture(self._sim_forward)
+                self.load_state(*keep)
+            self._g_fwd.replay()
+        S = self.S
+        return self.x[S], self.v[S], self.C[S], self.F[S]
+
+    def sim_backward(self, gx, gv, gC, gF):
+        for dst, src in zip(self.g[0], (gx, gv, gC, gF)):
+            if src is None:
+                dst.zero_()
+            else:
+                dst.copy_(src)
+        if not self.use_graphs:
+            self._sim_backward()
+        else:
+            if self._g_bwd is None:
+                keep = [t.clone() for t in self.g[0]]
+                keep_w = [t.clone() for t in self.gWe + self.gWp]
+                self._g_bwd = self._capture(self._sim_backward)
+                for dst, src in zip(self.g[0], keep):
+                    dst.copy_(src)
+                for dst, src in zip(self.gWe + self.gWp, keep_w):
+                    dst.copy_(src)
+            self._g_bwd.replay()
+        return self.g[0]
+
+    def zero_weight_grads(self) -> None:
+        for t in self.gWe + self.gWp:
+            t.zero_()
+
+    # ------------------------------------------------------------------ sim -> render
+    def render_forward(self, de_x_prev: torch.Tensor, k_prev: torch.Tensor):
+        """bindings + covariance deformation + rasterization of the frame's final state."""
+        b, gs, S = self.bind, self.gs, self.S
+        de_x = (self.x[S] - self.center) / self.size
+        self._delta = de_x - de_x_prev
+        means3D = k_prev + ops.bind_spmm(b.rowptr, b.col, b.w, self._delta, self.n)
+        Fk = ops.bind_spmm(b.rowptr, b.col, b.w, self.F[S].reshape(self.n, 9), self.n)
+        cov = ops.deform_cov(gs["cov6"], Fk)
+        image, radii = ops.raster_fwd(self.settings, means3D, gs["shs"], None, gs["opac"], cov)
+        self._render_saved = (means3D, cov, radii)
+        return image, means3D, de_x
+
+    def render_backward(self, dL_dimage: torch.Tensor):
+        """dL/dimage -> dL/dx of the frame's final state (cov3D carries no gradient)."""
+        b, gs = self.bind, self.gs
+        means3D, cov, radii = self._render_saved
+        g3, _g2, *_ = ops.raster_bwd(self.settings, means3D, gs["shs"], None, gs["opac"], cov, radii, dL_dimage)
+        gde = ops.bind_spmm(b.rowptr, b.col, b.w, g3, self.n, transpose=True)
+        return gde / self.size
+
+    # ------------------------------------------------------------------ one frame, forward + backward
+    def frame_fwd_bwd(self, gt: torch.Tensor, de_x_prev, k_prev, g_state_next=None):
+        """S substeps + render + l2 loss, then the full reverse pass.  Returns
+        (loss, dL/d(state at frame start))."""
+        self.sim_forward()
+        image, means3D, de_x = self.render_forward(de_x_prev, k_prev)
+        diff = image - gt
+        loss = (diff * diff).mean()
+        dL_dimage = diff * (2.0 / diff.numel())
+        gx = self.render_backward(dL_dimage)
+        if g_state_next is not None:
+            gx = gx + g_state_next[0]
+            gv, gC, gF = g_state_next[1:]
+        else:
+            gv = gC = gF = None
+        g0 = self.sim_backward(gx, gv, gC, gF)
+        return loss, g0

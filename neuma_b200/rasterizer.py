@@ -46,6 +46,8 @@ class _RasterizeGaussians(torch.autograd.Function):
         op = opacities.detach().contiguous()
         cov = cov3Ds_precomp.detach().contiguous()
         color, radii = ops.raster_fwd(cs, m3, sh_, cp, op, cov)
+        # several forwards run before their backwards in a rollout: keep this call's state
+        ctx.saved_state = ops.raster_save_state(m3) if any(ctx.needs_input_grad) else None
         ctx.cs = cs
         ctx.save_for_backward(m3, op, cov, radii, *( [sh_] if sh_ is not None else [cp]))
         ctx.has_sh = sh_ is not None
@@ -58,9 +60,9 @@ class _RasterizeGaussians(torch.autograd.Function):
         sh, cp = (col, None) if ctx.has_sh else (None, col)
         need = ctx.needs_input_grad
         want_color = need[2] if ctx.has_sh else need[3]
-        # NB: the backward must run before the ctx of this device sees another forward
         g3, g2, gcov, gop, gcol = ops.raster_bwd(ctx.cs, m3, sh, cp, op, cov, radii, grad_color.contiguous(),
-                                                 want_cov=need[5], want_opacity=need[4], want_color=want_color)
+                                                 want_cov=need[5], want_opacity=need[4], want_color=want_color,
+                                                 saved=ctx.saved_state)
         if gop is not None:
             gop = gop.reshape(op.shape)
         return (g3 if need[0] else None, g2 if need[1] else None,

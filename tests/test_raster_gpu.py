@@ -123,3 +123,19 @@ def test_full_size_800(cuda_dev):
     b = ops.raster_bwd(cs, sc["means"].to(cuda_dev), sc["shs"].to(cuda_dev), None, sc["opac"].to(cuda_dev),
                        sc["cov6"].to(cuda_dev), radii, 2.0 * G)[0]
     assert float((b - 2 * a).norm() / b.norm()) < 1e-4
+
+
+def test_saved_state_backward(cuda_dev):
+    """Two forwards, then the backward of the FIRST from its saved state (rollout order,
+    finetune.py:360-414) == its backward taken immediately."""
+    from neuma_b200 import ops
+    s, a = make_scene(1200, W=96, H=96, seed=21)
+    _, b = make_scene(1500, W=96, H=96, seed=22)
+    G = torch.randn(3, 96, 96).to(cuda_dev)
+    cs, img, radii = _run_fwd(s, a, cuda_dev)
+    args = (a["means"].to(cuda_dev), a["shs"].to(cuda_dev), None, a["opac"].to(cuda_dev), a["cov6"].to(cuda_dev))
+    ref = ops.raster_bwd(cs, *args, radii, G)[0]
+    saved = ops.raster_save_state(img)
+    _run_fwd(s, b, cuda_dev)                       # clobbers the ctx state
+    got = ops.raster_bwd(cs, *args, radii, G, saved=saved)[0]
+    assert rel_err(got, ref) < 1e-5
