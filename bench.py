@@ -296,7 +296,8 @@ def run_gpu(args):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "particles": n, "grid": G, "gaussians": K, "image": [IMAGE, IMAGE],
-                   "sh_degree": 3, "substeps_per_frame": S, "views": 1, "instances_rendered": int(nr),
+                   "sh_degree": 3, "substeps_per_frame": S, "views": 1, "dt": spec["dt"],
+                   "instances_rendered": int(nr),
                    "mode": "fwd+bwd (l2 loss -> dL/dW_eff, dL/dstate0)", "weights": "jelly_0300 + LoRA r16 merged",
                    "l2": "flushed between timed steps (256 MiB write)", "parallelism": f"replicas x{world}"},
         "p2g_hbm_gbs": p2g_gbs, "p2g_hbm_frac_of_measured_peak": p2g_gbs / hbm_peak,

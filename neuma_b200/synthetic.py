@@ -13,13 +13,17 @@ import torch
 
 CHI2_3_095 = 7.814727903251179  # chi^2_3(0.95): the Mahalanobis gate of binding_utils.py
 
+# dt: the shipped configs use 1e-3 / 5e-4 at num_grids 32 (finetune-jd.yaml:35-45).  The explicit
+# MLS-MPM step is CFL-limited (dt ~ dx / wave speed): measured on the B200 with the shipped jelly
+# weights, 128^3 goes NaN within 10 substeps at dt = 1e-3 and is stable at 2.5e-4, so the scaled-up
+# grids scale dt with dx (SURVEY 8d's dt = 1e-3 at 128^3 does not survive contact with the GPU).
 WORKLOADS = {
     # name: Np, G, box lo/hi per axis, K, image, dt
     "bouncyball-5k-32": dict(n=5_000, G=32, ball=(0.5, 0.6, 0.5, 0.2), K=0, image=0, dt=1e-3),
     "bouncyball-50k-64": dict(n=50_000, G=64, ball=(0.5, 0.6, 0.5, 0.2), K=25_000, image=800, dt=1e-3),
-    "jellyduck-100k-128": dict(n=100_000, G=128, box=((0.3, 0.7),) * 3, K=50_000, image=800, dt=1e-3),
-    "claycat-200k-128": dict(n=200_000, G=128, box=((0.25, 0.75),) * 3, K=100_000, image=800, dt=5e-4),
-    "block-1m-256": dict(n=1_000_000, G=256, box=((0.2, 0.8), (0.2, 0.8), (0.1, 0.9)), K=0, image=0, dt=1e-3),
+    "jellyduck-100k-128": dict(n=100_000, G=128, box=((0.3, 0.7),) * 3, K=50_000, image=800, dt=2.5e-4),
+    "claycat-200k-128": dict(n=200_000, G=128, box=((0.25, 0.75),) * 3, K=100_000, image=800, dt=2.5e-4),
+    "block-1m-256": dict(n=1_000_000, G=256, box=((0.2, 0.8), (0.2, 0.8), (0.1, 0.9)), K=0, image=0, dt=1.25e-4),
 }
 
 
