@@ -19,14 +19,22 @@ import warp_shim as ws  # noqa: E402
 
 wp = ws.install()
 sys.path.insert(0, "/root/reference")
+# mpm.py:553-571 declares `lin_vel: np.ndarray = np.zeros(3)` in a @dataclass, which Python >= 3.11
+# rejects at import time; MPMInitData is not used here, so neutralise the decorator for the import.
+import dataclasses  # noqa: E402
+import torch  # noqa: E402,F401  (import before the patch: torch itself uses dataclasses)
+import einops  # noqa: E402,F401
+_dc = dataclasses.dataclass
+dataclasses.dataclass = lambda cls=None, **kw: cls if cls is not None else (lambda c: c)
 from modules.nclaw.sim.mpm import MPMModel  # noqa: E402
+dataclasses.dataclass = _dc
 from modules.nclaw.warp.svd import SVDFunction  # noqa: E402
 from modules.d3gs.utils.simulation_utils import deform_cov_by_F  # noqa: E402
 
 f32 = np.float32
 
 
-def run_case(G, n, bc, dt, seed, gravity=(0.0, -9.8, 0.0), bound=1, eps=6e-7, lo=0.08, hi=0.92):
+def run_case(G, n, bc, dt, seed, gravity=(0.0, -9.8, 0.0), bound=1, eps=6e-7, lo=0.08, hi=0.84):
     rng = np.random.default_rng(seed)
     x = (lo + (hi - lo) * rng.random((n, 3))).astype(f32)
     x[:5] = f32(0.02)                       # x * inv_dx < 0.5: int() truncation, not floor
