@@ -250,11 +250,19 @@ def run_gpu(args):
     gouts5 = [torch.empty_like(t_) for t_ in (xs, vs, Cs, Fs, st)]
     it, wm = 20, 3
     kt = {}
-    kt["grid_clear"] = event_time_us(lambda: ops.mpm_grid_clear(cc, xs), it, wm, flush)
-    kt["p2g"] = event_time_us(lambda: ops.mpm_p2g(cc, xs, vs, Cs, st, *statics[:2], statics[3]), it, wm, flush)
-    kt["g2p"] = event_time_us(lambda: ops.mpm_g2p(cc, xs, Fs, statics[2], statics[3], out=outb), it, wm, flush)
-    kt["mpm_substep_bwd"] = event_time_us(
-        lambda: ops.mpm_substep_bwd_into(cc, xs, vs, Cs, Fs, st, *statics, eng.v[s0 + 1], *gout, *gouts5), it, wm, flush)
+    sx = (eng.vol, eng.rho, eng.clip, eng.enabled)                 # statics in the engine's cell order
+    grid_s, adj_s, box_s = eng.grid[s0], eng.adj[s0], eng.box[s0]
+    box_tmp = torch.zeros(8, dtype=torch.int32, device=dev)
+    kt["grid_clear"] = event_time_us(lambda: ops.mpm_box_clear(cc, box_s, grid_s, None, box_tmp), it, wm, flush)
+    kt["p2g"] = event_time_us(lambda: ops.mpm_p2g_to(cc, xs, vs, Cs, st, sx[0], sx[1], sx[3], grid_s), it, wm, flush)
+    kt["grid_op"] = event_time_us(lambda: ops.mpm_grid_op_box(cc, box_s, grid_s, adj_s), it, wm, flush)
+    kt["g2p"] = event_time_us(lambda: ops.mpm_g2p_from(cc, xs, Fs, sx[2], sx[3], grid_s, outb, box_tmp), it, wm, flush)
+    # leave a valid (v, m) grid and a zeroed adjoint target in the slot for the backward timing
+    ops.mpm_rollout_fwd(cc, xs, vs, Cs, Fs, st, *sx, outb, grid_s, adj_s, box_s, box_tmp)
+
+    def _bwd():
+        ops.mpm_rollout_bwd(cc, xs, vs, Cs, Fs, st, *sx, outb[1], outb[2], *gout, grid_s, adj_s, box_s, *gouts5)
+    kt["mpm_substep_bwd"] = event_time_us(_bwd, it, wm, flush)
     kt["constitutive_fwd"] = event_time_us(lambda: ops.constitutive_fwd_into(0, Fs, *We, 0.0, gF_), it, wm, flush)
     kt["constitutive_bwd"] = event_time_us(
         lambda: ops.constitutive_bwd_into(0, Fs, *We, 0.0, gout[3], gF_, *gWt), it, wm, flush)
@@ -265,7 +273,7 @@ def run_gpu(args):
         lambda: ops.raster_bwd(settings, rs[0], gs["shs"], None, gs["opac"], rs[1], rs[2], dimg), 10, 2, flush)
     nr = ops.raster_binning(x0, 50 * 50)[0].shape[0]
     per_frame_us = {"constitutive_bwd": 2 * S * kt["constitutive_bwd"], "constitutive_fwd": 2 * S * kt["constitutive_fwd"],
-                    "mpm_fwd(clear+p2g+g2p)": S * (kt["grid_clear"] + kt["p2g"] + kt["g2p"]),
+                    "mpm_fwd(clear+p2g+grid_op+g2p)": S * (kt["grid_clear"] + kt["p2g"] + kt["grid_op"] + kt["g2p"]),
                     "mpm_substep_bwd": S * kt["mpm_substep_bwd"], "raster_fwd": kt["raster_fwd"],
                     "raster_bwd": kt["raster_bwd"]}
     peaks = {}
@@ -278,7 +286,7 @@ def run_gpu(args):
     p2g_bytes = 108 * n + 44 * Ng                              # clear 28 Ng + P2G 108 Np + 16 Ng
     p2g_gbs = p2g_bytes / (kt["grid_clear"] + kt["p2g"]) / 1e3
     fwd_bytes = 260 * n + 84 * Ng
-    mpm_fwd_gbs = fwd_bytes / (kt["grid_clear"] + kt["p2g"] + kt["g2p"]) / 1e3
+    mpm_fwd_gbs = fwd_bytes / (kt["grid_clear"] + kt["p2g"] + kt["grid_op"] + kt["g2p"]) / 1e3
     dominant = max(per_frame_us, key=per_frame_us.get)
     if dominant.startswith("constitutive"):
         # fused SVD + 13-64-64-9 MLP (+ LoRA merged); bwd = recompute + dgrad + wgrad = 3 x 5504 MAC / particle
@@ -286,10 +294,13 @@ def run_gpu(args):
         achieved = 2.0 * macs * n / (kt[dominant] * 1e-6) / 1e12
         roof = {"kernel": dominant + "_kernel", "bound": "tensor", "achieved": achieved, "peak": tf_peak,
                 "unit": "TFLOP/s", "frac": achieved / tf_peak, "traffic": None,
-                "note": "fp32 CUDA-core MLP today (0% tensor pipe); peak = sustained bf16 " + peak_src}
+                "note": "tcgen05 kind::f16 bf16x3 (6 bf16 products per fp32 MAC, counted as ONE MAC here); "
+                        "SVD/GELU/split CUDA-core work bounds the kernel, not the tensor pipe; peak = sustained bf16 "
+                        + peak_src}
     else:
         roof = {"kernel": "grid_clear+p2g", "bound": "hbm", "achieved": p2g_gbs, "peak": hbm_peak, "unit": "GB/s",
-                "frac": p2g_gbs / hbm_peak, "traffic": None, "note": "dense-grid algorithmic bytes; peak " + peak_src}
+                "frac": p2g_gbs / hbm_peak, "traffic": None, "note": "dense-grid algorithmic bytes (SURVEY 8d) over a box-sparse clear + P2G: the real traffic is "
+                        "smaller, so the fraction can exceed 1; peak " + peak_src}
     line = {
         "metric": "sim+render fwd+bwd frames/sec at 100k particles/128^3 grid; P2G HBM GB/s",
         "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),

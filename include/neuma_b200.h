@@ -134,6 +134,61 @@ int neuma_mpm_substep_bwd(neuma_ctx* ctx, const neuma_mpm_const* c, int n,
                           float* gx, float* gv, float* gC, float* gF, float* gstress,
                           void* stream);
 
+/* ---- MPM rollout path (MPMCacheDiffSim, modules/nclaw/sim/interface.py:108-123) --------
+ * The same substep with CALLER-OWNED packed grids, one per substep of a differentiable
+ * rollout, so the backward reads the forward's grid instead of recomputing P2G
+ * (mpm.py:312-315).  `grid` / `adj`: nz*G*G float4 nodes, plane-major (z slowest).
+ * `box`: int32[8] on the device = inclusive node bounding box (lo.xyz, hi.xyz, 2 pad) of
+ * the occupied nodes; clears and node passes touch only the box. */
+/* box of the nodes the particles at x touch (init + reduce) */
+int neuma_mpm_box_from_x(neuma_ctx* ctx, const neuma_mpm_const* c, int n, const float* x,
+                         const int32_t* enabled, int32_t* box, void* stream);
+/* grid.clear() (mpm.py:147-150) restricted to the box, on up to two grids (either may be
+ * NULL); box_reset (may be NULL) is set to the empty box */
+int neuma_mpm_box_clear(neuma_ctx* ctx, const neuma_mpm_const* c, const int32_t* box, float* grid0,
+                        float* grid1, int32_t* box_reset, void* stream);
+/* p2g (mpm.py:321-371) accumulating (mv, m) into `grid` */
+int neuma_mpm_p2g_to(neuma_ctx* ctx, const neuma_mpm_const* c, int n, const float* x, const float* v,
+                     const float* C, const float* stress, const float* vol, const float* rho,
+                     const int32_t* enabled, float* grid, void* stream);
+/* grid_op_* (mpm.py:373-429) over the box, in place: (mv, m) -> (v, m); components zeroed
+ * by the wall BC are stored as -0.0f.  adj_to_clear (may be NULL) is zeroed over the box. */
+int neuma_mpm_grid_op_box(neuma_ctx* ctx, const neuma_mpm_const* c, const int32_t* box, float* grid,
+                          float* adj_to_clear, void* stream);
+/* g2p (mpm.py:432-498) from a (v, m) grid; box_next (may be NULL; must hold the empty box
+ * or a partial reduction) receives the box of the nodes the NEW positions touch */
+int neuma_mpm_g2p_from(neuma_ctx* ctx, const neuma_mpm_const* c, int n, const float* x,
+                       const float* F, const float* clip_bound, const int32_t* enabled,
+                       const float* grid_v, float* x2, float* v2, float* C2, float* F2,
+                       int32_t* box_next, void* stream);
+/* MPMModel.forward (mpm.py:279-297) = box_clear(grid; resets box_next) + p2g_to +
+ * grid_op_box (also zeroes adj over the box if non-NULL) + g2p_from */
+int neuma_mpm_rollout_fwd(neuma_ctx* ctx, const neuma_mpm_const* c, int n, const float* x,
+                          const float* v, const float* C, const float* F, const float* stress,
+                          const float* vol, const float* rho, const float* clip_bound,
+                          const int32_t* enabled, float* x2, float* v2, float* C2, float* F2,
+                          float* grid, float* adj, const int32_t* box, int32_t* box_next,
+                          void* stream);
+/* MPMModel.backward (mpm.py:299-319) without the P2G recompute: grid_v is the (v, m) grid
+ * neuma_mpm_rollout_fwd left, adj a zeroed (over the box) scratch grid (overwritten), C2 the
+ * forward's C output (may be NULL: recomputed).  Gradient outputs as neuma_mpm_substep_bwd. */
+int neuma_mpm_rollout_bwd(neuma_ctx* ctx, const neuma_mpm_const* c, int n, const float* x,
+                          const float* v, const float* C, const float* F, const float* stress,
+                          const float* vol, const float* rho, const float* clip_bound,
+                          const int32_t* enabled, const float* v2, const float* C2,
+                          const float* gx2, const float* gv2, const float* gC2, const float* gF2,
+                          const float* grid_v, float* adj, const int32_t* box, float* gx, float* gv,
+                          float* gC, float* gF, float* gstress, void* stream);
+/* permutation that puts the particles in cell (Morton) order of their stencil base:
+ * perm[i] = index of the i-th particle in that order.  Not capturable (may grow the ctx
+ * scratch). */
+int neuma_mpm_cell_order(neuma_ctx* ctx, const neuma_mpm_const* c, int n, const float* x,
+                         int32_t* perm, void* stream);
+/* dst[i, :] = src[idx[i], :] for rows of `words_per_row` 32-bit words; inv[perm[i]] = i */
+int neuma_gather_rows(neuma_ctx* ctx, int n, int words_per_row, const void* src, const int32_t* idx,
+                      void* dst, void* stream);
+int neuma_invert_perm(neuma_ctx* ctx, int n, const int32_t* perm, int32_t* inv, void* stream);
+
 /* ---- SVD: modules/nclaw/warp/svd.py:59-96 ------------------------------ */
 /* batch_svd incl. the det<0 sign fix; outputs U [n,3,3], sigma [n,3], Vh [n,3,3] */
 int neuma_svd3_fwd(neuma_ctx* ctx, int n, const float* A, float* U, float* sigma, float* Vh,

@@ -56,6 +56,16 @@ SIGNATURES = {
     "neuma_mpm_halo_unpack_add": [_P, _CP, _I, _I, _P, _P],
     "neuma_mpm_substep_fwd": [_P, _CP, _I] + [_P] * 14,
     "neuma_mpm_substep_bwd": [_P, _CP, _I] + [_P] * 20,
+    "neuma_mpm_box_from_x": [_P, _CP, _I, _P, _P, _P, _P],
+    "neuma_mpm_box_clear": [_P, _CP, _P, _P, _P, _P, _P],
+    "neuma_mpm_p2g_to": [_P, _CP, _I] + [_P] * 9,
+    "neuma_mpm_grid_op_box": [_P, _CP, _P, _P, _P, _P],
+    "neuma_mpm_g2p_from": [_P, _CP, _I] + [_P] * 11,
+    "neuma_mpm_rollout_fwd": [_P, _CP, _I] + [_P] * 18,
+    "neuma_mpm_rollout_bwd": [_P, _CP, _I] + [_P] * 24,
+    "neuma_mpm_cell_order": [_P, _CP, _I, _P, _P, _P],
+    "neuma_gather_rows": [_P, _I, _I, _P, _P, _P, _P],
+    "neuma_invert_perm": [_P, _I, _P, _P, _P],
     "neuma_svd3_fwd": [_P, _I, _P, _P, _P, _P, _P],
     "neuma_svd3_bwd": [_P, _I] + [_P] * 8,
     "neuma_constitutive_fwd": [_P, _I, _I, _I, _P, _P, _P, _P, _F, _P, _P],

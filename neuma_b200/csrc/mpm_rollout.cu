@@ -1,0 +1,627 @@
+// Rollout path of the MLS-MPM substep for sm_100a: the same arithmetic as mpm.cu
+// (modules/nclaw/sim/mpm.py:279-498) laid out for a differentiable S-substep rollout
+// (experiments/finetune.py:360-414) on one B200:
+//
+//   * every substep writes its grid into its OWN caller-owned slot (S x G^3 x 16 B: 0.7 GB
+//     for S = 20 at 128^3 -- nothing next to 180 GB of HBM), so the backward reads the
+//     forward's grid instead of re-running P2G (the reference recomputes it, mpm.py:312-315);
+//   * grid_op runs once per node over the particles' bounding box, IN PLACE:
+//     (mv, m) -> (v, m).  A component the wall BC zeroed is stored as -0.0f, which is
+//     numerically 0 for G2P and tells the adjoint exactly which components pass a
+//     gradient (a naturally computed -0.0f cannot occur: the grid starts at +0 and
+//     +0 + -0 = +0);
+//   * clears and node passes touch only the bounding box of the occupied nodes, kept
+//     on the device (int32[8]: lo.xyz, hi.xyz inclusive) and updated by G2P for the
+//     next substep -- exact, no host round trip, CUDA-graph friendly;
+//   * the backward is  scatter adj(G2P) -> one node pass (adj(grid_op)) -> gather,
+//     and the per-(particle, node) work holds no divisions.
+//
+// Particles are expected in cell (Morton) order (neuma_mpm_cell_order): consecutive
+// lanes then touch neighbouring nodes, so the 27 node visits of a warp coalesce in L1/L2.
+#include "mpm_common.cuh"
+#include <cub/device/device_radix_sort.cuh>
+#include <limits.h>
+
+namespace {
+
+struct Box {
+  int lo[3], hi[3];
+};
+__device__ __forceinline__ Box load_box(const int32_t* __restrict__ b) {
+  Box r;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) { r.lo[a] = b[a]; r.hi[a] = b[3 + a]; }
+  return r;
+}
+
+__global__ void box_init_kernel(int32_t* box) {
+  if (threadIdx.x < 3) box[threadIdx.x] = INT_MAX;
+  else if (threadIdx.x < 6) box[threadIdx.x] = INT_MIN;
+  else if (threadIdx.x < 8) box[threadIdx.x] = 0;
+}
+
+// folds one particle's node range [base, base+2] (clamped to the slab) into the box
+__device__ __forceinline__ void box_accumulate(const neuma_mpm_const& c, bool active, float x0,
+                                               float x1, float x2, int32_t* __restrict__ box,
+                                               int* sbox /* shared int[6] */) {
+  int lo[3] = {INT_MAX, INT_MAX, INT_MAX}, hi[3] = {INT_MIN, INT_MIN, INT_MIN};
+  if (active) {
+    const float p[3] = {x0 * c.inv_dx, x1 * c.inv_dx, x2 * c.inv_dx};
+    const int mn[3] = {0, 0, c.z_off}, mx[3] = {c.num_grids - 1, c.num_grids - 1, c.z_off + c.nz - 1};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const int b = (int)(p[a] - 0.5f);
+      lo[a] = max(b, mn[a]);
+      hi[a] = min(b + 2, mx[a]);
+    }
+  }
+  if (threadIdx.x < 6) sbox[threadIdx.x] = threadIdx.x < 3 ? INT_MAX : INT_MIN;
+  __syncthreads();
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const int l = __reduce_min_sync(0xffffffffu, lo[a]);
+    const int h = __reduce_max_sync(0xffffffffu, hi[a]);
+    if ((threadIdx.x & 31) == 0) {
+      atomicMin(&sbox[a], l);
+      atomicMax(&sbox[3 + a], h);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) atomicMin(&box[threadIdx.x], sbox[threadIdx.x]);
+  else if (threadIdx.x < 6) atomicMax(&box[threadIdx.x], sbox[threadIdx.x]);
+}
+
+__global__ void __launch_bounds__(256)
+box_reduce_kernel(neuma_mpm_const c, int n, const float* __restrict__ x,
+                  const int* __restrict__ enabled, int32_t* __restrict__ box) {
+  __shared__ int sbox[6];
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = p < n && enabled[p] != 0;
+  float px[3] = {0.f, 0.f, 0.f};
+  if (active) { px[0] = x[3 * p]; px[1] = x[3 * p + 1]; px[2] = x[3 * p + 2]; }
+  box_accumulate(c, active, px[0], px[1], px[2], box, sbox);
+}
+
+// iteration space of the node passes: the box, x-range widened to 128-byte rows
+struct BoxIter {
+  int x0, nx, ny, y0, z0;
+  long long total;
+};
+__device__ __forceinline__ BoxIter box_iter(const neuma_mpm_const& c, const Box& b) {
+  BoxIter it;
+  if (b.lo[0] > b.hi[0] || b.lo[1] > b.hi[1] || b.lo[2] > b.hi[2]) {
+    it.total = 0; it.x0 = it.nx = it.ny = it.y0 = it.z0 = 0;
+    return it;
+  }
+  it.x0 = b.lo[0] & ~7;
+  const int x1 = min(c.num_grids - 1, b.hi[0] | 7);
+  it.nx = x1 - it.x0 + 1;
+  it.y0 = b.lo[1];
+  it.ny = b.hi[1] - b.lo[1] + 1;
+  it.z0 = b.lo[2];
+  it.total = (long long)it.nx * it.ny * (b.hi[2] - b.lo[2] + 1);
+  return it;
+}
+__device__ __forceinline__ size_t box_node(const neuma_mpm_const& c, const BoxIter& it, long long i,
+                                           int& ix, int& iy, int& iz) {
+  const int row = (int)(i / it.nx);
+  ix = it.x0 + (int)(i - (long long)row * it.nx);
+  const int pl = row / it.ny;
+  iy = it.y0 + (row - pl * it.ny);
+  iz = it.z0 + pl;
+  return node_index(c, ix, iy, iz);
+}
+
+// zero the box region of up to two grids; optionally reset another box to "empty"
+__global__ void __launch_bounds__(256)
+box_clear_kernel(neuma_mpm_const c, const int32_t* __restrict__ box, float4* __restrict__ g0,
+                 float4* __restrict__ g1, int32_t* __restrict__ box_reset) {
+  if (box_reset && blockIdx.x == 0 && threadIdx.x < 8)
+    box_reset[threadIdx.x] = threadIdx.x < 3 ? INT_MAX : (threadIdx.x < 6 ? INT_MIN : 0);
+  const BoxIter it = box_iter(c, load_box(box));
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < it.total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int ix, iy, iz;
+    const size_t ni = box_node(c, it, i, ix, iy, iz);
+    if (g0) g0[ni] = z;
+    if (g1) g1[ni] = z;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+p2g_to_kernel(neuma_mpm_const c, int n, const float* __restrict__ x, const float* __restrict__ v,
+              const float* __restrict__ C, const float* __restrict__ stress,
+              const float* __restrict__ vol, const float* __restrict__ rho,
+              const int* __restrict__ enabled, float4* __restrict__ grid) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  if (enabled[p] == 0) return;
+  p2g_particle(c, p, x, v, C, stress, vol[p], rho[p], grid);
+}
+
+constexpr uint32_t NEG_ZERO = 0x80000000u;
+
+// grid_op over the box, in place: (mv, m) -> (v, m); BC-zeroed components become -0.0f.
+// Optionally zeroes the same nodes of `adj` (the backward's scatter target).
+__global__ void __launch_bounds__(256)
+grid_op_box_kernel(neuma_mpm_const c, const int32_t* __restrict__ box, float4* __restrict__ grid,
+                   float4* __restrict__ adj) {
+  const BoxIter it = box_iter(c, load_box(box));
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < it.total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int ix, iy, iz;
+    const size_t ni = box_node(c, it, i, ix, iy, iz);
+    const float4 q = grid[ni];
+    float v[3], pass[3], inv_m, vp[3];
+    node_velocity(c, q, ix, iy, iz, v, pass, inv_m, vp);
+    if (q.w > 0.0f) {
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+        if (pass[a] == 0.0f) v[a] = __uint_as_float(NEG_ZERO);
+    }
+    grid[ni] = make_float4(v[0], v[1], v[2], q.w);
+    if (adj) adj[ni] = z;
+  }
+}
+
+// g2p from a (v, m) grid (mpm.py:432-498); optionally folds the new positions into the
+// next substep's box.
+template <bool WITH_BOX>
+__global__ void __launch_bounds__(256)
+g2p_from_kernel(neuma_mpm_const c, int n, const float* __restrict__ x, const float* __restrict__ F,
+                const float* __restrict__ clip, const int* __restrict__ enabled,
+                const float4* __restrict__ grid, float* __restrict__ x2, float* __restrict__ v2,
+                float* __restrict__ C2, float* __restrict__ F2, int32_t* __restrict__ box_next) {
+  __shared__ int sbox[6];
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = p < n && enabled[p] != 0;
+  float nx3[3] = {0.f, 0.f, 0.f};
+  if (active) {
+    const float px[3] = {x[3 * p], x[3 * p + 1], x[3 * p + 2]};
+    const Stencil s = make_stencil(px[0], px[1], px[2], c.inv_dx);
+    float nv[3] = {0.f, 0.f, 0.f};
+    float nC[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const float k4 = 4.0f * c.inv_dx * c.inv_dx;
+#pragma unroll
+    for (int kk = 0; kk < 3; ++kk)
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const int ix = s.b[0] + i, iy = s.b[1] + j, iz = s.b[2] + kk;
+          if (!node_in_range(c, ix, iy, iz)) continue;
+          const float4 q = grid[node_index(c, ix, iy, iz)];
+          const float gv[3] = {q.x, q.y, q.z};
+          const float d[3] = {((float)i - s.f[0]) * c.dx, ((float)j - s.f[1]) * c.dx,
+                              ((float)kk - s.f[2]) * c.dx};
+          const float w = s.w[0][i] * s.w[1][j] * s.w[2][kk];
+          const float w4 = k4 * w;
+#pragma unroll
+          for (int a = 0; a < 3; ++a) {
+            nv[a] += w * gv[a];
+#pragma unroll
+            for (int b = 0; b < 3; ++b) nC[3 * a + b] += w4 * (gv[a] * d[b]);
+          }
+        }
+    float Fo[9], Fn[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Fo[i] = F[9 * p + i];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b) {
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+          acc += ((a == k ? 1.0f : 0.0f) + c.dt * nC[3 * a + k]) * Fo[3 * k + b];
+        Fn[3 * a + b] = acc;
+      }
+    const float bnd = clip[p] * c.dx;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      float nx = px[a] + c.dt * nv[a];
+      nx = fminf(fmaxf(nx, 0.0f + bnd), 1.0f - bnd);
+      nx3[a] = nx;
+      x2[3 * p + a] = nx;
+      v2[3 * p + a] = nv[a];
+    }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      C2[9 * p + i] = nC[i];
+      F2[9 * p + i] = Fn[i];
+    }
+  }
+  if (WITH_BOX) box_accumulate(c, active, nx3[0], nx3[1], nx3[2], box_next, sbox);
+}
+
+// backward pass 1: scatter adj(G2P)'s dL/dv_node into adj (xyz; w unused)
+__global__ void __launch_bounds__(256)
+bwd_scatter_adj_kernel(neuma_mpm_const c, int n, const float* __restrict__ x,
+                       const float* __restrict__ F, const float* __restrict__ clip,
+                       const int* __restrict__ enabled, const float* __restrict__ v2,
+                       const float* __restrict__ gx2, const float* __restrict__ gv2,
+                       const float* __restrict__ gC2, const float* __restrict__ gF2,
+                       float4* __restrict__ gadj) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  if (enabled[p] == 0) return;
+  const G2PAdj g = g2p_adjoint_inputs(c, p, x, F, clip, v2, gx2, gv2, gC2, gF2);
+  const Stencil s = make_stencil(x[3 * p], x[3 * p + 1], x[3 * p + 2], c.inv_dx);
+  const float k4 = 4.0f * c.inv_dx * c.inv_dx;
+#pragma unroll
+  for (int kk = 0; kk < 3; ++kk)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const int ix = s.b[0] + i, iy = s.b[1] + j, iz = s.b[2] + kk;
+        if (!node_in_range(c, ix, iy, iz)) continue;
+        const float d[3] = {((float)i - s.f[0]) * c.dx, ((float)j - s.f[1]) * c.dx,
+                            ((float)kk - s.f[2]) * c.dx};
+        const float w = s.w[0][i] * s.w[1][j] * s.w[2][kk];
+        float o[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+          o[a] = w * (g.gvt[a] + k4 * (g.gCt[3 * a] * d[0] + g.gCt[3 * a + 1] * d[1] +
+                                       g.gCt[3 * a + 2] * d[2]));
+        red_add_f4(gadj + node_index(c, ix, iy, iz), o[0], o[1], o[2], 0.0f);
+      }
+}
+
+// backward pass 2, per node of the box: adj(grid_op).  (v, m) and dL/dv -> (dL/dmv, dL/dm),
+// in place in adj.   v = mv / (m + eps) + g dt  =>  dL/dmv = pass * gv / (m + eps),
+// dL/dm = -(mv / (m + eps)) . dL/dmv
+__global__ void __launch_bounds__(256)
+bwd_node_kernel(neuma_mpm_const c, const int32_t* __restrict__ box,
+                const float4* __restrict__ grid, float4* __restrict__ adj) {
+  const BoxIter it = box_iter(c, load_box(box));
+  const float gdt[3] = {c.gravity[0] * c.dt, c.gravity[1] * c.dt, c.gravity[2] * c.dt};
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < it.total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int ix, iy, iz;
+    const size_t ni = box_node(c, it, i, ix, iy, iz);
+    const float4 q = grid[ni];
+    const float4 ga = adj[ni];
+    const bool has = q.w > 0.0f;
+    const float inv_m = has ? 1.0f / (q.w + c.eps) : 0.0f;
+    const float v[3] = {q.x, q.y, q.z}, g[3] = {ga.x, ga.y, ga.z};
+    float gmv[3], gm = 0.f;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const bool pass = has && __float_as_uint(v[a]) != NEG_ZERO;
+      gmv[a] = pass ? g[a] * inv_m : 0.0f;
+      gm -= pass ? (v[a] - gdt[a]) * gmv[a] : 0.0f;
+    }
+    adj[ni] = make_float4(gmv[0], gmv[1], gmv[2], gm);
+  }
+}
+
+// backward pass 3, per particle: gather v_node and (dL/dmv, dL/dm) of its 27 nodes and
+// accumulate adj(G2P) (the terms that need v_node) and adj(P2G).
+template <bool HAVE_C2>
+__global__ void __launch_bounds__(128)
+bwd_gather_v_kernel(neuma_mpm_const c, int n, const float* __restrict__ x,
+                    const float* __restrict__ v, const float* __restrict__ C,
+                    const float* __restrict__ F, const float* __restrict__ stress,
+                    const float* __restrict__ vol, const float* __restrict__ rho,
+                    const float* __restrict__ clip, const int* __restrict__ enabled,
+                    const float* __restrict__ v2, const float* __restrict__ C2,
+                    const float* __restrict__ gx2, const float* __restrict__ gv2,
+                    const float* __restrict__ gC2, const float* __restrict__ gF2,
+                    const float4* __restrict__ grid, const float4* __restrict__ gadj,
+                    float* __restrict__ gx, float* __restrict__ gv, float* __restrict__ gC,
+                    float* __restrict__ gF, float* __restrict__ gstress) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  if (enabled[p] == 0) {
+    if (gx) for (int a = 0; a < 3; ++a) gx[3 * p + a] = 0.f;
+    if (gv) for (int a = 0; a < 3; ++a) gv[3 * p + a] = 0.f;
+    if (gC) for (int a = 0; a < 9; ++a) gC[9 * p + a] = 0.f;
+    if (gF) for (int a = 0; a < 9; ++a) gF[9 * p + a] = 0.f;
+    if (gstress) for (int a = 0; a < 9; ++a) gstress[9 * p + a] = 0.f;
+    return;
+  }
+  const float p_vol = vol[p];
+  const float p_mass = p_vol * rho[p];
+  const Stencil s = make_stencil(x[3 * p], x[3 * p + 1], x[3 * p + 2], c.inv_dx);
+  const float ks = -c.dt * p_vol * 4.0f * c.inv_dx * c.inv_dx;
+  const float k4 = 4.0f * c.inv_dx * c.inv_dx;
+  float A[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) A[i] = ks * stress[9 * p + i] + p_mass * C[9 * p + i];
+  const float pv[3] = {p_mass * v[3 * p], p_mass * v[3 * p + 1], p_mass * v[3 * p + 2]};
+  const G2PAdj g = g2p_adjoint_inputs(c, p, x, F, clip, v2, gx2, gv2, gC2, gF2);
+
+  float acc_gmv[3] = {0.f, 0.f, 0.f};
+  float gA[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float gd[3] = {0.f, 0.f, 0.f};
+  float gw[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+  float nC[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int kk = 0; kk < 3; ++kk)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const int ix = s.b[0] + i, iy = s.b[1] + j, iz = s.b[2] + kk;
+        if (!node_in_range(c, ix, iy, iz)) continue;
+        const size_t ni = node_index(c, ix, iy, iz);
+        const float4 q = grid[ni];
+        const float4 ga = gadj[ni];
+        const float vn[3] = {q.x, q.y, q.z};
+        const float gmv[3] = {ga.x, ga.y, ga.z};
+        const float gm = ga.w;
+        const float d[3] = {((float)i - s.f[0]) * c.dx, ((float)j - s.f[1]) * c.dx,
+                            ((float)kk - s.f[2]) * c.dx};
+        const float w = s.w[0][i] * s.w[1][j] * s.w[2][kk];
+        float gCt_d[3], gCtT_v[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          gCt_d[a] = g.gCt[3 * a] * d[0] + g.gCt[3 * a + 1] * d[1] + g.gCt[3 * a + 2] * d[2];
+          gCtT_v[a] = g.gCt[a] * vn[0] + g.gCt[3 + a] * vn[1] + g.gCt[6 + a] * vn[2];
+        }
+        float gW = vn[0] * g.gvt[0] + vn[1] * g.gvt[1] + vn[2] * g.gvt[2] +
+                   k4 * (vn[0] * gCt_d[0] + vn[1] * gCt_d[1] + vn[2] * gCt_d[2]);
+        float Ad[3], ATg[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          Ad[a] = A[3 * a] * d[0] + A[3 * a + 1] * d[1] + A[3 * a + 2] * d[2];
+          ATg[a] = A[a] * gmv[0] + A[3 + a] * gmv[1] + A[6 + a] * gmv[2];
+        }
+        gW += gmv[0] * (pv[0] + Ad[0]) + gmv[1] * (pv[1] + Ad[1]) + gmv[2] * (pv[2] + Ad[2]) +
+              gm * p_mass;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          acc_gmv[a] += w * gmv[a];
+          gd[a] += w * (k4 * gCtT_v[a] + ATg[a]);
+#pragma unroll
+          for (int b = 0; b < 3; ++b) {
+            gA[3 * a + b] += w * (gmv[a] * d[b]);
+            if (!HAVE_C2) nC[3 * a + b] += (k4 * w) * (vn[a] * d[b]);
+          }
+        }
+        gw[0][i] += gW * (s.w[1][j] * s.w[2][kk]);
+        gw[1][j] += gW * (s.w[0][i] * s.w[2][kk]);
+        gw[2][kk] += gW * (s.w[0][i] * s.w[1][j]);
+      }
+  if (gx) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const float f = s.f[a];
+      float gf = gw[a][0] * (-(1.5f - f)) + gw[a][1] * (-2.0f * (f - 1.0f)) + gw[a][2] * (f - 0.5f);
+      gf -= c.dx * gd[a];
+      gx[3 * p + a] = finite_or_zero(g.gxn[a] + c.inv_dx * gf);
+    }
+  }
+  if (gv) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) gv[3 * p + a] = finite_or_zero(p_mass * acc_gmv[a]);
+  }
+  if (gC) {
+#pragma unroll
+    for (int a = 0; a < 9; ++a) gC[9 * p + a] = finite_or_zero(p_mass * gA[a]);
+  }
+  if (gstress) {
+#pragma unroll
+    for (int a = 0; a < 9; ++a) gstress[9 * p + a] = finite_or_zero(ks * gA[a]);
+  }
+  if (gF) {
+    if (HAVE_C2) {
+#pragma unroll
+      for (int a = 0; a < 9; ++a) nC[a] = C2[9 * p + a];
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b) {
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+          acc += ((a == k ? 1.0f : 0.0f) + c.dt * nC[3 * k + a]) * gF2[9 * p + 3 * k + b];
+        gF[9 * p + 3 * a + b] = finite_or_zero(acc);
+      }
+  }
+}
+
+// ------------------------------------------------------------------ cell order
+__device__ __forceinline__ uint32_t spread3(uint32_t v) {  // 10 bits -> every third bit
+  v &= 0x3FFu;
+  v = (v | (v << 16)) & 0x030000FFu;
+  v = (v | (v << 8)) & 0x0300F00Fu;
+  v = (v | (v << 4)) & 0x030C30C3u;
+  v = (v | (v << 2)) & 0x09249249u;
+  return v;
+}
+__global__ void __launch_bounds__(256)
+cell_key_kernel(neuma_mpm_const c, int n, const float* __restrict__ x, uint32_t* __restrict__ keys,
+                int32_t* __restrict__ ids) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  uint32_t b[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const int t = (int)(x[3 * p + a] * c.inv_dx - 0.5f);
+    b[a] = (uint32_t)min(max(t, 0), 1023);
+  }
+  // z is the slowest grid axis: give it the most significant interleaved bit
+  keys[p] = spread3(b[0]) | (spread3(b[1]) << 1) | (spread3(b[2]) << 2);
+  ids[p] = p;
+}
+
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(int n, int words, const uint32_t* __restrict__ src, const int32_t* __restrict__ idx,
+                   uint32_t* __restrict__ dst) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)n * words) return;
+  const int r = (int)(t / words), w = (int)(t - (long long)r * words);
+  dst[t] = src[(size_t)idx[r] * words + w];
+}
+__global__ void __launch_bounds__(256)
+invert_perm_kernel(int n, const int32_t* __restrict__ perm, int32_t* __restrict__ inv) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) inv[perm[i]] = i;
+}
+
+inline int node_pass_blocks(neuma_ctx* ctx) { return ctx->num_sms * 8; }
+
+int check_slab(neuma_ctx* ctx, const neuma_mpm_const* c) {
+  if (!ctx || !c) return 2;
+  if (c->num_grids <= 0 || c->nz <= 0 || c->z_off < 0 || c->z_off + c->nz > c->num_grids + 4)
+    return neuma_fail_msg(ctx, "neuma_mpm: bad grid extents");
+  if (c->bc != 0 && c->bc != 1) return neuma_fail_msg(ctx, "neuma_mpm: bc must be 0 or 1");
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int neuma_mpm_box_from_x(neuma_ctx* ctx, const neuma_mpm_const* c, int n, const float* x,
+                         const int32_t* enabled, int32_t* box, void* stream) {
+  if (int r = check_slab(ctx, c)) return r;
+  cudaStream_t st = (cudaStream_t)stream;
+  box_init_kernel<<<1, 32, 0, st>>>(box);
+  NEUMA_LAUNCH_CHECK(ctx, "box_init_kernel");
+  if (n <= 0) return 0;
+  box_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(*c, n, x, enabled, box);
+  NEUMA_LAUNCH_CHECK(ctx, "box_reduce_kernel");
+  return 0;
+}
+
+int neuma_mpm_box_clear(neuma_ctx* ctx, const neuma_mpm_const* c, const int32_t* box, float* grid0,
+                        float* grid1, int32_t* box_reset, void* stream) {
+  if (int r = check_slab(ctx, c)) return r;
+  box_clear_kernel<<<node_pass_blocks(ctx), 256, 0, (cudaStream_t)stream>>>(
+      *c, box, (float4*)grid0, (float4*)grid1, box_reset);
+  NEUMA_LAUNCH_CHECK(ctx, "box_clear_kernel");
+  return 0;
+}
+
+int neuma_mpm_p2g_to(neuma_ctx* ctx, const neuma_mpm_const* c, int n, const float* x, const float* v,
+                     const float* C, const float* stress, const float* vol, const float* rho,
+                     const int32_t* enabled, float* grid, void* stream) {
+  if (int r = check_slab(ctx, c)) return r;
+  if (n <= 0) return 0;
+  p2g_to_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(*c, n, x, v, C, stress, vol, rho,
+                                                                    enabled, (float4*)grid);
+  NEUMA_LAUNCH_CHECK(ctx, "p2g_to_kernel");
+  return 0;
+}
+
+int neuma_mpm_grid_op_box(neuma_ctx* ctx, const neuma_mpm_const* c, const int32_t* box, float* grid,
+                          float* adj_to_clear, void* stream) {
+  if (int r = check_slab(ctx, c)) return r;
+  grid_op_box_kernel<<<node_pass_blocks(ctx), 256, 0, (cudaStream_t)stream>>>(
+      *c, box, (float4*)grid, (float4*)adj_to_clear);
+  NEUMA_LAUNCH_CHECK(ctx, "grid_op_box_kernel");
+  return 0;
+}
+
+int neuma_mpm_g2p_from(neuma_ctx* ctx, const neuma_mpm_const* c, int n, const float* x,
+                       const float* F, const float* clip_bound, const int32_t* enabled,
+                       const float* grid_v, float* x2, float* v2, float* C2, float* F2,
+                       int32_t* box_next, void* stream) {
+  if (int r = check_slab(ctx, c)) return r;
+  if (n <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (box_next)
+    g2p_from_kernel<true><<<(n + 255) / 256, 256, 0, st>>>(*c, n, x, F, clip_bound, enabled,
+                                                           (const float4*)grid_v, x2, v2, C2, F2,
+                                                           box_next);
+  else
+    g2p_from_kernel<false><<<(n + 255) / 256, 256, 0, st>>>(*c, n, x, F, clip_bound, enabled,
+                                                            (const float4*)grid_v, x2, v2, C2, F2,
+                                                            nullptr);
+  NEUMA_LAUNCH_CHECK(ctx, "g2p_from_kernel");
+  return 0;
+}
+
+int neuma_mpm_rollout_fwd(neuma_ctx* ctx, const neuma_mpm_const* c, int n, const float* x,
+                          const float* v, const float* C, const float* F, const float* stress,
+                          const float* vol, const float* rho, const float* clip_bound,
+                          const int32_t* enabled, float* x2, float* v2, float* C2, float* F2,
+                          float* grid, float* adj, const int32_t* box, int32_t* box_next,
+                          void* stream) {
+  if (!grid || !box) return neuma_fail_msg(ctx, "neuma_mpm_rollout_fwd: grid and box are required");
+  if (int r = neuma_mpm_box_clear(ctx, c, box, grid, nullptr, box_next, stream)) return r;
+  if (int r = neuma_mpm_p2g_to(ctx, c, n, x, v, C, stress, vol, rho, enabled, grid, stream)) return r;
+  if (int r = neuma_mpm_grid_op_box(ctx, c, box, grid, adj, stream)) return r;
+  return neuma_mpm_g2p_from(ctx, c, n, x, F, clip_bound, enabled, grid, x2, v2, C2, F2, box_next,
+                            stream);
+}
+
+int neuma_mpm_rollout_bwd(neuma_ctx* ctx, const neuma_mpm_const* c, int n, const float* x,
+                          const float* v, const float* C, const float* F, const float* stress,
+                          const float* vol, const float* rho, const float* clip_bound,
+                          const int32_t* enabled, const float* v2, const float* C2,
+                          const float* gx2, const float* gv2, const float* gC2, const float* gF2,
+                          const float* grid_v, float* adj, const int32_t* box, float* gx, float* gv,
+                          float* gC, float* gF, float* gstress, void* stream) {
+  if (int r = check_slab(ctx, c)) return r;
+  if (n <= 0) return 0;
+  if (!v2 || !gx2 || !gv2 || !gC2 || !gF2 || !grid_v || !adj || !box)
+    return neuma_fail_msg(ctx, "neuma_mpm_rollout_bwd: NULL argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  bwd_scatter_adj_kernel<<<(n + 255) / 256, 256, 0, st>>>(*c, n, x, F, clip_bound, enabled, v2, gx2,
+                                                          gv2, gC2, gF2, (float4*)adj);
+  NEUMA_LAUNCH_CHECK(ctx, "bwd_scatter_adj_kernel");
+  bwd_node_kernel<<<node_pass_blocks(ctx), 256, 0, st>>>(*c, box, (const float4*)grid_v, (float4*)adj);
+  NEUMA_LAUNCH_CHECK(ctx, "bwd_node_kernel");
+  if (C2)
+    bwd_gather_v_kernel<true><<<(n + 127) / 128, 128, 0, st>>>(
+        *c, n, x, v, C, F, stress, vol, rho, clip_bound, enabled, v2, C2, gx2, gv2, gC2, gF2,
+        (const float4*)grid_v, (const float4*)adj, gx, gv, gC, gF, gstress);
+  else
+    bwd_gather_v_kernel<false><<<(n + 127) / 128, 128, 0, st>>>(
+        *c, n, x, v, C, F, stress, vol, rho, clip_bound, enabled, v2, C2, gx2, gv2, gC2, gF2,
+        (const float4*)grid_v, (const float4*)adj, gx, gv, gC, gF, gstress);
+  NEUMA_LAUNCH_CHECK(ctx, "bwd_gather_v_kernel");
+  return 0;
+}
+
+int neuma_mpm_cell_order(neuma_ctx* ctx, const neuma_mpm_const* c, int n, const float* x,
+                         int32_t* perm, void* stream) {
+  if (int r = check_slab(ctx, c)) return r;
+  if (n <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  int bits = 1;
+  while ((1 << bits) < c->num_grids && bits < 10) ++bits;
+  size_t temp = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, temp, (const uint32_t*)nullptr, (uint32_t*)nullptr,
+                                  (const int32_t*)nullptr, (int32_t*)nullptr, n, 0, 3 * bits, st);
+  const size_t karr = ((size_t)n * 4 + 255) & ~(size_t)255;
+  if (int r = neuma_ensure_scratch(ctx, 3 * karr + temp)) return r;
+  uint8_t* base = (uint8_t*)ctx->scratch;
+  uint32_t* keys = (uint32_t*)base;
+  uint32_t* keys2 = (uint32_t*)(base + karr);
+  int32_t* ids = (int32_t*)(base + 2 * karr);
+  cell_key_kernel<<<(n + 255) / 256, 256, 0, st>>>(*c, n, x, keys, ids);
+  NEUMA_LAUNCH_CHECK(ctx, "cell_key_kernel");
+  NEUMA_CUDA(ctx, cub::DeviceRadixSort::SortPairs(base + 3 * karr, temp, keys, keys2, ids, perm, n, 0,
+                                                  3 * bits, st));
+  ctx->launches += 3;
+  return 0;
+}
+
+int neuma_gather_rows(neuma_ctx* ctx, int n, int words_per_row, const void* src, const int32_t* idx,
+                      void* dst, void* stream) {
+  if (!ctx) return 2;
+  if (n <= 0 || words_per_row <= 0) return 0;
+  const long long total = (long long)n * words_per_row;
+  gather_rows_kernel<<<(int)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      n, words_per_row, (const uint32_t*)src, idx, (uint32_t*)dst);
+  NEUMA_LAUNCH_CHECK(ctx, "gather_rows_kernel");
+  return 0;
+}
+
+int neuma_invert_perm(neuma_ctx* ctx, int n, const int32_t* perm, int32_t* inv, void* stream) {
+  if (!ctx) return 2;
+  if (n <= 0) return 0;
+  invert_perm_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n, perm, inv);
+  NEUMA_LAUNCH_CHECK(ctx, "invert_perm_kernel");
+  return 0;
+}
+
+}  // extern "C"

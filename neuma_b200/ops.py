@@ -283,3 +283,71 @@ def mpm_substep_bwd_into(c: MPMConstC, x, v, Cm, F, stress, vol, rho, clip_bound
                  ptr(stress), ptr(vol), ptr(rho), ptr(clip_bound), ptr(enabled), ptr(v2),
                  ptr(gx2), ptr(gv2), ptr(gC2), ptr(gF2), ptr(gx), ptr(gv), ptr(gC), ptr(gF), ptr(gstress),
                  _stream(x))
+
+
+# --------------------------------------------------------------------- MPM rollout path
+# (caller-owned per-substep grids + device-side bounding boxes; see include/neuma_b200.h)
+def mpm_box_from_x(c: MPMConstC, x, enabled, box) -> None:
+    _ctx(x).call("neuma_mpm_box_from_x", C.byref(c), x.shape[0], ptr(x), ptr(enabled), ptr(box), _stream(x))
+
+
+def mpm_box_clear(c: MPMConstC, box, grid0=None, grid1=None, box_reset=None) -> None:
+    _ctx(box).call("neuma_mpm_box_clear", C.byref(c), ptr(box), ptr(grid0), ptr(grid1), ptr(box_reset),
+                   _stream(box))
+
+
+def mpm_p2g_to(c: MPMConstC, x, v, Cm, stress, vol, rho, enabled, grid) -> None:
+    _ctx(x).call("neuma_mpm_p2g_to", C.byref(c), x.shape[0], ptr(x), ptr(v), ptr(Cm), ptr(stress),
+                 ptr(vol), ptr(rho), ptr(enabled), ptr(grid), _stream(x))
+
+
+def mpm_grid_op_box(c: MPMConstC, box, grid, adj_to_clear=None) -> None:
+    _ctx(grid).call("neuma_mpm_grid_op_box", C.byref(c), ptr(box), ptr(grid), ptr(adj_to_clear), _stream(grid))
+
+
+def mpm_g2p_from(c: MPMConstC, x, F, clip_bound, enabled, grid_v, out, box_next=None) -> None:
+    x2, v2, C2, F2 = out
+    _ctx(x).call("neuma_mpm_g2p_from", C.byref(c), x.shape[0], ptr(x), ptr(F), ptr(clip_bound), ptr(enabled),
+                 ptr(grid_v), ptr(x2), ptr(v2), ptr(C2), ptr(F2), ptr(box_next), _stream(x))
+
+
+def mpm_rollout_fwd(c: MPMConstC, x, v, Cm, F, stress, vol, rho, clip_bound, enabled, out, grid, adj, box,
+                    box_next) -> None:
+    x2, v2, C2, F2 = out
+    _ctx(x).call("neuma_mpm_rollout_fwd", C.byref(c), x.shape[0], ptr(x), ptr(v), ptr(Cm), ptr(F), ptr(stress),
+                 ptr(vol), ptr(rho), ptr(clip_bound), ptr(enabled), ptr(x2), ptr(v2), ptr(C2), ptr(F2),
+                 ptr(grid), ptr(adj), ptr(box), ptr(box_next), _stream(x))
+
+
+def mpm_rollout_bwd(c: MPMConstC, x, v, Cm, F, stress, vol, rho, clip_bound, enabled, v2, C2, gx2, gv2, gC2, gF2,
+                    grid_v, adj, box, gx, gv, gC, gF, gstress) -> None:
+    _ctx(x).call("neuma_mpm_rollout_bwd", C.byref(c), x.shape[0], ptr(x), ptr(v), ptr(Cm), ptr(F), ptr(stress),
+                 ptr(vol), ptr(rho), ptr(clip_bound), ptr(enabled), ptr(v2), ptr(C2), ptr(gx2), ptr(gv2),
+                 ptr(gC2), ptr(gF2), ptr(grid_v), ptr(adj), ptr(box), ptr(gx), ptr(gv), ptr(gC), ptr(gF),
+                 ptr(gstress), _stream(x))
+
+
+def mpm_cell_order(c: MPMConstC, x: torch.Tensor) -> torch.Tensor:
+    """perm (int32[n]): particle indices in cell (Morton) order of their stencil base."""
+    x = _f32(x)
+    perm = torch.empty(x.shape[0], device=x.device, dtype=torch.int32)
+    _ctx(x).call("neuma_mpm_cell_order", C.byref(c), x.shape[0], ptr(x), ptr(perm), _stream(x))
+    return perm
+
+
+def gather_rows(src: torch.Tensor, idx: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[i] = src[idx[i]] for contiguous 32-bit rows (fp32 / int32)."""
+    if src.element_size() != 4 or not src.is_contiguous():
+        raise NeumaError("gather_rows: contiguous 32-bit rows expected")
+    n = idx.shape[0]
+    if out is None:
+        out = torch.empty((n,) + tuple(src.shape[1:]), device=src.device, dtype=src.dtype)
+    words = int(src.numel() // max(src.shape[0], 1))
+    _ctx(src).call("neuma_gather_rows", n, words, ptr(src), ptr(idx), ptr(out), _stream(src))
+    return out
+
+
+def invert_perm(perm: torch.Tensor) -> torch.Tensor:
+    inv = torch.empty_like(perm)
+    _ctx(perm).call("neuma_invert_perm", perm.shape[0], ptr(perm), ptr(inv), _stream(perm))
+    return inv

@@ -12,6 +12,12 @@ the same kernels with the Python/autograd overhead removed:
     modules/nclaw/sim/interface.py:108-123; SURVEY 8f.1);
   * the S-substep forward and the S-substep backward are each captured once into a
     CUDA graph (static buffers) and replayed;
+  * the MPM substeps run the rollout path of the library (csrc/mpm_rollout.cu): particles
+    are put in cell (Morton) order at load_state(), every substep keeps its own packed grid
+    (S x G^3 x 16 B, plus as much again for the adjoint scatter target) so the backward
+    reads the forward's grid instead of re-running P2G, and clears / node passes touch only
+    the device-side bounding box of the occupied nodes.  Everything this class returns or
+    accepts is in the CALLER's particle order;
   * LoRA is handled by the caller: the engine takes merged weights and returns
     dL/dW_eff (see neuma_b200.material for the un-merge).
 """
@@ -29,10 +35,15 @@ class FusedFrame:
     def __init__(self, n: int, cconst, statics, We: Sequence[torch.Tensor], Wp: Sequence[torch.Tensor],
                  alpha: float, substeps: int, device, bind=None, gaussians=None,
                  settings: Optional[RasterSettingsC] = None, center=None, size=None,
-                 elastic_kind: int = ops.KIND_ELASTIC, use_graphs: bool = True):
+                 elastic_kind: int = ops.KIND_ELASTIC, use_graphs: bool = True, sort: bool = True):
         self.n, self.S, self.dev = int(n), int(substeps), device
         self.c = cconst
-        self.vol, self.rho, self.clip, self.enabled = statics
+        self._statics_in = tuple(t.contiguous() for t in statics)
+        # statics in the engine's (cell-sorted) particle order; refreshed by load_state()
+        self.vol, self.rho, self.clip, self.enabled = [t.clone() for t in self._statics_in]
+        self.sort = bool(sort)
+        self.perm = torch.arange(n, device=device, dtype=torch.int32)   # sorted slot -> caller index
+        self.inv = self.perm.clone()                                    # caller index -> sorted slot
         self.We = [w.detach().contiguous() for w in We]
         self.Wp = [w.detach().contiguous() for w in Wp]
         self.alpha = float(alpha)
@@ -60,6 +71,11 @@ class FusedFrame:
         self.use_graphs = use_graphs
         self._g_fwd = self._g_bwd = None
         self._ctx = ops._ctx(self.x)
+        # per-substep packed grids ((mv, m) -> (v, m) in place), adjoint scatter targets, boxes
+        nodes = cconst.nz * cconst.num_grids * cconst.num_grids
+        self.grid = torch.empty(S, nodes, 4, **f)
+        self.adj = torch.empty(S, nodes, 4, **f)
+        self.box = torch.zeros(S + 1, 8, device=device, dtype=torch.int32)
 
     # ------------------------------------------------------------------ sim
     def _sim_forward(self) -> None:
@@ -67,9 +83,10 @@ class FusedFrame:
         for s in range(self.S):
             ctx = self._ctx
             ops.constitutive_fwd_into(self.kind_e, self.F[s], *self.We, 0.0, self.stress[s])
-            ops.mpm_substep_fwd(c, self.x[s], self.v[s], self.C[s], self.F[s], self.stress[s], self.vol, self.rho,
+            ops.mpm_rollout_fwd(c, self.x[s], self.v[s], self.C[s], self.F[s], self.stress[s], self.vol, self.rho,
                                 self.clip, self.enabled,
-                                out=(self.x[s + 1], self.v[s + 1], self.C[s + 1], self.Ftrial[s]))
+                                (self.x[s + 1], self.v[s + 1], self.C[s + 1], self.Ftrial[s]),
+                                self.grid[s], self.adj[s], self.box[s], self.box[s + 1])
             ops.constitutive_fwd_into(ops.KIND_PLASTIC, self.Ftrial[s], *self.Wp, self.alpha, self.F[s + 1])
 
     def _sim_backward(self) -> None:
@@ -83,9 +100,10 @@ class FusedFrame:
             ops.constitutive_bwd_into(ops.KIND_PLASTIC, self.Ftrial[s], *self.Wp, self.alpha, gF_next,
                                       self.gFtrial, *self.gWp)
             gx, gv, gC, gF = self.g[nxt]
-            ops.mpm_substep_bwd_into(c, self.x[s], self.v[s], self.C[s], self.F[s], self.stress[s], self.vol,
-                                     self.rho, self.clip, self.enabled, self.v[s + 1],
-                                     gx2, gv2, gC2, self.gFtrial, gx, gv, gC, gF, self.gstress)
+            ops.mpm_rollout_bwd(c, self.x[s], self.v[s], self.C[s], self.F[s], self.stress[s], self.vol,
+                                self.rho, self.clip, self.enabled, self.v[s + 1], self.C[s + 1],
+                                gx2, gv2, gC2, self.gFtrial, self.grid[s], self.adj[s], self.box[s],
+                                gx, gv, gC, gF, self.gstress)
             # elasticity: stress[s] = E(F[s]);  dL/dF[s] += E'(F[s])^T gstress
             ops.constitutive_bwd_into(self.kind_e, self.F[s], *self.We, 0.0, self.gstress, self.gF_e, *self.gWe)
             gF.add_(self.gF_e)
@@ -108,29 +126,51 @@ class FusedFrame:
         return graph
 
     def load_state(self, x, v, C, F) -> None:
-        self.x[0].copy_(x, non_blocking=True)
-        self.v[0].copy_(v, non_blocking=True)
-        self.C[0].copy_(C, non_blocking=True)
-        self.F[0].copy_(F, non_blocking=True)
+        """State at the start of the frame, in the caller's particle order (device or pinned
+        host tensors).  Re-sorts the particles by cell and recomputes the node box."""
+        dev = self.dev
+        x, v, C, F = [t.to(dev, non_blocking=True).contiguous() for t in (x, v, C, F)]
+        if self.sort:
+            self.perm.copy_(ops.mpm_cell_order(self.c, x))
+            self.inv.copy_(ops.invert_perm(self.perm))
+            for dst, src in ((self.x[0], x), (self.v[0], v), (self.C[0], C), (self.F[0], F),
+                             (self.vol, self._statics_in[0]), (self.rho, self._statics_in[1]),
+                             (self.clip, self._statics_in[2]), (self.enabled, self._statics_in[3])):
+                ops.gather_rows(src, self.perm, out=dst)
+        else:
+            self.x[0].copy_(x)
+            self.v[0].copy_(v)
+            self.C[0].copy_(C)
+            self.F[0].copy_(F)
+        ops.mpm_box_from_x(self.c, self.x[0], self.enabled, self.box[0])
+
+    def _to_caller(self, t: torch.Tensor) -> torch.Tensor:
+        return ops.gather_rows(t, self.inv) if self.sort else t
+
+    def _to_sorted(self, t: torch.Tensor, out=None) -> torch.Tensor:
+        if self.sort:
+            return ops.gather_rows(t.contiguous(), self.perm, out=out)
+        if out is not None:
+            out.copy_(t)
+            return out
+        return t
 
     def sim_forward(self):
         if not self.use_graphs:
             self._sim_forward()
         else:
             if self._g_fwd is None:
-                keep = [t[0].clone() for t in (self.x, self.v, self.C, self.F)]
-                self._g_fwd = self._capture(self._sim_forward)
-                self.load_state(*keep)
+                self._g_fwd = self._capture(self._sim_forward)   # slot 0 (state, box) is read-only: replay-safe
             self._g_fwd.replay()
         S = self.S
-        return self.x[S], self.v[S], self.C[S], self.F[S]
+        return tuple(self._to_caller(t[S]) for t in (self.x, self.v, self.C, self.F))
 
     def sim_backward(self, gx, gv, gC, gF):
         for dst, src in zip(self.g[0], (gx, gv, gC, gF)):
             if src is None:
                 dst.zero_()
             else:
-                dst.copy_(src)
+                self._to_sorted(src, out=dst)
         if not self.use_graphs:
             self._sim_backward()
         else:
@@ -143,7 +183,7 @@ class FusedFrame:
                 for dst, src in zip(self.gWe + self.gWp, keep_w):
                     dst.copy_(src)
             self._g_bwd.replay()
-        return self.g[0]
+        return [self._to_caller(t) for t in self.g[0]]
 
     def zero_weight_grads(self) -> None:
         for t in self.gWe + self.gWp:
@@ -153,10 +193,10 @@ class FusedFrame:
     def render_forward(self, de_x_prev: torch.Tensor, k_prev: torch.Tensor):
         """bindings + covariance deformation + rasterization of the frame's final state."""
         b, gs, S = self.bind, self.gs, self.S
-        de_x = (self.x[S] - self.center) / self.size
+        de_x = (self._to_caller(self.x[S]) - self.center) / self.size
         self._delta = de_x - de_x_prev
         means3D = k_prev + ops.bind_spmm(b.rowptr, b.col, b.w, self._delta, self.n)
-        Fk = ops.bind_spmm(b.rowptr, b.col, b.w, self.F[S].reshape(self.n, 9), self.n)
+        Fk = ops.bind_spmm(b.rowptr, b.col, b.w, self._to_caller(self.F[S]).reshape(self.n, 9), self.n)
         cov = ops.deform_cov(gs["cov6"], Fk)
         image, radii = ops.raster_fwd(self.settings, means3D, gs["shs"], None, gs["opac"], cov)
         self._render_saved = (means3D, cov, radii)

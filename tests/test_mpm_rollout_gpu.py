@@ -1,0 +1,147 @@
+"""GPU parity of the rollout MPM path (csrc/mpm_rollout.cu: per-substep grids, device-side
+node boxes, in-place grid_op, cell-ordered particles) against the CPU oracle, through the C ABI."""
+import pytest
+import torch
+
+from oracle import mpm_oracle as O
+from util import make_cloud, rel_err
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4  # north_star: particle x/v/F within 1e-4 rel fp32
+
+
+def _dev(d, dev):
+    return {k: t.to(dev) for k, t in d.items()}
+
+
+def _consts(G, dt, bc, eps=6e-7, gravity=(0.0, -9.8, 0.0), bound=1):
+    from neuma_b200 import ops
+    return (O.MPMConst(num_grids=G, dt=dt, bound=bound, gravity=gravity, eps=eps, bc=bc),
+            ops.mpm_const(G, dt, bound, gravity, eps, bc))
+
+
+def _buffers(G, dev, slots=1):
+    grid = torch.full((slots, G ** 3, 4), float("nan"), device=dev)     # stale garbage outside the box
+    adj = torch.full((slots, G ** 3, 4), float("nan"), device=dev)
+    box = torch.zeros(slots + 1, 8, dtype=torch.int32, device=dev)
+    return grid, adj, box
+
+
+@pytest.mark.parametrize("n,G,bc,lo,hi", [(5000, 32, "noslip", 0.3, 0.7), (20000, 64, "freeslip", 0.3, 0.7),
+                                          (3000, 16, "noslip", 0.02, 0.98), (3000, 16, "freeslip", 0.02, 0.98),
+                                          (333, 16, "noslip", 0.4, 0.45)])
+def test_rollout_fwd_bwd_vs_oracle(cuda_dev, n, G, bc, lo, hi):
+    """clouds touching the walls exercise the BC -0.0f marker and the box clamping"""
+    from neuma_b200 import ops
+    co, cc = _consts(G, 1e-3, bc)
+    d = make_cloud(n, G, seed=5 + n, lo=lo, hi=hi, disabled_frac=0.05)
+    # keep the reference's latent out-of-range write out of the test
+    d["x"].clamp_(max=1 - 1.6 / G)
+    g = _dev(d, cuda_dev)
+    grid, adj, box = _buffers(G, cuda_dev)
+    ops.mpm_box_from_x(cc, g["x"], g["enabled"], box[0])
+    out = tuple(torch.empty_like(g[k]) for k in ("x", "v", "C", "F"))
+    ops.mpm_rollout_fwd(cc, g["x"], g["v"], g["C"], g["F"], g["stress"], g["vol"], g["rho"], g["clip"],
+                        g["enabled"], out, grid[0], adj[0], box[0], box[1])
+    d64 = {k: (t.double() if t.is_floating_point() else t) for k, t in d.items()}
+    o = O.substep_fwd(co, d64["x"], d64["v"], d64["C"], d64["F"], d64["stress"], d64["vol"],
+                      d64["rho"], d64["clip"], d["enabled"])
+    on = d["enabled"] != 0
+    for a, b, name in zip(out, o, "xvCF"):
+        assert rel_err(a.cpu()[on], b[on]) < RTOL, name
+    # the box handed to the next substep is the exact node box of the new positions
+    box_ref = torch.zeros(8, dtype=torch.int32, device=cuda_dev)
+    ops.mpm_box_from_x(cc, out[0], g["enabled"], box_ref)
+    assert torch.equal(box[1], box_ref)
+    base = (o[0][on] * G - 0.5).to(torch.int64)                      # trunc toward zero
+    lo_ref = base.min(0).values.clamp(min=0)
+    hi_ref = (base.max(0).values + 2).clamp(max=G - 1)
+    assert box_ref[:3].cpu().tolist() == lo_ref.tolist() and box_ref[3:6].cpu().tolist() == hi_ref.tolist()
+
+    gen = torch.Generator().manual_seed(11)
+    gouts = [torch.randn(n, 3, generator=gen), torch.randn(n, 3, generator=gen),
+             torch.randn(n, 3, 3, generator=gen), torch.randn(n, 3, 3, generator=gen)]
+    og = O.substep_bwd(co, d["x"], d["v"], d["C"], d["F"], d["stress"], d64["vol"], d64["rho"],
+                       d64["clip"], d["enabled"], *gouts)
+    for with_c2 in (True, False):
+        if not with_c2:   # adj was consumed by the first backward: zero it over the box again
+            ops.mpm_box_clear(cc, box[0], adj[0])
+        grads = [torch.empty_like(g[k]) for k in ("x", "v", "C", "F", "stress")]
+        ops.mpm_rollout_bwd(cc, g["x"], g["v"], g["C"], g["F"], g["stress"], g["vol"], g["rho"], g["clip"],
+                            g["enabled"], out[1], out[2] if with_c2 else None,
+                            *[t.to(cuda_dev) for t in gouts], grid[0], adj[0], box[0], *grads)
+        for a, b, name in zip(grads, og, ["gx", "gv", "gC", "gF", "gstress"]):
+            assert rel_err(a, b) < 5e-4, name  # fp32 atomics vs fp64 autograd
+            assert torch.all(a[~on.to(cuda_dev)] == 0)
+
+
+def test_rollout_matches_substep_entry_points(cuda_dev):
+    """same library, the two paths: per-substep (recompute) vs rollout (saved grid)"""
+    from neuma_b200 import ops
+    co, cc = _consts(64, 5e-4, "noslip")
+    n = 30000
+    d = make_cloud(n, 64, seed=9)
+    g = _dev(d, cuda_dev)
+    ref = ops.mpm_substep_fwd(cc, g["x"], g["v"], g["C"], g["F"], g["stress"], g["vol"], g["rho"], g["clip"],
+                              g["enabled"])
+    grid, adj, box = _buffers(64, cuda_dev)
+    ops.mpm_box_from_x(cc, g["x"], g["enabled"], box[0])
+    out = tuple(torch.empty_like(t) for t in ref)
+    ops.mpm_rollout_fwd(cc, g["x"], g["v"], g["C"], g["F"], g["stress"], g["vol"], g["rho"], g["clip"],
+                        g["enabled"], out, grid[0], adj[0], box[0], box[1])
+    for a, b in zip(out, ref):
+        assert rel_err(a, b) < 2e-6
+    gouts = [torch.randn_like(t) for t in ref]
+    gref = ops.mpm_substep_bwd(cc, g["x"], g["v"], g["C"], g["F"], g["stress"], g["vol"], g["rho"], g["clip"],
+                               g["enabled"], ref[1], *gouts)
+    grads = [torch.empty_like(g[k]) for k in ("x", "v", "C", "F", "stress")]
+    ops.mpm_rollout_bwd(cc, g["x"], g["v"], g["C"], g["F"], g["stress"], g["vol"], g["rho"], g["clip"],
+                        g["enabled"], out[1], out[2], *gouts, grid[0], adj[0], box[0], *grads)
+    for a, b in zip(grads, gref):
+        assert rel_err(a, b) < 5e-5
+
+
+def test_cell_order_and_gather(cuda_dev):
+    from neuma_b200 import ops
+    co, cc = _consts(32, 1e-3, "noslip")
+    n = 7777
+    d = make_cloud(n, 32, seed=1)
+    x = d["x"].to(cuda_dev)
+    perm = ops.mpm_cell_order(cc, x)
+    assert sorted(perm.cpu().tolist()) == list(range(n))               # a permutation
+    xs = ops.gather_rows(x, perm)
+    assert torch.equal(xs, x[perm.long()])
+    inv = ops.invert_perm(perm)
+    assert torch.equal(ops.gather_rows(xs, inv), x)
+    # keys are non-decreasing along the order: Morton code of the truncated stencil base
+    b = (xs.cpu() * 32 - 0.5).to(torch.int64).clamp(0, 1023)
+
+    def spread(v):
+        out = torch.zeros_like(v)
+        for i in range(10):
+            out |= ((v >> i) & 1) << (3 * i)
+        return out
+    key = spread(b[:, 0]) | (spread(b[:, 1]) << 1) | (spread(b[:, 2]) << 2)
+    assert torch.all(key[1:] >= key[:-1])
+    # int32 rows too (the `enabled` flags)
+    e = torch.arange(n, dtype=torch.int32, device=cuda_dev)
+    assert torch.equal(ops.gather_rows(e, perm), perm)
+
+
+def test_empty_box(cuda_dev):
+    """all particles disabled / no particles: empty box, the node passes do nothing"""
+    from neuma_b200 import ops
+    co, cc = _consts(16, 1e-3, "noslip")
+    d = make_cloud(100, 16, seed=4)
+    d["enabled"][:] = 0
+    g = _dev(d, cuda_dev)
+    grid, adj, box = _buffers(16, cuda_dev)
+    ops.mpm_box_from_x(cc, g["x"], g["enabled"], box[0])
+    assert box[0, 0].item() > box[0, 3].item()
+    out = tuple(torch.full_like(g[k], 7.0) for k in ("x", "v", "C", "F"))
+    ops.mpm_rollout_fwd(cc, g["x"], g["v"], g["C"], g["F"], g["stress"], g["vol"], g["rho"], g["clip"],
+                        g["enabled"], out, grid[0], adj[0], box[0], box[1])
+    torch.cuda.synchronize()
+    assert torch.all(out[0] == 7.0)                                     # disabled particles are not written
+    assert torch.isnan(grid).all()                                      # nothing was touched

@@ -46,6 +46,24 @@ for n, G in [(100_000, 128), (200_000, 128), (1_000_000, 256), (50_000, 64)]:
     b = lambda: ops.mpm_substep_bwd(cc, d["x"], d["v"], d["C"], d["F"], d["stress"], d["vol"], d["rho"], d["clip"], d["enabled"], out[1], *gouts)
     res["substep_bwd_us"] = timeit(b)
     res["substep_bwd_hot_us"] = timeit(b, flush_l2=False)
+    # ---- rollout path (per-substep grid, box-sparse node passes), caller order vs cell order
+    for tag, dd in (("", d), ("_sorted", None)):
+        if dd is None:
+            perm = ops.mpm_cell_order(cc, d["x"])
+            dd = {k: ops.gather_rows(t.contiguous(), perm) for k, t in d.items()}
+        grid = torch.zeros(Ng, 4, device=dev); adj = torch.zeros(Ng, 4, device=dev)
+        box = torch.zeros(2, 8, dtype=torch.int32, device=dev)
+        ops.mpm_box_from_x(cc, dd["x"], dd["enabled"], box[0])
+        res["r_clear_us" + tag] = timeit(lambda: ops.mpm_box_clear(cc, box[0], grid, None, box[1]))
+        res["r_p2g_us" + tag] = timeit(lambda: ops.mpm_p2g_to(cc, dd["x"], dd["v"], dd["C"], dd["stress"], dd["vol"], dd["rho"], dd["enabled"], grid))
+        res["r_gridop_us" + tag] = timeit(lambda: ops.mpm_grid_op_box(cc, box[0], grid, adj))
+        res["r_g2p_us" + tag] = timeit(lambda: ops.mpm_g2p_from(cc, dd["x"], dd["F"], dd["clip"], dd["enabled"], grid, out, box[1]))
+        rf = lambda: ops.mpm_rollout_fwd(cc, dd["x"], dd["v"], dd["C"], dd["F"], dd["stress"], dd["vol"], dd["rho"], dd["clip"], dd["enabled"], out, grid, adj, box[0], box[1])
+        res["r_fwd_us" + tag] = timeit(rf)
+        g5 = [torch.empty_like(dd[k]) for k in ("x", "v", "C", "F", "stress")]
+        rb = lambda: ops.mpm_rollout_bwd(cc, dd["x"], dd["v"], dd["C"], dd["F"], dd["stress"], dd["vol"], dd["rho"], dd["clip"], dd["enabled"], out[1], out[2], *gouts, grid, adj, box[0], *g5)
+        res["r_bwd_us" + tag] = timeit(rb)
+        res["r_p2g_algo_GBs" + tag] = (108 * n + 44 * Ng) / (res["r_clear_us" + tag] + res["r_p2g_us" + tag]) / 1e3
     res["fwd_algo_GBs"] = (260 * n + 84 * Ng) / res["substep_fwd_us"] / 1e3
     res["p2g_algo_GBs"] = (108 * n + 44 * Ng) / (res["clear_us"] + res["p2g_us"]) / 1e3
     res["const_fwd_us"] = timeit(lambda: ops.constitutive_fwd(0, d["F"], W0, W1, W2))
