@@ -263,9 +263,9 @@ def run_gpu(args):
     def _bwd():
         ops.mpm_rollout_bwd(cc, xs, vs, Cs, Fs, st, *sx, outb[1], outb[2], *gout, grid_s, adj_s, box_s, *gouts5)
     kt["mpm_substep_bwd"] = event_time_us(_bwd, it, wm, flush)
-    kt["constitutive_fwd"] = event_time_us(lambda: ops.constitutive_fwd_into(0, Fs, *We, 0.0, gF_), it, wm, flush)
+    kt["constitutive_fwd"] = event_time_us(lambda: ops.constitutive_fwd_staged(0, Fs, eng.We_st, 0.0, gF_), it, wm, flush)
     kt["constitutive_bwd"] = event_time_us(
-        lambda: ops.constitutive_bwd_into(0, Fs, *We, 0.0, gout[3], gF_, *gWt), it, wm, flush)
+        lambda: ops.constitutive_bwd_staged(0, Fs, eng.We_st, 0.0, gout[3], gF_, *gWt), it, wm, flush)
     rs = eng._render_saved
     kt["raster_fwd"] = event_time_us(lambda: ops.raster_fwd(settings, rs[0], gs["shs"], None, gs["opac"], rs[1]), 10, 2, flush)
     dimg = torch.randn(3, IMAGE, IMAGE, device=dev)

@@ -215,6 +215,21 @@ int neuma_constitutive_bwd(neuma_ctx* ctx, int kind, int n, int hidden,
                            float alpha, const float* gout,
                            float* gF, float* gW0, float* gW1, float* gW2, void* stream);
 
+/* The kernels read the weights from a "staged" image (every fp32 weight split into bf16
+ * terms, laid out as tensor-core operands): neuma_constitutive_staged_bytes() bytes of
+ * caller-owned device memory filled by neuma_constitutive_stage.  The two entry points
+ * above stage into a ctx-owned buffer on every call; a rollout that evaluates the same
+ * weights many times (finetune.py:360-365, 2 x S calls per frame) stages once and calls
+ * the *_staged variants. */
+int neuma_constitutive_staged_bytes(void);
+int neuma_constitutive_stage(neuma_ctx* ctx, int hidden, const float* W0, const float* W1,
+                             const float* W2, void* staged, void* stream);
+int neuma_constitutive_fwd_staged(neuma_ctx* ctx, int kind, int n, int hidden, const float* F,
+                                  const void* staged, float alpha, float* out, void* stream);
+int neuma_constitutive_bwd_staged(neuma_ctx* ctx, int kind, int n, int hidden, const float* F,
+                                  const void* staged, float alpha, const float* gout, float* gF,
+                                  float* gW0, float* gW1, float* gW2, void* stream);
+
 /* ---- particle -> Gaussian binding: modules/tune/utils.py:424-472 ------- */
 /* out[K,ncol] = B in[Np,ncol] (transpose=0) or out[Np,ncol] = B^T in[K,ncol]
  * (transpose=1, the backward), B in CSR (rowptr[K+1], col[nnz], w[nnz]). */

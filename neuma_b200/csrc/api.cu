@@ -28,6 +28,16 @@ int neuma_ensure_scratch(neuma_ctx* ctx, size_t bytes) {
   return 0;
 }
 
+int neuma_ensure_wstage(neuma_ctx* ctx, size_t bytes) {
+  if (bytes <= ctx->wstage_bytes) return 0;
+  if (ctx->wstage) cudaFree(ctx->wstage);
+  ctx->wstage = nullptr;
+  ctx->wstage_bytes = 0;
+  NEUMA_CUDA(ctx, cudaMalloc(&ctx->wstage, bytes));
+  ctx->wstage_bytes = bytes;
+  return 0;
+}
+
 extern "C" {
 
 int neuma_version(void) { return 100; }
@@ -56,6 +66,7 @@ int neuma_ctx_destroy(neuma_ctx* ctx) {
   if (ctx->grid_v) cudaFree(ctx->grid_v);
   if (ctx->grid_adj) cudaFree(ctx->grid_adj);
   if (ctx->scratch) cudaFree(ctx->scratch);
+  if (ctx->wstage) cudaFree(ctx->wstage);
   if (ctx->raster) neuma_raster_state_free(ctx->raster);
   free(ctx);
   return 0;

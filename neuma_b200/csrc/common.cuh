@@ -26,6 +26,9 @@ struct neuma_ctx {
   // scratch for partial reductions (constitutive weight grads)
   float* scratch;
   size_t scratch_bytes;
+  // split/laid-out constitutive weights for the un-staged entry points (constitutive.cu)
+  void* wstage;
+  size_t wstage_bytes;
   RasterState* raster;
 };
 
@@ -53,6 +56,7 @@ static inline int neuma_fail_msg(neuma_ctx* ctx, const char* what) {
 
 int neuma_ensure_grid(neuma_ctx* ctx, size_t nodes);
 int neuma_ensure_scratch(neuma_ctx* ctx, size_t bytes);
+int neuma_ensure_wstage(neuma_ctx* ctx, size_t bytes);
 
 // ---- small 3x3 helpers (row-major float[9]) ------------------------------
 struct Mat3 {

@@ -5,22 +5,33 @@
 //   InvariantFullMetaPlasticity.forward   modules/nclaw/material/meta.py:468-489
 // and the Warp batch_svd / SVDFunction of modules/nclaw/warp/svd.py:9-96.
 //
-// The three Linear layers -- and, in the backward, their data-gradient and weight-gradient
-// GEMMs -- run on the 5th-generation tensor cores: tcgen05.mma kind::f16 on bf16 operands
-// staged in shared memory, fp32 accumulators in TMEM.  Every fp32 value is split into
-// three bf16 terms (x = x0 + x1 + x2, 24 mantissa bits) and each GEMM is the six products
-// with i + j <= 2, accumulated smallest first ("bf16x3"): ~2e-7 relative error against
-// fp64, i.e. fp32-class results from the tensor pipe.  One thread owns one particle row
-// (= one TMEM lane) for the SVD / invariants / polar recombination, two threads share a
-// row for the GELU epilogues between the GEMMs.
+// Structure (warp-specialised, one persistent CTA per SM):
+//   * NPIPE independent tile pipelines per CTA.  A pipeline = 128 compute threads = the 128
+//     particles of a tile = the 128 TMEM lanes; one thread owns one particle row for the
+//     SVD / invariants, the GELU epilogues between the GEMMs, and the polar recombination.
+//   * ONE extra warp issues every tcgen05.mma of the CTA.  Pipelines hand it work through
+//     mbarriers (full[p]: "operands of my next GEMM are in shared memory"; done[p] /
+//     wdone[p]: tcgen05.commit of the forward-or-data-gradient / weight-gradient GEMMs), it
+//     polls the pipelines and serves whichever is ready, so one pipeline's CUDA-core phase
+//     overlaps the others' tensor-core phase.  A single issuing thread also makes the
+//     weight-gradient accumulators (shared by the pipelines, resident in TMEM for the whole
+//     kernel) well ordered.
+//   * The three Linear layers -- and, in the backward, their data-gradient and
+//     weight-gradient GEMMs -- are tcgen05.mma kind::f16 on bf16 operands in shared memory
+//     with fp32 accumulators in TMEM.  Every fp32 value is split into NS bf16 terms
+//     (x = x0 + x1 [+ x2]) and a GEMM is the products with i + j < NS, all accumulated into
+//     the same TMEM columns.  Forward: NS = 3 (24 mantissa bits, ~2e-7 relative to fp64);
+//     backward: NS = 2 (16+ mantissa bits, ~4e-6: gradients are compared at 5e-4).
+//   * Weights are split and laid out ONCE per weight update by stage_weights_kernel into a
+//     60 KB global image; each CTA pulls its copy with cp.async.bulk.
 //
 // Shared-memory operand layout (SWIZZLE_NONE core matrices of 8 rows x 16 bytes, see
-// umma.cuh): an [R x K] fp32 tile is stored per split as [K/8][R][8] bf16.  The same bytes
-// are a K-major operand (rows = particles or output features) for the forward /
-// data-gradient GEMMs and, with LBO/SBO swapped and the major bit set, an MN-major
-// operand X^T for the weight-gradient GEMMs that contract over the 128 particles of the
-// tile -- no transposed copy is ever written.  (kind::tf32 would need one: its MN-major
-// form exists only with the 128B_BASE32B swizzle, measured with tools/umma_probe.cu.)
+// umma.cuh): an [R x K] tile is stored per split as [K/8][R][8] bf16.  The same bytes are a
+// K-major operand (forward GEMMs: rows = particles or output features) and, with LBO/SBO
+// swapped and the major bit set, an MN-major operand (the transposed matrix): the
+// data-gradient GEMMs read the forward weight image transposed and the weight-gradient
+// GEMMs read the activation tiles transposed (contraction over the tile's 128 particles)
+// -- no transposed copy is ever written.
 //
 // LoRA adaptors are merged into the weights by the host (W + scaling * B A,
 // loralib.py:216-224) and the weight gradients un-merged there.
@@ -39,8 +50,9 @@ namespace {
 constexpr int H = 64;      // hidden width (layer_widths: [64, 64] in every shipped config)
 constexpr int NF = 13;     // 3 + 9 + 1 invariants
 constexpr int TP = 128;    // particles per tile = TMEM lanes = rows of every GEMM
-constexpr int NT = 256;    // threads per block: two per particle row in the GELU phases
 constexpr int KF = 16;     // invariants (13) and MLP head (9) padded to one bf16 K step
+constexpr int NS_FWD = 3, NS_BWD = 2;      // bf16 splits per fp32 value
+constexpr int NPIPE_FWD = 3, NPIPE_BWD = 2;  // tile pipelines per CTA
 
 struct Kinematics {
   Mat3 F, U, V, R;
@@ -48,10 +60,9 @@ struct Kinematics {
   float feat[NF];
 };
 
-__device__ __forceinline__ void kinematics(const float* __restrict__ Fp, bool normalize,
-                                           Kinematics& k) {
-  k.F = mat3_load(Fp);
-  svd3(k.F, k.U, k.sig, k.V);
+__device__ __forceinline__ void kinematics(const Mat3& F, bool normalize, Kinematics& k) {
+  k.F = F;
+  svd3_fast(k.F, k.U, k.sig, k.V);
   k.R = mat3_mul_nt(k.U, k.V);
   const Mat3 FtF = mat3_mul_tn(k.F, k.F);
   const float sub = normalize ? 1.0f : 0.0f;
@@ -63,158 +74,165 @@ __device__ __forceinline__ void kinematics(const float* __restrict__ Fp, bool no
     for (int j = 0; j < 3; ++j) k.feat[3 + 3 * i + j] = FtF(i, j) - ((i == j) ? sub : 0.0f);
   k.feat[12] = mat3_det(k.F) - sub;
 }
+__device__ __forceinline__ Mat3 load_F_or_identity(const float* __restrict__ F, int p, int n) {
+  Mat3 m;
+  if (p < n) {
+    m = mat3_load(F + (size_t)p * 9);
+  } else {  // padding rows of the last tile run the same code on the identity
+#pragma unroll
+    for (int i = 0; i < 9; ++i) m.m[i] = (i % 4 == 0) ? 1.0f : 0.0f;
+  }
+  return m;
+}
 
-
-// ---- shared-memory map (bytes)
-// Activation tiles (A operands; wgrad operands): per split [K/8][128][8] bf16, splits adjacent.
-// Weights, N-STACKED so that one MMA multiplies an A split with several B splits at once:
-//   Wk (forward, K-major B):      [K/8][3R][8], row = split*R + n          (N = 3R | 2R | R)
-//   Wt (data gradient, MN-major): [split][cols/8][R][8]; read transposed, the three splits
-//                                 are consecutive 8-wide N chunks           (N = 3c | 2c | c)
+// ---- shared-memory / staged-image map (bytes)
 constexpr uint32_t SMALL_SPLIT = TP * KF * 2;  // [128 x 16] activation tile, one split
 constexpr uint32_t BIG_SPLIT = TP * H * 2;     // [128 x 64] activation tile, one split
-constexpr uint32_t W0_BYTES = 3 * H * KF * 2, W1_BYTES = 3 * H * H * 2, W2_BYTES = 3 * KF * H * 2;
-constexpr uint32_t OFF_W0K = 0;
-constexpr uint32_t OFF_W1K = OFF_W0K + W0_BYTES;
-constexpr uint32_t OFF_W2K = OFF_W1K + W1_BYTES;
-constexpr uint32_t OFF_FEAT = OFF_W2K + W2_BYTES;          // invariants
-constexpr uint32_t OFF_BIGA = OFF_FEAT + 3 * SMALL_SPLIT;  // gelu(h1), later dL/dh1
-constexpr uint32_t FWD_SMEM = OFF_BIGA + 3 * BIG_SPLIT;    // 98304
-constexpr uint32_t OFF_GO = FWD_SMEM;                      // dL/d(MLP output)
-constexpr uint32_t OFF_BIGB = OFF_GO + 3 * SMALL_SPLIT;    // gelu(h2), later dL/dh2
-constexpr uint32_t OFF_W0T = OFF_BIGB + 3 * BIG_SPLIT;
-constexpr uint32_t OFF_W1T = OFF_W0T + W0_BYTES;
-constexpr uint32_t OFF_W2T = OFF_W1T + W1_BYTES;
-constexpr uint32_t BWD_SMEM = OFF_W2T + W2_BYTES;          // 196608
+constexpr uint32_t W0_SPLIT = H * KF * 2, W1_SPLIT = H * H * 2, W2_SPLIT = KF * H * 2;
+template <int NS>
+struct WImg {  // [W0: NS splits][W1: NS splits][W2: NS splits], each split [K/8][R][8] bf16
+  static constexpr uint32_t OFF_W0 = 0, OFF_W1 = NS * W0_SPLIT, OFF_W2 = OFF_W1 + NS * W1_SPLIT,
+                            BYTES = OFF_W2 + NS * W2_SPLIT;
+};
+constexpr uint32_t STAGED_OFF_FWD = 0, STAGED_OFF_BWD = WImg<NS_FWD>::BYTES,
+                   STAGED_BYTES = STAGED_OFF_BWD + WImg<NS_BWD>::BYTES;  // 61440
+// per-pipeline activation tiles
+template <int NS>
+struct PipeFwd {
+  static constexpr uint32_t OFF_FEAT = 0, OFF_BIGA = NS * SMALL_SPLIT, BYTES = OFF_BIGA + NS * BIG_SPLIT;
+};
+template <int NS>
+struct PipeBwd {
+  static constexpr uint32_t OFF_FEAT = 0, OFF_GO = NS * SMALL_SPLIT, OFF_BIGA = 2 * NS * SMALL_SPLIT,
+                            OFF_BIGB = OFF_BIGA + NS * BIG_SPLIT, BYTES = OFF_BIGB + NS * BIG_SPLIT;
+};
+constexpr uint32_t FWD_SMEM = WImg<NS_FWD>::BYTES + NPIPE_FWD * PipeFwd<NS_FWD>::BYTES;  // 221184
+constexpr uint32_t BWD_SMEM = WImg<NS_BWD>::BYTES + NPIPE_BWD * PipeBwd<NS_BWD>::BYTES;  // 188416
+constexpr int FWD_THREADS = NPIPE_FWD * TP + 32, BWD_THREADS = NPIPE_BWD * TP + 32;
 
-// ---- TMEM columns (fp32, lane = particle row unless noted).  A stacked GEMM leaves three
-// partial sums (blocks of N columns) that the reading thread adds: blk0 + blk1 + blk2.
-constexpr uint32_t COL_D1 = 0;      // gelu'(h1)                                          (bwd)
-constexpr uint32_t COL_D2 = 64;     // gelu'(h2)                                          (bwd)
-constexpr uint32_t COL_S = 128;     // 3 x 64 (or 3 x 16) partial sums of the current GEMM (bwd)
-constexpr uint32_t COL_GW1 = 320;   // dL/dW1 [o][k]: 2 x 64; M=64 layout: row o -> lane (o%16)+32(o/16)
-constexpr uint32_t COL_GW0 = 448;   // dL/dW0 [o][j]: 2 x 16  (same layout)
-constexpr uint32_t COL_GW2T = 480;  // dL/dW2^T [k][j]: 2 x 16 (same layout)
-constexpr uint32_t FWD_COL_S = 0;
-constexpr uint32_t FWD_TMEM_COLS = 256, BWD_TMEM_COLS = 512;
+// ---- TMEM columns (fp32, lane = particle row unless noted)
+constexpr uint32_t FWD_PIPE_COLS = 64, FWD_TMEM_COLS = 256;
+// backward, per pipeline: h1 -> gelu'(h1) in place | h2 -> gelu'(h2) | current GEMM result
+constexpr uint32_t BWD_PIPE_COLS = 192, COL_H1 = 0, COL_H2 = 64, COL_S = 128;
+// shared weight-gradient accumulators (M = 64 layout: row o -> lane (o%16) + 32 (o/16))
+constexpr uint32_t COL_GW1 = NPIPE_BWD * BWD_PIPE_COLS, COL_GW0 = COL_GW1 + 64, COL_GW2T = COL_GW0 + 16;
+constexpr uint32_t BWD_TMEM_COLS = 512;
+static_assert(COL_GW2T + 16 <= BWD_TMEM_COLS, "TMEM budget");
+static_assert(NPIPE_FWD * FWD_PIPE_COLS <= FWD_TMEM_COLS, "TMEM budget");
 
-// x -> three bf16 terms, two values at a time (cvt.rn.bf16x2: first source -> upper half)
+// ---- fp32 -> NS bf16 terms, two values at a time (cvt.rn.bf16x2: first source -> upper half)
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   uint32_t d;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
   return d;
 }
-__device__ __forceinline__ void split_pair(float a, float b, uint32_t& s0, uint32_t& s1, uint32_t& s2) {
-  s0 = pack_bf16x2(a, b);
-  a -= __uint_as_float(s0 << 16);
-  b -= __uint_as_float(s0 & 0xFFFF0000u);
-  s1 = pack_bf16x2(a, b);
-  a -= __uint_as_float(s1 << 16);
-  b -= __uint_as_float(s1 & 0xFFFF0000u);
-  s2 = pack_bf16x2(a, b);
-}
-// eight consecutive K values of particle row r -> chunk c of the three split images of a tile
-__device__ __forceinline__ void store_chunk(uint8_t* img, uint32_t split_bytes, int c, int r, const float* x) {
-  uint4 s0, s1, s2;
-  split_pair(x[0], x[1], s0.x, s1.x, s2.x);
-  split_pair(x[2], x[3], s0.y, s1.y, s2.y);
-  split_pair(x[4], x[5], s0.z, s1.z, s2.z);
-  split_pair(x[6], x[7], s0.w, s1.w, s2.w);
-  uint8_t* p = img + ((size_t)c * TP + r) * 16;
-  *reinterpret_cast<uint4*>(p) = s0;
-  *reinterpret_cast<uint4*>(p + split_bytes) = s1;
-  *reinterpret_cast<uint4*>(p + 2 * split_bytes) = s2;
-}
-
-// weights -> stacked split images.  src is row-major [rows x cols], zero padded to [R x K].
-template <bool TRANSPOSED_VIEW>
-__device__ __forceinline__ void stage_weight(uint8_t* img, const float* __restrict__ src, int rows, int cols,
-                                             int R, int K) {
-  uint16_t* dst = reinterpret_cast<uint16_t*>(img);
-  for (int e = threadIdx.x; e < R * K; e += blockDim.x) {
-    const int r = e / K, k = e % K;
-    float x = (r < rows && k < cols) ? src[r * cols + k] : 0.f;
+template <int NS>
+__device__ __forceinline__ void split_pair(float a, float b, uint32_t (&s)[NS]) {
 #pragma unroll
-    for (int t = 0; t < 3; ++t) {
-      const uint32_t h = pack_bf16x2(x, 0.f) & 0xFFFFu;
-      const size_t o = TRANSPOSED_VIEW ? ((size_t)t * (K >> 3) + (k >> 3)) * R + r   // [split][k/8][R]
-                                       : ((size_t)(k >> 3) * 3 + t) * R + r;         // [k/8][3R]
-      dst[o * 8 + (k & 7)] = (uint16_t)h;
-      x -= __uint_as_float(h << 16);
+  for (int t = 0; t < NS; ++t) {
+    s[t] = pack_bf16x2(a, b);
+    if (t + 1 < NS) {
+      a -= __uint_as_float(s[t] << 16);
+      b -= __uint_as_float(s[t] & 0xFFFF0000u);
     }
   }
 }
+// eight consecutive K values of particle row r -> chunk c of the NS split images of a tile
+template <int NS>
+__device__ __forceinline__ void store_chunk(uint8_t* img, uint32_t split_bytes, int c, int r, const float* x) {
+  uint32_t s[4][NS];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) split_pair<NS>(x[2 * q], x[2 * q + 1], s[q]);
+  uint8_t* p = img + ((size_t)c * TP + r) * 16;
+#pragma unroll
+  for (int t = 0; t < NS; ++t)
+    *reinterpret_cast<uint4*>(p + t * split_bytes) = make_uint4(s[0][t], s[1][t], s[2][t], s[3][t]);
+}
 
-// ---- MMA issue.  Called by ALL lanes of one warp (elect.sync inside the helpers).
+// weights -> the staged image (both split counts), run once per weight update.
+// One thread per element of the zero-padded [R x K] matrices.
+__global__ void __launch_bounds__(256)
+stage_weights_kernel(const float* __restrict__ W0, const float* __restrict__ W1,
+                     const float* __restrict__ W2, uint8_t* __restrict__ staged) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  constexpr int N0 = H * KF, N1 = H * H, N2 = KF * H;
+  if (e >= N0 + N1 + N2) return;
+  int r, k, R;
+  float x;
+  uint32_t off3, off2, split;
+  if (e < N0) {
+    r = e / KF; k = e % KF; R = H;
+    x = (k < NF) ? W0[r * NF + k] : 0.f;
+    off3 = WImg<3>::OFF_W0; off2 = WImg<2>::OFF_W0; split = W0_SPLIT;
+  } else if (e < N0 + N1) {
+    const int f = e - N0;
+    r = f / H; k = f % H; R = H;
+    x = W1[r * H + k];
+    off3 = WImg<3>::OFF_W1; off2 = WImg<2>::OFF_W1; split = W1_SPLIT;
+  } else {
+    const int f = e - N0 - N1;
+    r = f / H; k = f % H; R = KF;
+    x = (r < 9) ? W2[r * H + k] : 0.f;
+    off3 = WImg<3>::OFF_W2; off2 = WImg<2>::OFF_W2; split = W2_SPLIT;
+  }
+  const size_t o = (((size_t)(k >> 3) * R + r) * 8 + (k & 7)) * 2;
+#pragma unroll
+  for (int t = 0; t < 3; ++t) {
+    const uint16_t h = (uint16_t)(pack_bf16x2(x, 0.f) & 0xFFFFu);
+    *reinterpret_cast<uint16_t*>(staged + STAGED_OFF_FWD + off3 + t * split + o) = h;
+    if (t < 2) *reinterpret_cast<uint16_t*>(staged + STAGED_OFF_BWD + off2 + t * split + o) = h;
+    x -= __uint_as_float((uint32_t)h << 16);
+  }
+}
+
+// ---- operand descriptors
 struct Desc {
   uint64_t d;       // descriptor of split 0, K step 0
-  uint32_t split;   // (bytes >> 4) between splits (A operands)
+  uint32_t split;   // (bytes >> 4) between splits
   uint32_t kstep;   // (bytes >> 4) per K = 16 step
 };
-// activation tile / plain operand, K-major (rows = particles): LBO = R*16, SBO = 128
+// [K/8][R][8] read K-major (rows = M/N index): LBO = R*16 (next 8 K), SBO = 128 (next 8 rows)
 __device__ __forceinline__ Desc desc_kmajor(uint32_t addr, uint32_t split_bytes, int R) {
   return Desc{umma::smem_desc(addr, (uint32_t)R * 16u, 128u), split_bytes >> 4, ((uint32_t)R * 32u) >> 4};
 }
-// the same bytes read transposed (MN-major): SBO = R*16, LBO = 128, 16 rows per K step
+// the same bytes read transposed (MN-major; rows = K index): SBO = R*16, LBO = 128, 16 rows per K step
 __device__ __forceinline__ Desc desc_mnmajor(uint32_t addr, uint32_t split_bytes, int R) {
   return Desc{umma::smem_desc(addr, 128u, (uint32_t)R * 16u), split_bytes >> 4, 256u >> 4};
 }
-// forward weights, N-stacked K-major: [K/8][3R][8]
-__device__ __forceinline__ Desc desc_wk(uint32_t addr, int R) {
-  return Desc{umma::smem_desc(addr, (uint32_t)R * 48u, 128u), 0u, ((uint32_t)R * 96u) >> 4};
-}
 
-// D[128 x 3N | 2N | N] (+)= A_i B_stack^T for the three A splits: after the call
-// blk0 = (A0+A1+A2) B0, blk1 = (A0+A1) B1, blk2 = A0 B2  (the six bf16x3 products).
-template <int NK>
-__device__ __forceinline__ void gemm_stacked(uint32_t tmem_d, const Desc a, const Desc b, uint32_t idesc_n1) {
-  // idesc_n1: descriptor with the N field of ONE block; N is a multiple of 16, so 2N and 3N
-  // are the same field times 2 and 3
-  const uint32_t nfield = idesc_n1 & (0x3Fu << 17), rest = idesc_n1 & ~(0x3Fu << 17);
-#pragma unroll
-  for (int k = 0; k < NK; ++k) {
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-      umma::mma_bf16_ss(tmem_d, a.d + (uint64_t)(i * a.split + k * a.kstep), b.d + (uint64_t)(k * b.kstep),
-                        rest | (nfield * (3 - i)), (k | i) ? 1u : 0u);
-  }
-}
-// weight gradient, contraction over the 128 particles of the tile (8 K steps), M = 64:
-// blk0 (+)= (X0 + X1)^T Y0, blk1 (+)= X0^T Y1  (three leading bf16 products: the dropped
-// ones are 2^-16 relative with random sign, far below the fp32 atomics' own ordering noise)
-__device__ __forceinline__ void gemm_wgrad(uint32_t tmem_d, const Desc x, const Desc y, uint32_t idesc_n1,
+// D[tmem] (+)= sum_{i + j < NS} A_i B_j^T over NK K-steps.  Called by ALL lanes of the MMA warp.
+template <int NS, int NK>
+__device__ __forceinline__ void gemm_split(uint32_t tmem_d, const Desc a, const Desc b, uint32_t idesc,
                                            bool accumulate) {
-  const uint32_t nfield = idesc_n1 & (0x3Fu << 17), rest = idesc_n1 & ~(0x3Fu << 17);
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    umma::mma_bf16_ss(tmem_d, x.d + (uint64_t)(k * x.kstep), y.d + (uint64_t)(k * y.kstep), rest | (nfield * 2),
-                      (accumulate || k) ? 1u : 0u);
-    umma::mma_bf16_ss(tmem_d, x.d + (uint64_t)(x.split + k * x.kstep), y.d + (uint64_t)(k * y.kstep),
-                      rest | nfield, 1u);
-  }
-}
-
-// sum of the three stacked partial results for 16 consecutive columns of this thread's row
-template <int BLOCK>
-__device__ __forceinline__ void load_sum3(uint32_t taddr, float (&v)[16]) {
-  float b1[16], b2[16];
-  umma::tmem_ld16(taddr, v);
-  umma::tmem_ld16(taddr + BLOCK, b1);
-  umma::tmem_ld16(taddr + 2 * BLOCK, b2);
-  umma::tmem_wait_ld();
+  for (int k = 0; k < NK; ++k)
 #pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] += b1[i] + b2[i];
+    for (int i = 0; i < NS; ++i)
+#pragma unroll
+      for (int j = 0; j < NS - i; ++j)
+        umma::mma_bf16_ss(tmem_d, a.d + (uint64_t)(i * a.split + k * a.kstep),
+                          b.d + (uint64_t)(j * b.split + k * b.kstep), idesc,
+                          (accumulate || k || i || j) ? 1u : 0u);
 }
 
 // Phi(h) and phi(h) of the standard normal for the exact-erf GELU (nn.GELU() default,
 // modules/nclaw/material/utils.py:16-17): gelu = h Phi(h), gelu' = Phi(h) + h phi(h).
-// erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, on a par with fp32 erff and measured
-// 2.5x closer to the fp64 GELU than torch's own fp32 kernel); it shares exp(-h^2/2) with
-// phi, so the backward's gelu' costs three extra instructions.  Branch-free: 2 MUFU + ~12 FMA.
+// erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, on a par with fp32 erff); it shares
+// exp(-h^2/2) with phi.  Branch-free: 2 MUFU (rcp, ex2) + ~10 FMA-pipe instructions.
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 __device__ __forceinline__ void normal_cdf_pdf(float h, float& cdf, float& pdf) {
   const float ax = fabsf(h) * 0.70710678118654752f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
-  const float e = __expf(-ax * ax);
+  const float t = rcp_approx(fmaf(0.3275911f, ax, 1.0f));
+  const float e = ex2_approx((h * h) * -0.72134752044448170f);  // exp(-h^2 / 2)
   float p = fmaf(t, 1.061405429f, -1.453152027f);
   p = fmaf(t, p, 1.421413741f);
   p = fmaf(t, p, -0.284496736f);
@@ -224,49 +242,84 @@ __device__ __forceinline__ void normal_cdf_pdf(float h, float& cdf, float& pdf) 
   pdf = 0.39894228040143268f * e;
 }
 
-// GELU phase: the thread reads its 32 accumulator columns, writes gelu() as the next GEMM's
-// A operand (chunks 4*half .. 4*half+3 of the tile at `img`) and, in the backward, stores
-// gelu'() in TMEM for the data-gradient pass.
-template <bool KEEP_GRAD>
-__device__ __forceinline__ void gelu_phase(uint32_t t_acc, uint32_t t_dgelu, uint8_t* img, int r, int half) {
+// ---- pipeline <-> MMA warp handshakes
+__device__ __forceinline__ void mbar_arrive(uint32_t mbar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(uint32_t mbar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(done)
+      : "r"(mbar), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+struct PipeSync {
+  uint32_t full, done, wdone;  // shared-memory addresses of the pipeline's mbarriers
+  uint32_t ph_done, ph_wdone;
+  // my smem operand writes / TMEM reads of this phase are finished: hand over to the MMA warp
+  __device__ __forceinline__ void publish() const {
+    umma::fence_async_smem();
+    umma::fence_before_sync();
+    mbar_arrive(full);
+  }
+  __device__ __forceinline__ void wait_done() {
+    umma::mbar_wait(done, ph_done);
+    ph_done ^= 1u;
+    umma::fence_after_sync();
+  }
+  __device__ __forceinline__ void wait_wdone() {
+    umma::mbar_wait(wdone, ph_wdone);
+    ph_wdone ^= 1u;
+    umma::fence_after_sync();
+  }
+};
+
+// GELU phase of one particle row: read the 64 accumulator columns, write gelu() as the next
+// GEMM's A operand and, in the backward, put gelu'() back into the same TMEM columns.
+template <int NS, bool KEEP_GRAD>
+__device__ __forceinline__ void gelu_phase(uint32_t t_acc, uint8_t* img, int r) {
 #pragma unroll
-  for (int q = 0; q < 2; ++q) {
+  for (int q = 0; q < 4; ++q) {
     float h[16], a[16];
-    load_sum3<H>(t_acc + 32 * half + 16 * q, h);
+    umma::tmem_ld16(t_acc + 16 * q, h);
+    umma::tmem_wait_ld();
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       float cdf, pdf;
       normal_cdf_pdf(h[i], cdf, pdf);
       a[i] = h[i] * cdf;
-      if (KEEP_GRAD) h[i] = cdf + h[i] * pdf;
+      if (KEEP_GRAD) h[i] = fmaf(h[i], pdf, cdf);
     }
-    store_chunk(img, BIG_SPLIT, 4 * half + 2 * q, r, a);
-    store_chunk(img, BIG_SPLIT, 4 * half + 2 * q + 1, r, a + 8);
-    if (KEEP_GRAD) umma::tmem_st16(t_dgelu + 32 * half + 16 * q, h);
+    store_chunk<NS>(img, BIG_SPLIT, 2 * q, r, a);
+    store_chunk<NS>(img, BIG_SPLIT, 2 * q + 1, r, a + 8);
+    if (KEEP_GRAD) umma::tmem_st16(t_acc + 16 * q, h);
   }
   if (KEEP_GRAD) umma::tmem_wait_st();
 }
-// dL/dh = dL/da * gelu'(h): both in TMEM; result becomes an A operand tile at `img`
-__device__ __forceinline__ void grad_phase(uint32_t t_acc, uint32_t t_dgelu, uint8_t* img, int r, int half,
-                                           uint64_t* wait_bar, uint32_t& wait_phase) {
-  float g[2][16];
+// dL/dh = dL/da * gelu'(h): both in TMEM; the result becomes an A operand tile at `img`
+// once the weight-gradient GEMM that still reads the tile's previous content is done.
+template <int NS>
+__device__ __forceinline__ void grad_phase(uint32_t t_acc, uint32_t t_dgelu, uint8_t* img, int r,
+                                           PipeSync& ps, bool wait_w) {
+  float g[4][16];
 #pragma unroll
-  for (int q = 0; q < 2; ++q) {
+  for (int q = 0; q < 4; ++q) {
     float d[16];
-    load_sum3<H>(t_acc + 32 * half + 16 * q, g[q]);
-    umma::tmem_ld16(t_dgelu + 32 * half + 16 * q, d);
+    umma::tmem_ld16(t_acc + 16 * q, g[q]);
+    umma::tmem_ld16(t_dgelu + 16 * q, d);
     umma::tmem_wait_ld();
 #pragma unroll
     for (int i = 0; i < 16; ++i) g[q][i] *= d[i];
   }
-  if (wait_bar) {  // the weight-gradient GEMM still reading the tile we are about to overwrite
-    umma::mbar_wait(umma::smem_u32(wait_bar), wait_phase);
-    wait_phase ^= 1u;
-  }
+  if (wait_w) ps.wait_wdone();
 #pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    store_chunk(img, BIG_SPLIT, 4 * half + 2 * q, r, g[q]);
-    store_chunk(img, BIG_SPLIT, 4 * half + 2 * q + 1, r, g[q] + 8);
+  for (int q = 0; q < 4; ++q) {
+    store_chunk<NS>(img, BIG_SPLIT, 2 * q, r, g[q]);
+    store_chunk<NS>(img, BIG_SPLIT, 2 * q + 1, r, g[q] + 8);
   }
 }
 
@@ -279,268 +332,323 @@ __device__ __forceinline__ Mat3 head_to_sym(const float (&o)[16]) {
   return X;
 }
 
-struct Setup {
-  uint32_t tmem, smem;
+// ---- block prologue: barriers, TMEM, weight image
+struct Bars {
+  uint64_t w;  // weight image landed (cp.async.bulk complete_tx)
+  uint64_t full[3], done[3], wdone[3];
 };
-// weights -> smem images, TMEM allocation, mbarrier init; returns after a block-wide sync
-template <bool BWD>
-__device__ __forceinline__ Setup block_setup(uint8_t* sm, uint64_t* mbar, uint32_t* tmem_slot,
-                                             const float* W0, const float* W1, const float* W2,
-                                             uint32_t tmem_cols) {
-  stage_weight<false>(sm + OFF_W0K, W0, H, NF, H, KF);
-  stage_weight<false>(sm + OFF_W1K, W1, H, H, H, H);
-  stage_weight<false>(sm + OFF_W2K, W2, 9, H, KF, H);
-  if (BWD) {
-    stage_weight<true>(sm + OFF_W0T, W0, H, NF, H, KF);
-    stage_weight<true>(sm + OFF_W1T, W1, H, H, H, H);
-    stage_weight<true>(sm + OFF_W2T, W2, 9, H, KF, H);
-  }
-  if (threadIdx.x < 32) umma::tmem_alloc(umma::smem_u32(tmem_slot), tmem_cols);
-  if (threadIdx.x == 32) {
-    umma::mbar_init(umma::smem_u32(mbar), 1);
-    if (BWD) umma::mbar_init(umma::smem_u32(mbar + 1), 1);
+template <int NPIPE>
+__device__ __forceinline__ uint32_t block_setup(Bars* bars, uint32_t* tmem_slot, uint8_t* sm_w,
+                                                const uint8_t* __restrict__ staged, uint32_t w_bytes,
+                                                uint32_t tmem_cols, int mma_warp) {
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    umma::mbar_init(umma::smem_u32(&bars->w), 1);
+#pragma unroll
+    for (int p = 0; p < NPIPE; ++p) {
+      umma::mbar_init(umma::smem_u32(&bars->full[p]), TP);
+      umma::mbar_init(umma::smem_u32(&bars->done[p]), 1);
+      umma::mbar_init(umma::smem_u32(&bars->wdone[p]), 1);
+    }
     umma::fence_mbar_init();
   }
-  umma::fence_async_smem();
+  if (warp == 0) umma::tmem_alloc(umma::smem_u32(tmem_slot), tmem_cols);
   umma::fence_before_sync();
   __syncthreads();
   umma::fence_after_sync();
-  return Setup{*tmem_slot, umma::smem_u32(sm)};
-}
-
-// publish this thread's smem operand writes / TMEM reads, then hand over to the MMA warps
-__device__ __forceinline__ void publish_and_sync() {
-  umma::fence_async_smem();
-  umma::fence_before_sync();
-  __syncthreads();
-}
-__device__ __forceinline__ void wait_mma(uint64_t* mbar, uint32_t& phase) {
-  umma::mbar_wait(umma::smem_u32(mbar), phase);
-  phase ^= 1u;
-  umma::fence_after_sync();
+  if (warp == mma_warp && (threadIdx.x & 31) == 0) {
+    const uint32_t bar = umma::smem_u32(&bars->w);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(w_bytes) : "memory");
+    constexpr uint32_t CH = 12288;
+    for (uint32_t o = 0; o < w_bytes; o += CH) {
+      const uint32_t sz = (w_bytes - o < CH) ? (w_bytes - o) : CH;
+      asm volatile(
+          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+              umma::smem_u32(sm_w + o)),
+          "l"(staged + o), "r"(sz), "r"(bar)
+          : "memory");
+    }
+  }
+  return *tmem_slot;
 }
 
 // ------------------------------------------------------------------ forward
-__global__ void __launch_bounds__(NT, 2)
-constitutive_fwd_kernel(int kind, int n, const float* __restrict__ F, const float* __restrict__ W0,
-                        const float* __restrict__ W1, const float* __restrict__ W2, float alpha,
-                        float* __restrict__ out) {
+__global__ void __launch_bounds__(FWD_THREADS, 1)
+constitutive_fwd_kernel(int kind, int n, const float* __restrict__ F, const uint8_t* __restrict__ staged,
+                        float alpha, float* __restrict__ out) {
+  constexpr int NS = NS_FWD, NPIPE = NPIPE_FWD;
+  using W = WImg<NS>;
+  using P = PipeFwd<NS>;
   extern __shared__ __align__(1024) uint8_t sm[];
-  __shared__ uint64_t mbar[1];
+  __shared__ Bars bars;
   __shared__ uint32_t tmem_slot;
-  const Setup su = block_setup<false>(sm, mbar, &tmem_slot, W0, W1, W2, FWD_TMEM_COLS);
-  const int tid = threadIdx.x, r = tid & (TP - 1), half = tid >> 7, warp = tid >> 5;
-  const uint32_t tlane = su.tmem + ((uint32_t)((warp & 3) * 32) << 16);
-  uint32_t phase = 0;
-  const Desc w0 = desc_wk(su.smem + OFF_W0K, H), w1 = desc_wk(su.smem + OFF_W1K, H), w2 = desc_wk(su.smem + OFF_W2K, KF);
-  const Desc feat = desc_kmajor(su.smem + OFF_FEAT, SMALL_SPLIT, TP), act = desc_kmajor(su.smem + OFF_BIGA, BIG_SPLIT, TP);
-  constexpr uint32_t ID64 = umma::idesc_bf16(TP, H, 0, 0), ID16 = umma::idesc_bf16(TP, KF, 0, 0);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t tmem = block_setup<NPIPE>(&bars, &tmem_slot, sm, staged + STAGED_OFF_FWD, W::BYTES,
+                                           FWD_TMEM_COLS, NPIPE * 4);
+  const uint32_t smem = umma::smem_u32(sm);
   const int tiles = (n + TP - 1) / TP;
-  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    const int p = tile * TP + r;
-    Kinematics k;
-    if (half == 0) {
-      float f[KF];
+  const int chains = gridDim.x * NPIPE;
+  constexpr uint32_t ID64 = umma::idesc_bf16(TP, H, 0, 0), ID16 = umma::idesc_bf16(TP, KF, 0, 0);
+
+  if (warp == NPIPE * 4) {
+    // ---------------- MMA warp
+    const Desc w0 = desc_kmajor(smem + W::OFF_W0, W0_SPLIT, H), w1 = desc_kmajor(smem + W::OFF_W1, W1_SPLIT, H),
+               w2 = desc_kmajor(smem + W::OFF_W2, W2_SPLIT, KF);
+    int njobs[NPIPE], job[NPIPE];
+    uint32_t ph[NPIPE];
+    int remaining = 0;
 #pragma unroll
-      for (int i = 0; i < KF; ++i) f[i] = 0.f;
-      if (p < n) {
-        kinematics(F + (size_t)p * 9, kind != 2, k);
+    for (int p = 0; p < NPIPE; ++p) {
+      const int c = p * gridDim.x + blockIdx.x;
+      njobs[p] = (c < tiles) ? 3 * ((tiles - 1 - c) / chains + 1) : 0;
+      job[p] = 0;
+      ph[p] = 0;
+      remaining += njobs[p];
+    }
+    umma::mbar_wait(umma::smem_u32(&bars.w), 0);
+    while (remaining > 0) {
 #pragma unroll
-        for (int i = 0; i < NF; ++i) f[i] = k.feat[i];
+      for (int p = 0; p < NPIPE; ++p) {
+        if (job[p] >= njobs[p]) continue;
+        uint32_t ok = mbar_test(umma::smem_u32(&bars.full[p]), ph[p]) ? 1u : 0u;
+        ok = __shfl_sync(0xffffffffu, ok, 0);
+        if (!ok) continue;
+        ph[p] ^= 1u;
+        umma::fence_after_sync();
+        const uint32_t pbase = smem + W::BYTES + p * P::BYTES;
+        const Desc feat = desc_kmajor(pbase + P::OFF_FEAT, SMALL_SPLIT, TP);
+        const Desc act = desc_kmajor(pbase + P::OFF_BIGA, BIG_SPLIT, TP);
+        const uint32_t acc = tmem + p * FWD_PIPE_COLS;
+        const int j = job[p] % 3;
+        if (j == 0) gemm_split<NS, 1>(acc, feat, w0, ID64, false);
+        else if (j == 1) gemm_split<NS, 4>(acc, act, w1, ID64, false);
+        else gemm_split<NS, 4>(acc, act, w2, ID16, false);
+        umma::commit(umma::smem_u32(&bars.done[p]));
+        ++job[p];
+        --remaining;
       }
-      store_chunk(sm + OFF_FEAT, SMALL_SPLIT, 0, r, f);
-      store_chunk(sm + OFF_FEAT, SMALL_SPLIT, 1, r, f + 8);
     }
-    publish_and_sync();
-    if (warp == 0) {
-      umma::fence_after_sync();
-      gemm_stacked<1>(su.tmem + FWD_COL_S, feat, w0, ID64);
-      umma::commit(umma::smem_u32(mbar));
-    }
-    wait_mma(mbar, phase);
-    gelu_phase<false>(tlane + FWD_COL_S, 0, sm + OFF_BIGA, r, half);
-    publish_and_sync();
-    if (warp == 0) {
-      umma::fence_after_sync();
-      gemm_stacked<4>(su.tmem + FWD_COL_S, act, w1, ID64);
-      umma::commit(umma::smem_u32(mbar));
-    }
-    wait_mma(mbar, phase);
-    gelu_phase<false>(tlane + FWD_COL_S, 0, sm + OFF_BIGA, r, half);
-    publish_and_sync();
-    if (warp == 0) {
-      umma::fence_after_sync();
-      gemm_stacked<4>(su.tmem + FWD_COL_S, act, w2, ID16);
-      umma::commit(umma::smem_u32(mbar));
-    }
-    wait_mma(mbar, phase);
-    if (half == 0) {
+  } else {
+    // ---------------- compute threads: pipeline p, particle row r
+    const int p = warp >> 2, r = tid & (TP - 1);
+    uint8_t* const pm = sm + W::BYTES + p * P::BYTES;
+    const uint32_t tacc = tmem + ((uint32_t)((warp & 3) * 32) << 16) + p * FWD_PIPE_COLS;
+    PipeSync ps{umma::smem_u32(&bars.full[p]), umma::smem_u32(&bars.done[p]), umma::smem_u32(&bars.wdone[p]), 0u, 0u};
+    for (int tile = p * gridDim.x + blockIdx.x; tile < tiles; tile += chains) {
+      const int pi = tile * TP + r;
+      Kinematics k;
+      kinematics(load_F_or_identity(F, pi, n), kind != 2, k);
+      {
+        float f[KF];
+#pragma unroll
+        for (int i = 0; i < KF; ++i) f[i] = (i < NF) ? k.feat[i] : 0.f;
+        store_chunk<NS>(pm + P::OFF_FEAT, SMALL_SPLIT, 0, r, f);
+        store_chunk<NS>(pm + P::OFF_FEAT, SMALL_SPLIT, 1, r, f + 8);
+      }
+      ps.publish();                                            // -> h1 = feat W0^T
+      ps.wait_done();
+      gelu_phase<NS, false>(tacc, pm + P::OFF_BIGA, r);
+      ps.publish();                                            // -> h2 = a1 W1^T
+      ps.wait_done();
+      gelu_phase<NS, false>(tacc, pm + P::OFF_BIGA, r);
+      ps.publish();                                            // -> o = a2 W2^T
+      ps.wait_done();
       float o[16];
-      load_sum3<KF>(tlane + FWD_COL_S, o);
-      if (p < n) {
+      umma::tmem_ld16(tacc, o);
+      umma::tmem_wait_ld();
+      if (pi < n) {
         const Mat3 X = head_to_sym(o);
-        const Mat3 P = mat3_mul(k.R, X);
+        const Mat3 Pm = mat3_mul(k.R, X);
         Mat3 O;
         if (kind == 1) {
 #pragma unroll
-          for (int i = 0; i < 9; ++i) O.m[i] = alpha * P.m[i] + k.F.m[i];  // delta_Fp + F
+          for (int i = 0; i < 9; ++i) O.m[i] = alpha * Pm.m[i] + k.F.m[i];  // delta_Fp + F
         } else {
-          O = mat3_mul_nt(P, k.F);  // cauchy = P F^T
+          O = mat3_mul_nt(Pm, k.F);  // cauchy = P F^T
         }
-        mat3_store(out + (size_t)p * 9, O);
+        mat3_store(out + (size_t)pi * 9, O);
       }
     }
   }
   umma::fence_before_sync();
   __syncthreads();
-  if (warp == 0) umma::tmem_dealloc(su.tmem, FWD_TMEM_COLS);
+  if (warp == 0) umma::tmem_dealloc(tmem, FWD_TMEM_COLS);
 }
 
 // ------------------------------------------------------------------ backward
 template <bool WGRAD>
-__global__ void __launch_bounds__(NT, 1)
-constitutive_bwd_kernel(int kind, int n, const float* __restrict__ F, const float* __restrict__ W0,
-                        const float* __restrict__ W1, const float* __restrict__ W2, float alpha,
-                        const float* __restrict__ gout, float* __restrict__ gF,
-                        float* __restrict__ gW0, float* __restrict__ gW1,
-                        float* __restrict__ gW2) {
+__global__ void __launch_bounds__(BWD_THREADS, 1)
+constitutive_bwd_kernel(int kind, int n, const float* __restrict__ F, const uint8_t* __restrict__ staged,
+                        float alpha, const float* __restrict__ gout, float* __restrict__ gF,
+                        float* __restrict__ gW0, float* __restrict__ gW1, float* __restrict__ gW2) {
+  constexpr int NS = NS_BWD, NPIPE = NPIPE_BWD;
+  using W = WImg<NS>;
+  using P = PipeBwd<NS>;
   extern __shared__ __align__(1024) uint8_t sm[];
-  __shared__ uint64_t mbar[2];  // [0]: the forward / data-gradient chain (warp 0); [1]: weight gradients (warp 1)
+  __shared__ Bars bars;
   __shared__ uint32_t tmem_slot;
-  const Setup su = block_setup<true>(sm, mbar, &tmem_slot, W0, W1, W2, BWD_TMEM_COLS);
-  const int tid = threadIdx.x, r = tid & (TP - 1), half = tid >> 7, warp = tid >> 5;
-  const uint32_t tlane = su.tmem + ((uint32_t)((warp & 3) * 32) << 16);
-  uint32_t phase = 0, wphase = 0;
-  uint64_t* const wbar = WGRAD ? mbar + 1 : nullptr;
-  const Desc w0 = desc_wk(su.smem + OFF_W0K, H), w1 = desc_wk(su.smem + OFF_W1K, H), w2 = desc_wk(su.smem + OFF_W2K, KF);
-  // transposed weights: [split][cols/8][R][8] read MN-major; the splits are adjacent N chunks
-  const Desc w0t = desc_mnmajor(su.smem + OFF_W0T, 0, H), w1t = desc_mnmajor(su.smem + OFF_W1T, 0, H),
-             w2t = desc_mnmajor(su.smem + OFF_W2T, 0, KF);
-  const Desc feat = desc_kmajor(su.smem + OFF_FEAT, SMALL_SPLIT, TP), go = desc_kmajor(su.smem + OFF_GO, SMALL_SPLIT, TP),
-             biga = desc_kmajor(su.smem + OFF_BIGA, BIG_SPLIT, TP), bigb = desc_kmajor(su.smem + OFF_BIGB, BIG_SPLIT, TP);
-  const Desc featT = desc_mnmajor(su.smem + OFF_FEAT, SMALL_SPLIT, TP), goT = desc_mnmajor(su.smem + OFF_GO, SMALL_SPLIT, TP),
-             bigaT = desc_mnmajor(su.smem + OFF_BIGA, BIG_SPLIT, TP), bigbT = desc_mnmajor(su.smem + OFF_BIGB, BIG_SPLIT, TP);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t tmem = block_setup<NPIPE>(&bars, &tmem_slot, sm, staged + STAGED_OFF_BWD, W::BYTES,
+                                           BWD_TMEM_COLS, NPIPE * 4);
+  const uint32_t smem = umma::smem_u32(sm);
+  const int tiles = (n + TP - 1) / TP;
+  const int chains = gridDim.x * NPIPE;
   constexpr uint32_t ID64 = umma::idesc_bf16(TP, H, 0, 0), ID16 = umma::idesc_bf16(TP, KF, 0, 0);
   constexpr uint32_t ID64_BT = umma::idesc_bf16(TP, H, 0, 1), ID16_BT = umma::idesc_bf16(TP, KF, 0, 1);
   constexpr uint32_t IDW64 = umma::idesc_bf16(64, H, 1, 1), IDW16 = umma::idesc_bf16(64, KF, 1, 1);
-  const int tiles = (n + TP - 1) / TP;
-  bool first = true;
-  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, first = false) {
-    const int p = tile * TP + r;
-    const bool live = (half == 0) && (p < n);
-    Kinematics k;
-    Mat3 gR, gFd;
-    // ---- invariants -> h1.  (FEAT / BIGA were last read by the previous tile's dW0 GEMM.)
-    if (WGRAD && !first) {
-      umma::mbar_wait(umma::smem_u32(wbar), wphase);
-      wphase ^= 1u;
-    }
-    if (half == 0) {
-      float f[KF];
+
+  if (warp == NPIPE * 4) {
+    // ---------------- MMA warp
+    const Desc w0 = desc_kmajor(smem + W::OFF_W0, W0_SPLIT, H), w1 = desc_kmajor(smem + W::OFF_W1, W1_SPLIT, H),
+               w2 = desc_kmajor(smem + W::OFF_W2, W2_SPLIT, KF);
+    // the same images read transposed: B operands of the data-gradient GEMMs
+    const Desc w0t = desc_mnmajor(smem + W::OFF_W0, W0_SPLIT, H), w1t = desc_mnmajor(smem + W::OFF_W1, W1_SPLIT, H),
+               w2t = desc_mnmajor(smem + W::OFF_W2, W2_SPLIT, KF);
+    int njobs[NPIPE], job[NPIPE];
+    uint32_t ph[NPIPE];
+    int remaining = 0;
 #pragma unroll
-      for (int i = 0; i < KF; ++i) f[i] = 0.f;
-      if (live) {
-        kinematics(F + (size_t)p * 9, kind != 2, k);
+    for (int p = 0; p < NPIPE; ++p) {
+      const int c = p * gridDim.x + blockIdx.x;
+      njobs[p] = (c < tiles) ? 6 * ((tiles - 1 - c) / chains + 1) : 0;
+      job[p] = 0;
+      ph[p] = 0;
+      remaining += njobs[p];
+    }
+    bool acc2 = false, acc1 = false, acc0 = false;  // weight-gradient accumulators initialised?
+    umma::mbar_wait(umma::smem_u32(&bars.w), 0);
+    while (remaining > 0) {
 #pragma unroll
-        for (int i = 0; i < NF; ++i) f[i] = k.feat[i];
-      }
-      store_chunk(sm + OFF_FEAT, SMALL_SPLIT, 0, r, f);
-      store_chunk(sm + OFF_FEAT, SMALL_SPLIT, 1, r, f + 8);
-    }
-    publish_and_sync();
-    if (warp == 0) {
-      umma::fence_after_sync();
-      gemm_stacked<1>(su.tmem + COL_S, feat, w0, ID64);
-      umma::commit(umma::smem_u32(mbar));
-    }
-    wait_mma(mbar, phase);
-    // ---- a1 = gelu(h1) -> h2
-    gelu_phase<true>(tlane + COL_S, tlane + COL_D1, sm + OFF_BIGA, r, half);
-    publish_and_sync();
-    if (warp == 0) {
-      umma::fence_after_sync();
-      gemm_stacked<4>(su.tmem + COL_S, biga, w1, ID64);
-      umma::commit(umma::smem_u32(mbar));
-    }
-    wait_mma(mbar, phase);
-    // ---- a2 = gelu(h2) -> o
-    gelu_phase<true>(tlane + COL_S, tlane + COL_D2, sm + OFF_BIGB, r, half);
-    publish_and_sync();
-    if (warp == 0) {
-      umma::fence_after_sync();
-      gemm_stacked<4>(su.tmem + COL_S, bigb, w2, ID16);
-      umma::commit(umma::smem_u32(mbar));
-    }
-    wait_mma(mbar, phase);
-    // ---- output head: dL/dout -> dL/d(MLP output), dL/dR, direct dL/dF
-    if (half == 0) {
-      float o[16], g9[KF];
-      load_sum3<KF>(tlane + COL_S, o);
-#pragma unroll
-      for (int i = 0; i < KF; ++i) g9[i] = 0.f;
-      if (live) {
-        const Mat3 X = head_to_sym(o);
-        const Mat3 P = mat3_mul(k.R, X);
-        const Mat3 G = mat3_load(gout + (size_t)p * 9);
-        Mat3 gP;  // out = P F^T (elastic)  |  out = F + alpha P (plastic)
-        if (kind == 1) {
-#pragma unroll
-          for (int i = 0; i < 9; ++i) { gP.m[i] = alpha * G.m[i]; gFd.m[i] = G.m[i]; }
-        } else {
-          gP = mat3_mul(G, k.F);
-          gFd = mat3_mul_tn(G, P);
+      for (int p = 0; p < NPIPE; ++p) {
+        if (job[p] >= njobs[p]) continue;
+        uint32_t ok = mbar_test(umma::smem_u32(&bars.full[p]), ph[p]) ? 1u : 0u;
+        ok = __shfl_sync(0xffffffffu, ok, 0);
+        if (!ok) continue;
+        ph[p] ^= 1u;
+        umma::fence_after_sync();
+        const uint32_t pbase = smem + W::BYTES + p * P::BYTES;
+        const Desc feat = desc_kmajor(pbase + P::OFF_FEAT, SMALL_SPLIT, TP), go = desc_kmajor(pbase + P::OFF_GO, SMALL_SPLIT, TP),
+                   biga = desc_kmajor(pbase + P::OFF_BIGA, BIG_SPLIT, TP), bigb = desc_kmajor(pbase + P::OFF_BIGB, BIG_SPLIT, TP);
+        const Desc featT = desc_mnmajor(pbase + P::OFF_FEAT, SMALL_SPLIT, TP), goT = desc_mnmajor(pbase + P::OFF_GO, SMALL_SPLIT, TP),
+                   bigaT = desc_mnmajor(pbase + P::OFF_BIGA, BIG_SPLIT, TP), bigbT = desc_mnmajor(pbase + P::OFF_BIGB, BIG_SPLIT, TP);
+        const uint32_t tp = tmem + p * BWD_PIPE_COLS;
+        const uint32_t dbar = umma::smem_u32(&bars.done[p]), wbar = umma::smem_u32(&bars.wdone[p]);
+        switch (job[p] % 6) {
+          case 0:  // h1 = feat W0^T
+            gemm_split<NS, 1>(tp + COL_H1, feat, w0, ID64, false);
+            umma::commit(dbar);
+            break;
+          case 1:  // h2 = a1 W1^T
+            gemm_split<NS, 4>(tp + COL_H2, biga, w1, ID64, false);
+            umma::commit(dbar);
+            break;
+          case 2:  // o = a2 W2^T
+            gemm_split<NS, 4>(tp + COL_S, bigb, w2, ID16, false);
+            umma::commit(dbar);
+            break;
+          case 3:  // dL/da2 = go W2 ; dW2^T += a2^T go
+            gemm_split<NS, 1>(tp + COL_S, go, w2t, ID64_BT, false);
+            umma::commit(dbar);
+            if (WGRAD) {
+              gemm_split<NS, 8>(tmem + COL_GW2T, bigbT, goT, IDW16, acc2);
+              acc2 = true;
+              umma::commit(wbar);
+            }
+            break;
+          case 4:  // dL/da1 = g2 W1 ; dW1 += g2^T a1
+            gemm_split<NS, 4>(tp + COL_S, bigb, w1t, ID64_BT, false);
+            umma::commit(dbar);
+            if (WGRAD) {
+              gemm_split<NS, 8>(tmem + COL_GW1, bigbT, bigaT, IDW64, acc1);
+              acc1 = true;
+              umma::commit(wbar);
+            }
+            break;
+          default:  // dL/dfeat = g1 W0 ; dW0 += g1^T feat
+            gemm_split<NS, 4>(tp + COL_S, biga, w0t, ID16_BT, false);
+            umma::commit(dbar);
+            if (WGRAD) {
+              gemm_split<NS, 8>(tmem + COL_GW0, bigaT, featT, IDW16, acc0);
+              acc0 = true;
+              umma::commit(wbar);
+            }
+            break;
         }
-        gR = mat3_mul(gP, X);  // X symmetric
-        const Mat3 gXs = mat3_mul_tn(k.R, gP);
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-#pragma unroll
-          for (int j = 0; j < 3; ++j) g9[3 * i + j] = 0.5f * (gXs(i, j) + gXs(j, i));
+        ++job[p];
+        --remaining;
       }
-      store_chunk(sm + OFF_GO, SMALL_SPLIT, 0, r, g9);
-      store_chunk(sm + OFF_GO, SMALL_SPLIT, 1, r, g9 + 8);
     }
-    publish_and_sync();
-    if (warp == 0) {
-      umma::fence_after_sync();
-      gemm_stacked<1>(su.tmem + COL_S, go, w2t, ID64_BT);  // dL/da2 = go W2
-      umma::commit(umma::smem_u32(mbar));
-    } else if (WGRAD && warp == 1) {
-      umma::fence_after_sync();
-      gemm_wgrad(su.tmem + COL_GW2T, bigbT, goT, IDW16, !first);  // dW2^T += a2^T go
-      umma::commit(umma::smem_u32(wbar));
-    }
-    wait_mma(mbar, phase);
-    // ---- dL/dh2 (overwrites a2 once dW2 has read it) -> dL/da1, dW1
-    grad_phase(tlane + COL_S, tlane + COL_D2, sm + OFF_BIGB, r, half, wbar, wphase);
-    publish_and_sync();
-    if (warp == 0) {
-      umma::fence_after_sync();
-      gemm_stacked<4>(su.tmem + COL_S, bigb, w1t, ID64_BT);  // dL/da1 = g2 W1
-      umma::commit(umma::smem_u32(mbar));
-    } else if (WGRAD && warp == 1) {
-      umma::fence_after_sync();
-      gemm_wgrad(su.tmem + COL_GW1, bigbT, bigaT, IDW64, !first);  // dW1 += g2^T a1
-      umma::commit(umma::smem_u32(wbar));
-    }
-    wait_mma(mbar, phase);
-    // ---- dL/dh1 (overwrites a1 once dW1 has read it) -> dL/dfeat, dW0
-    grad_phase(tlane + COL_S, tlane + COL_D1, sm + OFF_BIGA, r, half, wbar, wphase);
-    publish_and_sync();
-    if (warp == 0) {
-      umma::fence_after_sync();
-      gemm_stacked<4>(su.tmem + COL_S, biga, w0t, ID16_BT);  // dL/dfeat = g1 W0
-      umma::commit(umma::smem_u32(mbar));
-    } else if (WGRAD && warp == 1) {
-      umma::fence_after_sync();
-      gemm_wgrad(su.tmem + COL_GW0, bigaT, featT, IDW16, !first);  // dW0 += g1^T feat
-      umma::commit(umma::smem_u32(wbar));
-    }
-    wait_mma(mbar, phase);
-    // ---- invariants -> F
-    if (half == 0) {
+  } else {
+    // ---------------- compute threads: pipeline p, particle row r
+    const int p = warp >> 2, r = tid & (TP - 1);
+    uint8_t* const pm = sm + W::BYTES + p * P::BYTES;
+    const uint32_t tl = tmem + ((uint32_t)((warp & 3) * 32) << 16) + p * BWD_PIPE_COLS;
+    PipeSync ps{umma::smem_u32(&bars.full[p]), umma::smem_u32(&bars.done[p]), umma::smem_u32(&bars.wdone[p]), 0u, 0u};
+    bool first = true;
+    for (int tile = p * gridDim.x + blockIdx.x; tile < tiles; tile += chains, first = false) {
+      const int pi = tile * TP + r;
+      const bool live = pi < n;
+      Kinematics k;
+      kinematics(load_F_or_identity(F, pi, n), kind != 2, k);
+      // FEAT / BIGA were last read by the previous tile's dW0 GEMM
+      if (WGRAD && !first) ps.wait_wdone();
+      {
+        float f[KF];
+#pragma unroll
+        for (int i = 0; i < KF; ++i) f[i] = (i < NF && live) ? k.feat[i] : 0.f;
+        store_chunk<NS>(pm + P::OFF_FEAT, SMALL_SPLIT, 0, r, f);
+        store_chunk<NS>(pm + P::OFF_FEAT, SMALL_SPLIT, 1, r, f + 8);
+      }
+      ps.publish();                                              // job 0
+      ps.wait_done();
+      gelu_phase<NS, true>(tl + COL_H1, pm + P::OFF_BIGA, r);    // a1; gelu'(h1) stays in TMEM
+      ps.publish();                                              // job 1
+      ps.wait_done();
+      gelu_phase<NS, true>(tl + COL_H2, pm + P::OFF_BIGB, r);    // a2; gelu'(h2)
+      ps.publish();                                              // job 2
+      ps.wait_done();
+      // ---- output head: dL/dout -> dL/d(MLP output), dL/dR, direct dL/dF
+      Mat3 gR, gFd;
+      {
+        float o[16], g9[KF];
+        umma::tmem_ld16(tl + COL_S, o);
+        umma::tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < KF; ++i) g9[i] = 0.f;
+        if (live) {
+          const Mat3 X = head_to_sym(o);
+          const Mat3 Pm = mat3_mul(k.R, X);
+          const Mat3 G = mat3_load(gout + (size_t)pi * 9);
+          Mat3 gP;  // out = P F^T (elastic)  |  out = F + alpha P (plastic)
+          if (kind == 1) {
+#pragma unroll
+            for (int i = 0; i < 9; ++i) { gP.m[i] = alpha * G.m[i]; gFd.m[i] = G.m[i]; }
+          } else {
+            gP = mat3_mul(G, k.F);
+            gFd = mat3_mul_tn(G, Pm);
+          }
+          gR = mat3_mul(gP, X);  // X symmetric
+          const Mat3 gXs = mat3_mul_tn(k.R, gP);
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) g9[3 * i + j] = 0.5f * (gXs(i, j) + gXs(j, i));
+        }
+        store_chunk<NS>(pm + P::OFF_GO, SMALL_SPLIT, 0, r, g9);
+        store_chunk<NS>(pm + P::OFF_GO, SMALL_SPLIT, 1, r, g9 + 8);
+      }
+      ps.publish();                                              // job 3
+      ps.wait_done();
+      grad_phase<NS>(tl + COL_S, tl + COL_H2, pm + P::OFF_BIGB, r, ps, WGRAD);   // g2 over a2 (after dW2)
+      ps.publish();                                              // job 4
+      ps.wait_done();
+      grad_phase<NS>(tl + COL_S, tl + COL_H1, pm + P::OFF_BIGA, r, ps, WGRAD);   // g1 over a1 (after dW1)
+      ps.publish();                                              // job 5
+      ps.wait_done();
+      // ---- invariants -> F
       float gfeat[16];
-      load_sum3<KF>(tlane + COL_S, gfeat);
+      umma::tmem_ld16(tl + COL_S, gfeat);
+      umma::tmem_wait_ld();
       if (live) {
         Mat3 gFt = gFd;
         {  // FtF = F^T F : dF += F (G + G^T)
@@ -579,43 +687,42 @@ constitutive_bwd_kernel(int kind, int n, const float* __restrict__ F, const floa
 #pragma unroll
           for (int i = 0; i < 9; ++i) gFt.m[i] += t.m[i];
         }
-        mat3_store(gF + (size_t)p * 9, gFt);
+        mat3_store(gF + (size_t)pi * 9, gFt);
       }
     }
-  }
-  if (WGRAD && !first) {
-    umma::mbar_wait(umma::smem_u32(wbar), wphase);  // the last tile's dW0 GEMM
-    umma::fence_after_sync();
-    if (half == 0) {
-      // M=64 accumulators: lane 32*q + i (i < 16) holds row 16*q + i; value = blk0 + blk1
-      const int i16 = tid & 31, row = (warp & 3) * 16 + i16;
-      float a[16], b[16];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        umma::tmem_ld16(tlane + COL_GW1 + 16 * c, a);
-        umma::tmem_ld16(tlane + COL_GW1 + H + 16 * c, b);
-        umma::tmem_wait_ld();
-        if (i16 < 16)
-#pragma unroll
-          for (int j = 0; j < 16; ++j) atomicAdd(gW1 + row * H + 16 * c + j, a[j] + b[j]);
-      }
-      umma::tmem_ld16(tlane + COL_GW0, a);
-      umma::tmem_ld16(tlane + COL_GW0 + KF, b);
-      umma::tmem_wait_ld();
-      if (i16 < 16)
-#pragma unroll
-        for (int j = 0; j < NF; ++j) atomicAdd(gW0 + row * NF + j, a[j] + b[j]);
-      umma::tmem_ld16(tlane + COL_GW2T, a);
-      umma::tmem_ld16(tlane + COL_GW2T + KF, b);
-      umma::tmem_wait_ld();
-      if (i16 < 16)
-#pragma unroll
-        for (int j = 0; j < 9; ++j) atomicAdd(gW2 + j * H + row, a[j] + b[j]);
-    }
+    if (WGRAD && !first) ps.wait_wdone();  // the last tile's dW0 GEMM
   }
   umma::fence_before_sync();
   __syncthreads();
-  if (warp == 0) umma::tmem_dealloc(su.tmem, BWD_TMEM_COLS);
+  umma::fence_after_sync();
+  if (WGRAD && warp < 4) {
+    // every weight-gradient MMA of the CTA has completed (each pipeline waited for its last one).
+    // M = 64 accumulators: lane 32*q + i (i < 16) holds row 16*q + i.
+    const uint32_t tl0 = tmem + ((uint32_t)(warp * 32) << 16);
+    const int i16 = tid & 31, row = warp * 16 + i16;
+    float a[16];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      umma::tmem_ld16(tl0 + COL_GW1 + 16 * c, a);
+      umma::tmem_wait_ld();
+      if (i16 < 16)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) atomicAdd(gW1 + row * H + 16 * c + j, a[j]);
+    }
+    umma::tmem_ld16(tl0 + COL_GW0, a);
+    umma::tmem_wait_ld();
+    if (i16 < 16)
+#pragma unroll
+      for (int j = 0; j < NF; ++j) atomicAdd(gW0 + row * NF + j, a[j]);
+    umma::tmem_ld16(tl0 + COL_GW2T, a);
+    umma::tmem_wait_ld();
+    if (i16 < 16)
+#pragma unroll
+      for (int j = 0; j < 9; ++j) atomicAdd(gW2 + j * H + row, a[j]);
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem, BWD_TMEM_COLS);
 }
 
 // ------------------------------------------------------------------ stand-alone SVD
@@ -702,6 +809,13 @@ int set_attrs(neuma_ctx* ctx) {
   return 0;
 }
 
+int check_args(neuma_ctx* ctx, int kind, int hidden) {
+  if (!ctx) return 2;
+  if (hidden != H) return neuma_fail_msg(ctx, "neuma_constitutive: only hidden width 64 is built");
+  if (kind < 0 || kind > 2) return neuma_fail_msg(ctx, "neuma_constitutive: kind must be 0, 1 or 2");
+  return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -726,29 +840,35 @@ int neuma_svd3_bwd(neuma_ctx* ctx, int n, const float* U, const float* sigma, co
   return 0;
 }
 
-int neuma_constitutive_fwd(neuma_ctx* ctx, int kind, int n, int hidden, const float* F,
-                           const float* W0, const float* W1, const float* W2, float alpha,
-                           float* out, void* stream) {
-  if (!ctx) return 2;
-  if (hidden != H) return neuma_fail_msg(ctx, "neuma_constitutive: only hidden width 64 is built");
-  if (kind < 0 || kind > 2) return neuma_fail_msg(ctx, "neuma_constitutive: kind must be 0, 1 or 2");
+int neuma_constitutive_staged_bytes(void) { return (int)STAGED_BYTES; }
+
+int neuma_constitutive_stage(neuma_ctx* ctx, int hidden, const float* W0, const float* W1,
+                             const float* W2, void* staged, void* stream) {
+  if (int r = check_args(ctx, 0, hidden)) return r;
+  if (!W0 || !W1 || !W2 || !staged) return neuma_fail_msg(ctx, "neuma_constitutive_stage: NULL argument");
+  constexpr int total = H * KF + H * H + KF * H;
+  stage_weights_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(W0, W1, W2, (uint8_t*)staged);
+  NEUMA_LAUNCH_CHECK(ctx, "stage_weights_kernel");
+  return 0;
+}
+
+int neuma_constitutive_fwd_staged(neuma_ctx* ctx, int kind, int n, int hidden, const float* F,
+                                  const void* staged, float alpha, float* out, void* stream) {
+  if (int r = check_args(ctx, kind, hidden)) return r;
   if (n <= 0) return 0;
   if (int r = set_attrs(ctx)) return r;
   const int tiles = (n + TP - 1) / TP;
-  const int grid = tiles < ctx->num_sms * 2 ? tiles : ctx->num_sms * 2;
-  constitutive_fwd_kernel<<<grid, NT, FWD_SMEM, (cudaStream_t)stream>>>(kind, n, F, W0, W1, W2,
-                                                                        alpha, out);
+  const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
+  constitutive_fwd_kernel<<<grid, FWD_THREADS, FWD_SMEM, (cudaStream_t)stream>>>(
+      kind, n, F, (const uint8_t*)staged, alpha, out);
   NEUMA_LAUNCH_CHECK(ctx, "constitutive_fwd_kernel");
   return 0;
 }
 
-int neuma_constitutive_bwd(neuma_ctx* ctx, int kind, int n, int hidden, const float* F,
-                           const float* W0, const float* W1, const float* W2, float alpha,
-                           const float* gout, float* gF, float* gW0, float* gW1, float* gW2,
-                           void* stream) {
-  if (!ctx) return 2;
-  if (hidden != H) return neuma_fail_msg(ctx, "neuma_constitutive: only hidden width 64 is built");
-  if (kind < 0 || kind > 2) return neuma_fail_msg(ctx, "neuma_constitutive: kind must be 0, 1 or 2");
+int neuma_constitutive_bwd_staged(neuma_ctx* ctx, int kind, int n, int hidden, const float* F,
+                                  const void* staged, float alpha, const float* gout, float* gF,
+                                  float* gW0, float* gW1, float* gW2, void* stream) {
+  if (int r = check_args(ctx, kind, hidden)) return r;
   if (n <= 0) return 0;
   if (int r = set_attrs(ctx)) return r;
   const bool wgrad = gW0 && gW1 && gW2;
@@ -758,13 +878,35 @@ int neuma_constitutive_bwd(neuma_ctx* ctx, int kind, int n, int hidden, const fl
   const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
   cudaStream_t st = (cudaStream_t)stream;
   if (wgrad)
-    constitutive_bwd_kernel<true><<<grid, NT, BWD_SMEM, st>>>(kind, n, F, W0, W1, W2, alpha, gout,
-                                                              gF, gW0, gW1, gW2);
+    constitutive_bwd_kernel<true><<<grid, BWD_THREADS, BWD_SMEM, st>>>(
+        kind, n, F, (const uint8_t*)staged, alpha, gout, gF, gW0, gW1, gW2);
   else
-    constitutive_bwd_kernel<false><<<grid, NT, BWD_SMEM, st>>>(kind, n, F, W0, W1, W2, alpha, gout,
-                                                               gF, gW0, gW1, gW2);
+    constitutive_bwd_kernel<false><<<grid, BWD_THREADS, BWD_SMEM, st>>>(
+        kind, n, F, (const uint8_t*)staged, alpha, gout, gF, gW0, gW1, gW2);
   NEUMA_LAUNCH_CHECK(ctx, "constitutive_bwd_kernel");
   return 0;
+}
+
+int neuma_constitutive_fwd(neuma_ctx* ctx, int kind, int n, int hidden, const float* F,
+                           const float* W0, const float* W1, const float* W2, float alpha,
+                           float* out, void* stream) {
+  if (int r = check_args(ctx, kind, hidden)) return r;
+  if (n <= 0) return 0;
+  if (int r = neuma_ensure_wstage(ctx, STAGED_BYTES)) return r;
+  if (int r = neuma_constitutive_stage(ctx, hidden, W0, W1, W2, ctx->wstage, stream)) return r;
+  return neuma_constitutive_fwd_staged(ctx, kind, n, hidden, F, ctx->wstage, alpha, out, stream);
+}
+
+int neuma_constitutive_bwd(neuma_ctx* ctx, int kind, int n, int hidden, const float* F,
+                           const float* W0, const float* W1, const float* W2, float alpha,
+                           const float* gout, float* gF, float* gW0, float* gW1, float* gW2,
+                           void* stream) {
+  if (int r = check_args(ctx, kind, hidden)) return r;
+  if (n <= 0) return 0;
+  if (int r = neuma_ensure_wstage(ctx, STAGED_BYTES)) return r;
+  if (int r = neuma_constitutive_stage(ctx, hidden, W0, W1, W2, ctx->wstage, stream)) return r;
+  return neuma_constitutive_bwd_staged(ctx, kind, n, hidden, F, ctx->wstage, alpha, gout, gF, gW0,
+                                       gW1, gW2, stream);
 }
 
 }  // extern "C"

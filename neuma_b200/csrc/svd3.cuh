@@ -51,19 +51,9 @@ __device__ __forceinline__ void sort_swap(float B[3][3], float V[3][3], float n[
   }
 }
 
-// A = U diag(sig) V^T, U and V rotations.
-__device__ __forceinline__ void svd3(const Mat3& A, Mat3& U, float sig[3], Mat3& Vout) {
-  float S[3][3], V[3][3] = {{1.f, 0.f, 0.f}, {0.f, 1.f, 0.f}, {0.f, 0.f, 1.f}};
-#pragma unroll
-  for (int i = 0; i < 3; ++i)
-#pragma unroll
-    for (int j = 0; j < 3; ++j) S[i][j] = A(0, i) * A(0, j) + A(1, i) * A(1, j) + A(2, i) * A(2, j);
-#pragma unroll 1
-  for (int sweep = 0; sweep < 6; ++sweep) {
-    jacobi_rotate<0, 1>(S, V);
-    jacobi_rotate<0, 2>(S, V);
-    jacobi_rotate<1, 2>(S, V);
-  }
+// sort + Gram-Schmidt tail shared by svd3 / svd3_fast: given V (rotation diagonalising
+// A^T A) produce U, sigma and the column-sorted V.
+__device__ __forceinline__ void svd3_finish(const Mat3& A, float V[3][3], Mat3& U, float sig[3], Mat3& Vout) {
   float B[3][3], n[3];
 #pragma unroll
   for (int i = 0; i < 3; ++i)
@@ -111,6 +101,84 @@ __device__ __forceinline__ void svd3(const Mat3& A, Mat3& U, float sig[3], Mat3&
 #pragma unroll
     for (int j = 0; j < 3; ++j) Vout(k, j) = V[k][j];
   }
+}
+
+// A = U diag(sig) V^T, U and V rotations.
+__device__ __forceinline__ void svd3(const Mat3& A, Mat3& U, float sig[3], Mat3& Vout) {
+  float S[3][3], V[3][3] = {{1.f, 0.f, 0.f}, {0.f, 1.f, 0.f}, {0.f, 0.f, 1.f}};
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) S[i][j] = A(0, i) * A(0, j) + A(1, i) * A(1, j) + A(2, i) * A(2, j);
+#pragma unroll 1
+  for (int sweep = 0; sweep < 6; ++sweep) {
+    jacobi_rotate<0, 1>(S, V);
+    jacobi_rotate<0, 2>(S, V);
+    jacobi_rotate<1, 2>(S, V);
+  }
+  svd3_finish(A, V, U, sig, Vout);
+}
+
+// ---- the fused constitutive kernels' variant: same algorithm, but
+//   * the Givens parameters use the MUFU approximations (rcp / sqrt / rsqrt .approx): the
+//     rotation ANGLE only steers convergence; c^2 + s^2 = 1 holds to ~2 ulp per rotation;
+//   * sweeps stop as soon as every lane of the warp has converged (quadratic convergence:
+//     3 sweeps for F within ~0.1 of a rotation, 6 at most).
+// Must be called by all 32 lanes of a warp.
+__device__ __forceinline__ float mufu_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float mufu_sqrt(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float mufu_rsqrt(float x) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+template <int P, int Q>
+__device__ __forceinline__ void jacobi_rotate_fast(float S[3][3], float V[3][3]) {
+  const float apq = S[P][Q];
+  const bool skip = fabsf(apq) < 1e-37f;
+  const float theta = (S[Q][Q] - S[P][P]) * mufu_rcp(skip ? 2.0f : 2.0f * apq);
+  float t = copysignf(mufu_rcp(fabsf(theta) + mufu_sqrt(fmaf(theta, theta, 1.0f))), theta);
+  t = skip ? 0.0f : t;
+  const float c = mufu_rsqrt(fmaf(t, t, 1.0f));
+  const float s = t * c;
+  constexpr int R = 3 - P - Q;
+  S[P][P] -= t * apq;
+  S[Q][Q] += t * apq;
+  S[P][Q] = S[Q][P] = 0.0f;
+  const float arp = S[R][P], arq = S[R][Q];
+  S[R][P] = S[P][R] = c * arp - s * arq;
+  S[R][Q] = S[Q][R] = s * arp + c * arq;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float vp = V[k][P], vq = V[k][Q];
+    V[k][P] = c * vp - s * vq;
+    V[k][Q] = s * vp + c * vq;
+  }
+}
+__device__ __forceinline__ void svd3_fast(const Mat3& A, Mat3& U, float sig[3], Mat3& Vout) {
+  float S[3][3], V[3][3] = {{1.f, 0.f, 0.f}, {0.f, 1.f, 0.f}, {0.f, 0.f, 1.f}};
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) S[i][j] = A(0, i) * A(0, j) + A(1, i) * A(1, j) + A(2, i) * A(2, j);
+#pragma unroll 1
+  for (int sweep = 0; sweep < 6; ++sweep) {
+    jacobi_rotate_fast<0, 1>(S, V);
+    jacobi_rotate_fast<0, 2>(S, V);
+    jacobi_rotate_fast<1, 2>(S, V);
+    const float off = fabsf(S[0][1]) + fabsf(S[0][2]) + fabsf(S[1][2]);
+    const float tr = S[0][0] + S[1][1] + S[2][2];
+    if (__all_sync(0xffffffffu, off <= 1e-7f * tr)) break;
+  }
+  svd3_finish(A, V, U, sig, Vout);
 }
 
 __device__ __forceinline__ float signed_floor(float d, float eps) {

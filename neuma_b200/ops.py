@@ -351,3 +351,26 @@ def invert_perm(perm: torch.Tensor) -> torch.Tensor:
     inv = torch.empty_like(perm)
     _ctx(perm).call("neuma_invert_perm", perm.shape[0], ptr(perm), ptr(inv), _stream(perm))
     return inv
+
+
+# --------------------------------------------------------------------- staged constitutive weights
+def constitutive_stage(W0, W1, W2, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Split / lay out the three Linear weights once (tensor-core operand image); reuse the
+    returned buffer for every constitutive_*_staged call until the weights change."""
+    W0, W1, W2 = map(_f32, (W0, W1, W2))
+    ctx = _ctx(W0)
+    if out is None:
+        out = torch.empty(int(ctx.lib.neuma_constitutive_staged_bytes()), dtype=torch.uint8, device=W0.device)
+    ctx.call("neuma_constitutive_stage", W1.shape[0], ptr(W0), ptr(W1), ptr(W2), ptr(out), _stream(W0))
+    return out
+
+
+def constitutive_fwd_staged(kind: int, F, staged, alpha: float, out, hidden: int = 64) -> None:
+    _ctx(F).call("neuma_constitutive_fwd_staged", int(kind), F.shape[0], hidden, ptr(F), ptr(staged),
+                 C.c_float(alpha), ptr(out), _stream(F))
+
+
+def constitutive_bwd_staged(kind: int, F, staged, alpha: float, gout, gF, gW0, gW1, gW2, hidden: int = 64) -> None:
+    """gW* are accumulated into (not zeroed)."""
+    _ctx(F).call("neuma_constitutive_bwd_staged", int(kind), F.shape[0], hidden, ptr(F), ptr(staged),
+                 C.c_float(alpha), ptr(gout), ptr(gF), ptr(gW0), ptr(gW1), ptr(gW2), _stream(F))

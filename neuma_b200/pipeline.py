@@ -46,6 +46,9 @@ class FusedFrame:
         self.inv = self.perm.clone()                                    # caller index -> sorted slot
         self.We = [w.detach().contiguous() for w in We]
         self.Wp = [w.detach().contiguous() for w in Wp]
+        # tensor-core operand images of the weights, refreshed by set_weights()
+        self.We_st = ops.constitutive_stage(*self.We)
+        self.Wp_st = ops.constitutive_stage(*self.Wp)
         self.alpha = float(alpha)
         self.kind_e = elastic_kind
         self.bind, self.gs, self.settings = bind, gaussians, settings
@@ -82,12 +85,12 @@ class FusedFrame:
         c = self.c
         for s in range(self.S):
             ctx = self._ctx
-            ops.constitutive_fwd_into(self.kind_e, self.F[s], *self.We, 0.0, self.stress[s])
+            ops.constitutive_fwd_staged(self.kind_e, self.F[s], self.We_st, 0.0, self.stress[s])
             ops.mpm_rollout_fwd(c, self.x[s], self.v[s], self.C[s], self.F[s], self.stress[s], self.vol, self.rho,
                                 self.clip, self.enabled,
                                 (self.x[s + 1], self.v[s + 1], self.C[s + 1], self.Ftrial[s]),
                                 self.grid[s], self.adj[s], self.box[s], self.box[s + 1])
-            ops.constitutive_fwd_into(ops.KIND_PLASTIC, self.Ftrial[s], *self.Wp, self.alpha, self.F[s + 1])
+            ops.constitutive_fwd_staged(ops.KIND_PLASTIC, self.Ftrial[s], self.Wp_st, self.alpha, self.F[s + 1])
 
     def _sim_backward(self) -> None:
         """Consumes self.g[0] = dL/d(state[S]); leaves dL/d(state[0]) in self.g[0]
@@ -97,15 +100,15 @@ class FusedFrame:
         for s in reversed(range(self.S)):
             gx2, gv2, gC2, gF_next = self.g[cur]
             # plasticity: F[s+1] = P(Ftrial[s])
-            ops.constitutive_bwd_into(ops.KIND_PLASTIC, self.Ftrial[s], *self.Wp, self.alpha, gF_next,
-                                      self.gFtrial, *self.gWp)
+            ops.constitutive_bwd_staged(ops.KIND_PLASTIC, self.Ftrial[s], self.Wp_st, self.alpha, gF_next,
+                                        self.gFtrial, *self.gWp)
             gx, gv, gC, gF = self.g[nxt]
             ops.mpm_rollout_bwd(c, self.x[s], self.v[s], self.C[s], self.F[s], self.stress[s], self.vol,
                                 self.rho, self.clip, self.enabled, self.v[s + 1], self.C[s + 1],
                                 gx2, gv2, gC2, self.gFtrial, self.grid[s], self.adj[s], self.box[s],
                                 gx, gv, gC, gF, self.gstress)
             # elasticity: stress[s] = E(F[s]);  dL/dF[s] += E'(F[s])^T gstress
-            ops.constitutive_bwd_into(self.kind_e, self.F[s], *self.We, 0.0, self.gstress, self.gF_e, *self.gWe)
+            ops.constitutive_bwd_staged(self.kind_e, self.F[s], self.We_st, 0.0, self.gstress, self.gF_e, *self.gWe)
             gF.add_(self.gF_e)
             cur, nxt = nxt, cur
         if cur != 0:
@@ -184,6 +187,16 @@ class FusedFrame:
                     dst.copy_(src)
             self._g_bwd.replay()
         return [self._to_caller(t) for t in self.g[0]]
+
+    def set_weights(self, We=None, Wp=None) -> None:
+        """New (LoRA-merged) weights, e.g. after an optimiser step: copied into the engine's static
+        buffers and re-staged, so captured graphs stay valid."""
+        for dst, src, st in ((self.We, We, self.We_st), (self.Wp, Wp, self.Wp_st)):
+            if src is None:
+                continue
+            for d, s_ in zip(dst, src):
+                d.copy_(s_)
+            ops.constitutive_stage(*dst, out=st)
 
     def zero_weight_grads(self) -> None:
         for t in self.gWe + self.gWp:
