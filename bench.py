@@ -246,7 +246,7 @@ def run_gpu(args):
     outb = tuple(torch.empty_like(t_) for t_ in (xs, vs, Cs, Fs))
     gout = [torch.randn_like(t_) for t_ in outb]
     gF_ = torch.empty_like(Fs)
-    gWt = [torch.zeros_like(w) for w in We]
+    part_tmp = ops.constitutive_partials(Fs)
     gouts5 = [torch.empty_like(t_) for t_ in (xs, vs, Cs, Fs, st)]
     it, wm = 20, 3
     kt = {}
@@ -265,12 +265,28 @@ def run_gpu(args):
     kt["mpm_substep_bwd"] = event_time_us(_bwd, it, wm, flush)
     kt["constitutive_fwd"] = event_time_us(lambda: ops.constitutive_fwd_staged(0, Fs, eng.We_st, 0.0, gF_), it, wm, flush)
     kt["constitutive_bwd"] = event_time_us(
-        lambda: ops.constitutive_bwd_staged(0, Fs, eng.We_st, 0.0, gout[3], gF_, *gWt), it, wm, flush)
+        lambda: ops.constitutive_bwd_partials(0, Fs, eng.We_st, 0.0, gout[3], gF_, part_tmp), it, wm, flush)
     rs = eng._render_saved
     kt["raster_fwd"] = event_time_us(lambda: ops.raster_fwd(settings, rs[0], gs["shs"], None, gs["opac"], rs[1]), 10, 2, flush)
     dimg = torch.randn(3, IMAGE, IMAGE, device=dev)
     kt["raster_bwd"] = event_time_us(
         lambda: ops.raster_bwd(settings, rs[0], gs["shs"], None, gs["opac"], rs[1], rs[2], dimg), 10, 2, flush)
+    # in-situ breakdown of the frame (CUDA-graph replays / render calls, events, no flush)
+    def _ms(fn, reps=5):
+        fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        b.synchronize()
+        return a.elapsed_time(b) / reps
+    gz = [torch.zeros_like(t_) for t_ in (x0, v0, C0, F0)]
+    frame_ms = {"sim_fwd_graph": _ms(lambda: eng.sim_forward()),
+                "sim_bwd_graph": _ms(lambda: eng.sim_backward(*gz)),
+                "render_fwd": _ms(lambda: eng.render_forward(de_x_prev, k_prev)),
+                "render_bwd": _ms(lambda: eng.render_backward(dimg))}
     nr = ops.raster_binning(x0, 50 * 50)[0].shape[0]
     per_frame_us = {"constitutive_bwd": 2 * S * kt["constitutive_bwd"], "constitutive_fwd": 2 * S * kt["constitutive_fwd"],
                     "mpm_fwd(clear+p2g+grid_op+g2p)": S * (kt["grid_clear"] + kt["p2g"] + kt["grid_op"] + kt["g2p"]),
@@ -315,6 +331,7 @@ def run_gpu(args):
         "mpm_fwd_substep_gbs": mpm_fwd_gbs,
         "kernel_us": {k: round(v, 2) for k, v in kt.items()},
         "frame_share_us": {k: round(v, 1) for k, v in per_frame_us.items()},
+        "frame_ms_in_situ": {k: round(v, 3) for k, v in frame_ms.items()},
         "roofline": roof,
         "e2e": {"value": world * 1000.0 / e2e_ms_per_step, "unit": "frames/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms_per_step},

@@ -230,6 +230,17 @@ int neuma_constitutive_bwd_staged(neuma_ctx* ctx, int kind, int n, int hidden, c
                                   const void* staged, float alpha, const float* gout, float* gF,
                                   float* gW0, float* gW1, float* gW2, void* stream);
 
+/* Weight gradients without atomics: every CTA adds into its own slot of `gWpart`
+ * (neuma_constitutive_partials_floats(ctx) floats, zero-initialised by the caller once);
+ * neuma_constitutive_reduce_partials adds the slot sum into gW0/gW1/gW2 and zeroes the
+ * slots.  A rollout calls the first 2 x S times per frame and the second once. */
+int neuma_constitutive_partials_floats(neuma_ctx* ctx);
+int neuma_constitutive_bwd_partials(neuma_ctx* ctx, int kind, int n, int hidden, const float* F,
+                                    const void* staged, float alpha, const float* gout, float* gF,
+                                    float* gWpart, void* stream);
+int neuma_constitutive_reduce_partials(neuma_ctx* ctx, int hidden, float* gWpart, float* gW0,
+                                       float* gW1, float* gW2, void* stream);
+
 /* ---- particle -> Gaussian binding: modules/tune/utils.py:424-472 ------- */
 /* out[K,ncol] = B in[Np,ncol] (transpose=0) or out[Np,ncol] = B^T in[K,ncol]
  * (transpose=1, the backward), B in CSR (rowptr[K+1], col[nnz], w[nnz]). */

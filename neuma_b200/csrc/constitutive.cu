@@ -45,6 +45,24 @@
 #include "svd3.cuh"
 #include "umma.cuh"
 
+// Developer instrumentation (tools/phase_timing.py builds a copy with -DNEUMA_PHASE_TIMING):
+// thread 0 of CTA 0 accumulates clock64() deltas per phase of its pipeline.
+#ifdef NEUMA_PHASE_TIMING
+__device__ long long g_phase_cycles[32];
+#define PHASE_T0() long long pt__ = clock64()
+#define PHASE(i)                                             \
+  do {                                                       \
+    if (blockIdx.x == 0 && threadIdx.x == 0) {               \
+      const long long t__ = clock64();                       \
+      g_phase_cycles[i] += t__ - pt__;                       \
+      pt__ = t__;                                            \
+    }                                                        \
+  } while (0)
+#else
+#define PHASE_T0()
+#define PHASE(i)
+#endif
+
 namespace {
 
 constexpr int H = 64;      // hidden width (layer_widths: [64, 64] in every shipped config)
@@ -85,6 +103,15 @@ __device__ __forceinline__ Mat3 load_F_or_identity(const float* __restrict__ F, 
   return m;
 }
 
+// pull a particle's 36-byte row towards L1 ahead of its use (next tile's F, this tile's dL/dout)
+__device__ __forceinline__ void prefetch_row(const float* __restrict__ base, int p, int n) {
+  if (p < n) {
+    const char* a = reinterpret_cast<const char*>(base + (size_t)p * 9);
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(a));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(a + 32));
+  }
+}
+
 // ---- shared-memory / staged-image map (bytes)
 constexpr uint32_t SMALL_SPLIT = TP * KF * 2;  // [128 x 16] activation tile, one split
 constexpr uint32_t BIG_SPLIT = TP * H * 2;     // [128 x 64] activation tile, one split
@@ -117,6 +144,8 @@ constexpr uint32_t BWD_PIPE_COLS = 192, COL_H1 = 0, COL_H2 = 64, COL_S = 128;
 // shared weight-gradient accumulators (M = 64 layout: row o -> lane (o%16) + 32 (o/16))
 constexpr uint32_t COL_GW1 = NPIPE_BWD * BWD_PIPE_COLS, COL_GW0 = COL_GW1 + 64, COL_GW2T = COL_GW0 + 16;
 constexpr uint32_t BWD_TMEM_COLS = 512;
+// per-CTA weight-gradient partial sums: [dW1 64x64 | dW0 64x13 | dW2 9x64]
+constexpr int GW_OFF0 = H * H, GW_OFF2 = GW_OFF0 + H * NF, GW_FLOATS = GW_OFF2 + 9 * H;  // 5504
 static_assert(COL_GW2T + 16 <= BWD_TMEM_COLS, "TMEM budget");
 static_assert(NPIPE_FWD * FWD_PIPE_COLS <= FWD_TMEM_COLS, "TMEM budget");
 
@@ -204,15 +233,18 @@ __device__ __forceinline__ Desc desc_mnmajor(uint32_t addr, uint32_t split_bytes
 template <int NS, int NK>
 __device__ __forceinline__ void gemm_split(uint32_t tmem_d, const Desc a, const Desc b, uint32_t idesc,
                                            bool accumulate) {
-#pragma unroll
-  for (int k = 0; k < NK; ++k)
+  // K loop deliberately rolled: the MMA warp's code must stay small (instruction cache is shared
+  // with two or three compute pipelines running different phases)
+#pragma unroll 1
+  for (int k = 0; k < NK; ++k) {
+    const uint64_t ak = a.d + (uint64_t)(k * a.kstep), bk = b.d + (uint64_t)(k * b.kstep);
 #pragma unroll
     for (int i = 0; i < NS; ++i)
 #pragma unroll
       for (int j = 0; j < NS - i; ++j)
-        umma::mma_bf16_ss(tmem_d, a.d + (uint64_t)(i * a.split + k * a.kstep),
-                          b.d + (uint64_t)(j * b.split + k * b.kstep), idesc,
+        umma::mma_bf16_ss(tmem_d, ak + (uint64_t)(i * a.split), bk + (uint64_t)(j * b.split), idesc,
                           (accumulate || k || i || j) ? 1u : 0u);
+  }
 }
 
 // Phi(h) and phi(h) of the standard normal for the exact-erf GELU (nn.GELU() default,
@@ -282,7 +314,7 @@ struct PipeSync {
 // GEMM's A operand and, in the backward, put gelu'() back into the same TMEM columns.
 template <int NS, bool KEEP_GRAD>
 __device__ __forceinline__ void gelu_phase(uint32_t t_acc, uint8_t* img, int r) {
-#pragma unroll
+#pragma unroll 1
   for (int q = 0; q < 4; ++q) {
     float h[16], a[16];
     umma::tmem_ld16(t_acc + 16 * q, h);
@@ -305,21 +337,17 @@ __device__ __forceinline__ void gelu_phase(uint32_t t_acc, uint8_t* img, int r) 
 template <int NS>
 __device__ __forceinline__ void grad_phase(uint32_t t_acc, uint32_t t_dgelu, uint8_t* img, int r,
                                            PipeSync& ps, bool wait_w) {
-  float g[4][16];
-#pragma unroll
+  if (wait_w) ps.wait_wdone();
+#pragma unroll 1
   for (int q = 0; q < 4; ++q) {
-    float d[16];
-    umma::tmem_ld16(t_acc + 16 * q, g[q]);
+    float g[16], d[16];
+    umma::tmem_ld16(t_acc + 16 * q, g);
     umma::tmem_ld16(t_dgelu + 16 * q, d);
     umma::tmem_wait_ld();
 #pragma unroll
-    for (int i = 0; i < 16; ++i) g[q][i] *= d[i];
-  }
-  if (wait_w) ps.wait_wdone();
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    store_chunk<NS>(img, BIG_SPLIT, 2 * q, r, g[q]);
-    store_chunk<NS>(img, BIG_SPLIT, 2 * q + 1, r, g[q] + 8);
+    for (int i = 0; i < 16; ++i) g[i] *= d[i];
+    store_chunk<NS>(img, BIG_SPLIT, 2 * q, r, g);
+    store_chunk<NS>(img, BIG_SPLIT, 2 * q + 1, r, g + 8);
   }
 }
 
@@ -446,6 +474,7 @@ constitutive_fwd_kernel(int kind, int n, const float* __restrict__ F, const uint
         store_chunk<NS>(pm + P::OFF_FEAT, SMALL_SPLIT, 1, r, f + 8);
       }
       ps.publish();                                            // -> h1 = feat W0^T
+      prefetch_row(F, pi + chains * TP, n);
       ps.wait_done();
       gelu_phase<NS, false>(tacc, pm + P::OFF_BIGA, r);
       ps.publish();                                            // -> h2 = a1 W1^T
@@ -480,7 +509,8 @@ template <bool WGRAD>
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 constitutive_bwd_kernel(int kind, int n, const float* __restrict__ F, const uint8_t* __restrict__ staged,
                         float alpha, const float* __restrict__ gout, float* __restrict__ gF,
-                        float* __restrict__ gW0, float* __restrict__ gW1, float* __restrict__ gW2) {
+                        float* __restrict__ gW0, float* __restrict__ gW1, float* __restrict__ gW2,
+                        float* __restrict__ gWpart) {
   constexpr int NS = NS_BWD, NPIPE = NPIPE_BWD;
   using W = WImg<NS>;
   using P = PipeBwd<NS>;
@@ -488,8 +518,20 @@ constitutive_bwd_kernel(int kind, int n, const float* __restrict__ F, const uint
   __shared__ Bars bars;
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5;
+#ifdef NEUMA_PHASE_TIMING
+  long long kt__ = clock64();
+  if (threadIdx.x == 0) {
+    unsigned long long ns; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+    atomicMin((unsigned long long*)&g_phase_cycles[24], ns);
+    if (blockIdx.x == 0) g_phase_cycles[26] = clock64();
+  }
+#define KPHASE(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) { const long long t__ = clock64(); g_phase_cycles[i] += t__ - kt__; kt__ = t__; } } while (0)
+#else
+#define KPHASE(i)
+#endif
   const uint32_t tmem = block_setup<NPIPE>(&bars, &tmem_slot, sm, staged + STAGED_OFF_BWD, W::BYTES,
                                            BWD_TMEM_COLS, NPIPE * 4);
+  KPHASE(16);
   const uint32_t smem = umma::smem_u32(sm);
   const int tiles = (n + TP - 1) / TP;
   const int chains = gridDim.x * NPIPE;
@@ -585,13 +627,16 @@ constitutive_bwd_kernel(int kind, int n, const float* __restrict__ F, const uint
     const uint32_t tl = tmem + ((uint32_t)((warp & 3) * 32) << 16) + p * BWD_PIPE_COLS;
     PipeSync ps{umma::smem_u32(&bars.full[p]), umma::smem_u32(&bars.done[p]), umma::smem_u32(&bars.wdone[p]), 0u, 0u};
     bool first = true;
+    PHASE_T0();
     for (int tile = p * gridDim.x + blockIdx.x; tile < tiles; tile += chains, first = false) {
       const int pi = tile * TP + r;
       const bool live = pi < n;
       Kinematics k;
       kinematics(load_F_or_identity(F, pi, n), kind != 2, k);
+      PHASE(0);
       // FEAT / BIGA were last read by the previous tile's dW0 GEMM
       if (WGRAD && !first) ps.wait_wdone();
+      PHASE(15);
       {
         float f[KF];
 #pragma unroll
@@ -600,13 +645,21 @@ constitutive_bwd_kernel(int kind, int n, const float* __restrict__ F, const uint
         store_chunk<NS>(pm + P::OFF_FEAT, SMALL_SPLIT, 1, r, f + 8);
       }
       ps.publish();                                              // job 0
+      prefetch_row(gout, pi, n);
+      prefetch_row(F, pi + chains * TP, n);
+      PHASE(1);
       ps.wait_done();
+      PHASE(2);
       gelu_phase<NS, true>(tl + COL_H1, pm + P::OFF_BIGA, r);    // a1; gelu'(h1) stays in TMEM
       ps.publish();                                              // job 1
+      PHASE(3);
       ps.wait_done();
+      PHASE(4);
       gelu_phase<NS, true>(tl + COL_H2, pm + P::OFF_BIGB, r);    // a2; gelu'(h2)
       ps.publish();                                              // job 2
+      PHASE(5);
       ps.wait_done();
+      PHASE(6);
       // ---- output head: dL/dout -> dL/d(MLP output), dL/dR, direct dL/dF
       Mat3 gR, gFd;
       {
@@ -638,13 +691,19 @@ constitutive_bwd_kernel(int kind, int n, const float* __restrict__ F, const uint
         store_chunk<NS>(pm + P::OFF_GO, SMALL_SPLIT, 1, r, g9 + 8);
       }
       ps.publish();                                              // job 3
+      PHASE(7);
       ps.wait_done();
+      PHASE(8);
       grad_phase<NS>(tl + COL_S, tl + COL_H2, pm + P::OFF_BIGB, r, ps, WGRAD);   // g2 over a2 (after dW2)
       ps.publish();                                              // job 4
+      PHASE(9);
       ps.wait_done();
+      PHASE(10);
       grad_phase<NS>(tl + COL_S, tl + COL_H1, pm + P::OFF_BIGA, r, ps, WGRAD);   // g1 over a1 (after dW1)
       ps.publish();                                              // job 5
+      PHASE(11);
       ps.wait_done();
+      PHASE(12);
       // ---- invariants -> F
       float gfeat[16];
       umma::tmem_ld16(tl + COL_S, gfeat);
@@ -689,40 +748,84 @@ constitutive_bwd_kernel(int kind, int n, const float* __restrict__ F, const uint
         }
         mat3_store(gF + (size_t)pi * 9, gFt);
       }
+      PHASE(13);
     }
     if (WGRAD && !first) ps.wait_wdone();  // the last tile's dW0 GEMM
+    PHASE(14);
   }
+  KPHASE(17);
   umma::fence_before_sync();
   __syncthreads();
   umma::fence_after_sync();
+  KPHASE(18);
   if (WGRAD && warp < 4) {
     // every weight-gradient MMA of the CTA has completed (each pipeline waited for its last one).
     // M = 64 accumulators: lane 32*q + i (i < 16) holds row 16*q + i.
     const uint32_t tl0 = tmem + ((uint32_t)(warp * 32) << 16);
     const int i16 = tid & 31, row = warp * 16 + i16;
     float a[16];
+    if (gWpart) {
+      // this CTA's private slot of the partial-sum buffer: plain read-modify-write, no atomics
+      // (148 CTAs x 5504 same-address atomics cost ~25% of the kernel); reduced once per frame
+      // by reduce_partials_kernel.
+      float* part = gWpart + (size_t)blockIdx.x * GW_FLOATS;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      umma::tmem_ld16(tl0 + COL_GW1 + 16 * c, a);
+      for (int c = 0; c < 4; ++c) {
+        umma::tmem_ld16(tl0 + COL_GW1 + 16 * c, a);
+        umma::tmem_wait_ld();
+        if (i16 < 16) {
+          float4* q = reinterpret_cast<float4*>(part + row * H + 16 * c);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float4 t = q[j];
+            t.x += a[4 * j]; t.y += a[4 * j + 1]; t.z += a[4 * j + 2]; t.w += a[4 * j + 3];
+            q[j] = t;
+          }
+        }
+      }
+      umma::tmem_ld16(tl0 + COL_GW0, a);
       umma::tmem_wait_ld();
       if (i16 < 16)
 #pragma unroll
-        for (int j = 0; j < 16; ++j) atomicAdd(gW1 + row * H + 16 * c + j, a[j]);
+        for (int j = 0; j < NF; ++j) part[GW_OFF0 + row * NF + j] += a[j];
+      umma::tmem_ld16(tl0 + COL_GW2T, a);
+      umma::tmem_wait_ld();
+      if (i16 < 16)
+#pragma unroll
+        for (int j = 0; j < 9; ++j) part[GW_OFF2 + j * H + row] += a[j];
+    } else {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        umma::tmem_ld16(tl0 + COL_GW1 + 16 * c, a);
+        umma::tmem_wait_ld();
+        if (i16 < 16)
+#pragma unroll
+          for (int j = 0; j < 16; ++j) atomicAdd(gW1 + row * H + 16 * c + j, a[j]);
+      }
+      umma::tmem_ld16(tl0 + COL_GW0, a);
+      umma::tmem_wait_ld();
+      if (i16 < 16)
+#pragma unroll
+        for (int j = 0; j < NF; ++j) atomicAdd(gW0 + row * NF + j, a[j]);
+      umma::tmem_ld16(tl0 + COL_GW2T, a);
+      umma::tmem_wait_ld();
+      if (i16 < 16)
+#pragma unroll
+        for (int j = 0; j < 9; ++j) atomicAdd(gW2 + j * H + row, a[j]);
     }
-    umma::tmem_ld16(tl0 + COL_GW0, a);
-    umma::tmem_wait_ld();
-    if (i16 < 16)
-#pragma unroll
-      for (int j = 0; j < NF; ++j) atomicAdd(gW0 + row * NF + j, a[j]);
-    umma::tmem_ld16(tl0 + COL_GW2T, a);
-    umma::tmem_wait_ld();
-    if (i16 < 16)
-#pragma unroll
-      for (int j = 0; j < 9; ++j) atomicAdd(gW2 + j * H + row, a[j]);
   }
+  KPHASE(19);
   umma::fence_before_sync();
   __syncthreads();
   if (warp == 0) umma::tmem_dealloc(tmem, BWD_TMEM_COLS);
+  KPHASE(20);
+#ifdef NEUMA_PHASE_TIMING
+  if (threadIdx.x == 0) {
+    unsigned long long ns; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+    atomicMax((unsigned long long*)&g_phase_cycles[25], ns);
+    if (blockIdx.x == 0) { g_phase_cycles[27] = clock64(); g_phase_cycles[28] = (long long)ns; }
+  }
+#endif
 }
 
 // ------------------------------------------------------------------ stand-alone SVD
@@ -795,6 +898,22 @@ svd3_bwd_kernel(int n, const float* __restrict__ U, const float* __restrict__ si
   mat3_store(gA + (size_t)p * 9, mat3_mul(mat3_mul(u, inner), vh));
 }
 
+// gW += sum over the CTA slots of the partial buffer; the slots are zeroed for the next frame
+__global__ void __launch_bounds__(256)
+reduce_partials_kernel(int slots, float* __restrict__ part, float* __restrict__ gW0,
+                       float* __restrict__ gW1, float* __restrict__ gW2) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= GW_FLOATS) return;
+  float acc = 0.f;
+  for (int sidx = 0; sidx < slots; ++sidx) {
+    acc += part[(size_t)sidx * GW_FLOATS + e];
+    part[(size_t)sidx * GW_FLOATS + e] = 0.f;
+  }
+  if (e < GW_OFF0) gW1[e] += acc;
+  else if (e < GW_OFF2) gW0[e - GW_OFF0] += acc;
+  else gW2[e - GW_OFF2] += acc;
+}
+
 bool g_attr_set = false;
 
 int set_attrs(neuma_ctx* ctx) {
@@ -842,6 +961,19 @@ int neuma_svd3_bwd(neuma_ctx* ctx, int n, const float* U, const float* sigma, co
 
 int neuma_constitutive_staged_bytes(void) { return (int)STAGED_BYTES; }
 
+#ifdef NEUMA_PHASE_TIMING
+int neuma_debug_phase_cycles(long long* out_host, int reset) {
+  cudaDeviceSynchronize();
+  if (out_host) cudaMemcpyFromSymbol(out_host, g_phase_cycles, sizeof(g_phase_cycles));
+  if (reset) {
+    long long z[32] = {0};
+    z[24] = 0x7fffffffffffffffLL;
+    cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z));
+  }
+  return 0;
+}
+#endif
+
 int neuma_constitutive_stage(neuma_ctx* ctx, int hidden, const float* W0, const float* W1,
                              const float* W2, void* staged, void* stream) {
   if (int r = check_args(ctx, 0, hidden)) return r;
@@ -879,11 +1011,39 @@ int neuma_constitutive_bwd_staged(neuma_ctx* ctx, int kind, int n, int hidden, c
   cudaStream_t st = (cudaStream_t)stream;
   if (wgrad)
     constitutive_bwd_kernel<true><<<grid, BWD_THREADS, BWD_SMEM, st>>>(
-        kind, n, F, (const uint8_t*)staged, alpha, gout, gF, gW0, gW1, gW2);
+        kind, n, F, (const uint8_t*)staged, alpha, gout, gF, gW0, gW1, gW2, nullptr);
   else
     constitutive_bwd_kernel<false><<<grid, BWD_THREADS, BWD_SMEM, st>>>(
-        kind, n, F, (const uint8_t*)staged, alpha, gout, gF, gW0, gW1, gW2);
+        kind, n, F, (const uint8_t*)staged, alpha, gout, gF, gW0, gW1, gW2, nullptr);
   NEUMA_LAUNCH_CHECK(ctx, "constitutive_bwd_kernel");
+  return 0;
+}
+
+int neuma_constitutive_partials_floats(neuma_ctx* ctx) { return ctx ? ctx->num_sms * GW_FLOATS : 0; }
+
+int neuma_constitutive_bwd_partials(neuma_ctx* ctx, int kind, int n, int hidden, const float* F,
+                                    const void* staged, float alpha, const float* gout, float* gF,
+                                    float* gWpart, void* stream) {
+  if (int r = check_args(ctx, kind, hidden)) return r;
+  if (!gWpart) return neuma_fail_msg(ctx, "neuma_constitutive_bwd_partials: gWpart is NULL");
+  if (n <= 0) return 0;
+  if (int r = set_attrs(ctx)) return r;
+  const int tiles = (n + TP - 1) / TP;
+  const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
+  constitutive_bwd_kernel<true><<<grid, BWD_THREADS, BWD_SMEM, (cudaStream_t)stream>>>(
+      kind, n, F, (const uint8_t*)staged, alpha, gout, gF, nullptr, nullptr, nullptr, gWpart);
+  NEUMA_LAUNCH_CHECK(ctx, "constitutive_bwd_kernel");
+  return 0;
+}
+
+int neuma_constitutive_reduce_partials(neuma_ctx* ctx, int hidden, float* gWpart, float* gW0,
+                                       float* gW1, float* gW2, void* stream) {
+  if (int r = check_args(ctx, 0, hidden)) return r;
+  if (!gWpart || !gW0 || !gW1 || !gW2)
+    return neuma_fail_msg(ctx, "neuma_constitutive_reduce_partials: NULL argument");
+  reduce_partials_kernel<<<(GW_FLOATS + 255) / 256, 256, 0, (cudaStream_t)stream>>>(ctx->num_sms, gWpart,
+                                                                                   gW0, gW1, gW2);
+  NEUMA_LAUNCH_CHECK(ctx, "reduce_partials_kernel");
   return 0;
 }
 

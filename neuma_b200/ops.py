@@ -374,3 +374,21 @@ def constitutive_bwd_staged(kind: int, F, staged, alpha: float, gout, gF, gW0, g
     """gW* are accumulated into (not zeroed)."""
     _ctx(F).call("neuma_constitutive_bwd_staged", int(kind), F.shape[0], hidden, ptr(F), ptr(staged),
                  C.c_float(alpha), ptr(gout), ptr(gF), ptr(gW0), ptr(gW1), ptr(gW2), _stream(F))
+
+
+def constitutive_partials(like: torch.Tensor) -> torch.Tensor:
+    """Zeroed per-CTA weight-gradient partial-sum buffer for constitutive_bwd_partials."""
+    ctx = _ctx(like)
+    nfl = int(ctx.lib.neuma_constitutive_partials_floats(ctx.handle))
+    return torch.zeros(nfl, dtype=torch.float32, device=like.device)
+
+
+def constitutive_bwd_partials(kind: int, F, staged, alpha: float, gout, gF, gWpart, hidden: int = 64) -> None:
+    _ctx(F).call("neuma_constitutive_bwd_partials", int(kind), F.shape[0], hidden, ptr(F), ptr(staged),
+                 C.c_float(alpha), ptr(gout), ptr(gF), ptr(gWpart), _stream(F))
+
+
+def constitutive_reduce_partials(gWpart, gW0, gW1, gW2, hidden: int = 64) -> None:
+    """gW* += sum of the slots; the slots are zeroed."""
+    _ctx(gWpart).call("neuma_constitutive_reduce_partials", hidden, ptr(gWpart), ptr(gW0), ptr(gW1), ptr(gW2),
+                      _stream(gWpart))

@@ -69,6 +69,9 @@ class FusedFrame:
         self.gF_e = torch.empty(n, 3, 3, **f)
         self.gWe = [torch.zeros_like(w) for w in self.We]
         self.gWp = [torch.zeros_like(w) for w in self.Wp]
+        # per-CTA partial sums of the weight gradients (no atomics in the 2 x S backward calls)
+        self.gWe_part = ops.constitutive_partials(self.x)
+        self.gWp_part = ops.constitutive_partials(self.x)
         self.center = torch.zeros(3, **f) if center is None else center.to(**f)
         self.size = torch.ones(3, **f) if size is None else size.to(**f)
         self.use_graphs = use_graphs
@@ -100,17 +103,20 @@ class FusedFrame:
         for s in reversed(range(self.S)):
             gx2, gv2, gC2, gF_next = self.g[cur]
             # plasticity: F[s+1] = P(Ftrial[s])
-            ops.constitutive_bwd_staged(ops.KIND_PLASTIC, self.Ftrial[s], self.Wp_st, self.alpha, gF_next,
-                                        self.gFtrial, *self.gWp)
+            ops.constitutive_bwd_partials(ops.KIND_PLASTIC, self.Ftrial[s], self.Wp_st, self.alpha, gF_next,
+                                          self.gFtrial, self.gWp_part)
             gx, gv, gC, gF = self.g[nxt]
             ops.mpm_rollout_bwd(c, self.x[s], self.v[s], self.C[s], self.F[s], self.stress[s], self.vol,
                                 self.rho, self.clip, self.enabled, self.v[s + 1], self.C[s + 1],
                                 gx2, gv2, gC2, self.gFtrial, self.grid[s], self.adj[s], self.box[s],
                                 gx, gv, gC, gF, self.gstress)
             # elasticity: stress[s] = E(F[s]);  dL/dF[s] += E'(F[s])^T gstress
-            ops.constitutive_bwd_staged(self.kind_e, self.F[s], self.We_st, 0.0, self.gstress, self.gF_e, *self.gWe)
+            ops.constitutive_bwd_partials(self.kind_e, self.F[s], self.We_st, 0.0, self.gstress, self.gF_e,
+                                          self.gWe_part)
             gF.add_(self.gF_e)
             cur, nxt = nxt, cur
+        ops.constitutive_reduce_partials(self.gWe_part, *self.gWe)
+        ops.constitutive_reduce_partials(self.gWp_part, *self.gWp)
         if cur != 0:
             for a, b in zip(self.g[0], self.g[1]):
                 a.copy_(b)
