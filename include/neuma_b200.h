@@ -179,6 +179,22 @@ int neuma_mpm_rollout_bwd(neuma_ctx* ctx, const neuma_mpm_const* c, int n, const
                           const float* gx2, const float* gv2, const float* gC2, const float* gF2,
                           const float* grid_v, float* adj, const int32_t* box, float* gx, float* gv,
                           float* gC, float* gF, float* gstress, void* stream);
+/* the two halves of neuma_mpm_rollout_bwd, for the Z-slab path: scatter adj(G2P) into adj;
+ * [sum adj over the slab overlap planes with the neighbours]; node pass + gather */
+int neuma_mpm_bwd_scatter(neuma_ctx* ctx, const neuma_mpm_const* c, int n, const float* x,
+                          const float* F, const float* clip_bound, const int32_t* enabled,
+                          const float* v2, const float* gx2, const float* gv2, const float* gC2,
+                          const float* gF2, float* adj, void* stream);
+int neuma_mpm_bwd_node_gather(neuma_ctx* ctx, const neuma_mpm_const* c, int n, const float* x,
+                              const float* v, const float* C, const float* F, const float* stress,
+                              const float* vol, const float* rho, const float* clip_bound,
+                              const int32_t* enabled, const float* v2, const float* C2,
+                              const float* gx2, const float* gv2, const float* gC2, const float* gF2,
+                              const float* grid_v, float* adj, const int32_t* box, float* gx,
+                              float* gv, float* gC, float* gF, float* gstress, void* stream);
+/* dst += src over `nodes` packed float4 nodes: the receiving side of the Z-slab halo exchange
+ * (a slab's overlap planes are one contiguous block in the plane-major layout) */
+int neuma_mpm_planes_add(neuma_ctx* ctx, float* dst, const float* src, size_t nodes, void* stream);
 /* permutation that puts the particles in cell (Morton) order of their stencil base:
  * perm[i] = index of the i-th particle in that order.  Not capturable (may grow the ctx
  * scratch). */

@@ -63,6 +63,9 @@ SIGNATURES = {
     "neuma_mpm_g2p_from": [_P, _CP, _I] + [_P] * 11,
     "neuma_mpm_rollout_fwd": [_P, _CP, _I] + [_P] * 18,
     "neuma_mpm_rollout_bwd": [_P, _CP, _I] + [_P] * 24,
+    "neuma_mpm_bwd_scatter": [_P, _CP, _I] + [_P] * 11,
+    "neuma_mpm_bwd_node_gather": [_P, _CP, _I] + [_P] * 24,
+    "neuma_mpm_planes_add": [_P, _P, _P, C.c_size_t, _P],
     "neuma_mpm_cell_order": [_P, _CP, _I, _P, _P, _P],
     "neuma_gather_rows": [_P, _I, _I, _P, _P, _P, _P],
     "neuma_invert_perm": [_P, _I, _P, _P, _P],

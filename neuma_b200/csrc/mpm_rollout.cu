@@ -464,6 +464,17 @@ invert_perm_kernel(int n, const int32_t* __restrict__ perm, int32_t* __restrict_
   if (i < n) inv[perm[i]] = i;
 }
 
+// dst += src over n float4 nodes: the receiving side of the slab-halo exchange
+__global__ void __launch_bounds__(256)
+planes_add_kernel(float4* __restrict__ dst, const float4* __restrict__ src, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float4 a = dst[i];
+    const float4 b = src[i];
+    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    dst[i] = a;
+  }
+}
+
 inline int node_pass_blocks(neuma_ctx* ctx) { return ctx->num_sms * 8; }
 
 int check_slab(neuma_ctx* ctx, const neuma_mpm_const* c) {
@@ -552,21 +563,32 @@ int neuma_mpm_rollout_fwd(neuma_ctx* ctx, const neuma_mpm_const* c, int n, const
                             stream);
 }
 
-int neuma_mpm_rollout_bwd(neuma_ctx* ctx, const neuma_mpm_const* c, int n, const float* x,
-                          const float* v, const float* C, const float* F, const float* stress,
-                          const float* vol, const float* rho, const float* clip_bound,
-                          const int32_t* enabled, const float* v2, const float* C2,
-                          const float* gx2, const float* gv2, const float* gC2, const float* gF2,
-                          const float* grid_v, float* adj, const int32_t* box, float* gx, float* gv,
-                          float* gC, float* gF, float* gstress, void* stream) {
+int neuma_mpm_bwd_scatter(neuma_ctx* ctx, const neuma_mpm_const* c, int n, const float* x,
+                          const float* F, const float* clip_bound, const int32_t* enabled,
+                          const float* v2, const float* gx2, const float* gv2, const float* gC2,
+                          const float* gF2, float* adj, void* stream) {
+  if (int r = check_slab(ctx, c)) return r;
+  if (n <= 0) return 0;
+  if (!v2 || !gx2 || !gv2 || !gC2 || !gF2 || !adj)
+    return neuma_fail_msg(ctx, "neuma_mpm_bwd_scatter: NULL argument");
+  bwd_scatter_adj_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+      *c, n, x, F, clip_bound, enabled, v2, gx2, gv2, gC2, gF2, (float4*)adj);
+  NEUMA_LAUNCH_CHECK(ctx, "bwd_scatter_adj_kernel");
+  return 0;
+}
+
+int neuma_mpm_bwd_node_gather(neuma_ctx* ctx, const neuma_mpm_const* c, int n, const float* x,
+                              const float* v, const float* C, const float* F, const float* stress,
+                              const float* vol, const float* rho, const float* clip_bound,
+                              const int32_t* enabled, const float* v2, const float* C2,
+                              const float* gx2, const float* gv2, const float* gC2, const float* gF2,
+                              const float* grid_v, float* adj, const int32_t* box, float* gx,
+                              float* gv, float* gC, float* gF, float* gstress, void* stream) {
   if (int r = check_slab(ctx, c)) return r;
   if (n <= 0) return 0;
   if (!v2 || !gx2 || !gv2 || !gC2 || !gF2 || !grid_v || !adj || !box)
-    return neuma_fail_msg(ctx, "neuma_mpm_rollout_bwd: NULL argument");
+    return neuma_fail_msg(ctx, "neuma_mpm_bwd_node_gather: NULL argument");
   cudaStream_t st = (cudaStream_t)stream;
-  bwd_scatter_adj_kernel<<<(n + 255) / 256, 256, 0, st>>>(*c, n, x, F, clip_bound, enabled, v2, gx2,
-                                                          gv2, gC2, gF2, (float4*)adj);
-  NEUMA_LAUNCH_CHECK(ctx, "bwd_scatter_adj_kernel");
   bwd_node_kernel<<<node_pass_blocks(ctx), 256, 0, st>>>(*c, box, (const float4*)grid_v, (float4*)adj);
   NEUMA_LAUNCH_CHECK(ctx, "bwd_node_kernel");
   if (C2)
@@ -578,6 +600,31 @@ int neuma_mpm_rollout_bwd(neuma_ctx* ctx, const neuma_mpm_const* c, int n, const
         *c, n, x, v, C, F, stress, vol, rho, clip_bound, enabled, v2, C2, gx2, gv2, gC2, gF2,
         (const float4*)grid_v, (const float4*)adj, gx, gv, gC, gF, gstress);
   NEUMA_LAUNCH_CHECK(ctx, "bwd_gather_v_kernel");
+  return 0;
+}
+
+int neuma_mpm_rollout_bwd(neuma_ctx* ctx, const neuma_mpm_const* c, int n, const float* x,
+                          const float* v, const float* C, const float* F, const float* stress,
+                          const float* vol, const float* rho, const float* clip_bound,
+                          const int32_t* enabled, const float* v2, const float* C2,
+                          const float* gx2, const float* gv2, const float* gC2, const float* gF2,
+                          const float* grid_v, float* adj, const int32_t* box, float* gx, float* gv,
+                          float* gC, float* gF, float* gstress, void* stream) {
+  if (int r = neuma_mpm_bwd_scatter(ctx, c, n, x, F, clip_bound, enabled, v2, gx2, gv2, gC2, gF2, adj,
+                                    stream))
+    return r;
+  return neuma_mpm_bwd_node_gather(ctx, c, n, x, v, C, F, stress, vol, rho, clip_bound, enabled, v2, C2,
+                                   gx2, gv2, gC2, gF2, grid_v, adj, box, gx, gv, gC, gF, gstress,
+                                   stream);
+}
+
+int neuma_mpm_planes_add(neuma_ctx* ctx, float* dst, const float* src, size_t nodes, void* stream) {
+  if (!ctx) return 2;
+  if (nodes == 0) return 0;
+  size_t b = (nodes + 255) / 256;
+  if (b > (size_t)ctx->num_sms * 8) b = (size_t)ctx->num_sms * 8;
+  planes_add_kernel<<<(int)b, 256, 0, (cudaStream_t)stream>>>((float4*)dst, (const float4*)src, nodes);
+  NEUMA_LAUNCH_CHECK(ctx, "planes_add_kernel");
   return 0;
 }
 

@@ -392,3 +392,23 @@ def constitutive_reduce_partials(gWpart, gW0, gW1, gW2, hidden: int = 64) -> Non
     """gW* += sum of the slots; the slots are zeroed."""
     _ctx(gWpart).call("neuma_constitutive_reduce_partials", hidden, ptr(gWpart), ptr(gW0), ptr(gW1), ptr(gW2),
                       _stream(gWpart))
+
+
+def mpm_planes_add(dst: torch.Tensor, src: torch.Tensor) -> None:
+    """dst += src for packed float4 grid planes (slab-halo receive side)."""
+    if dst.numel() != src.numel() or dst.numel() % 4:
+        raise NeumaError("mpm_planes_add: shapes differ / not float4 nodes")
+    _ctx(dst).call("neuma_mpm_planes_add", ptr(dst), ptr(src), C.c_size_t(dst.numel() // 4), _stream(dst))
+
+
+def mpm_bwd_scatter(c: MPMConstC, x, F, clip_bound, enabled, v2, gx2, gv2, gC2, gF2, adj) -> None:
+    _ctx(x).call("neuma_mpm_bwd_scatter", C.byref(c), x.shape[0], ptr(x), ptr(F), ptr(clip_bound), ptr(enabled),
+                 ptr(v2), ptr(gx2), ptr(gv2), ptr(gC2), ptr(gF2), ptr(adj), _stream(x))
+
+
+def mpm_bwd_node_gather(c: MPMConstC, x, v, Cm, F, stress, vol, rho, clip_bound, enabled, v2, C2, gx2, gv2, gC2,
+                        gF2, grid_v, adj, box, gx, gv, gC, gF, gstress) -> None:
+    _ctx(x).call("neuma_mpm_bwd_node_gather", C.byref(c), x.shape[0], ptr(x), ptr(v), ptr(Cm), ptr(F),
+                 ptr(stress), ptr(vol), ptr(rho), ptr(clip_bound), ptr(enabled), ptr(v2), ptr(C2), ptr(gx2),
+                 ptr(gv2), ptr(gC2), ptr(gF2), ptr(grid_v), ptr(adj), ptr(box), ptr(gx), ptr(gv), ptr(gC), ptr(gF),
+                 ptr(gstress), _stream(x))

@@ -1,0 +1,131 @@
+"""Z-slab multi-GPU rollout (neuma_b200/slab.py) against the single-GPU fused engine: the
+same S-substep forward + backward, particle state / gradients compared in GLOBAL particle
+order.  world = 1 always runs; world = 2 / 4 need that many GPUs (gpurun --gpus N)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from util import make_cloud, rel_err
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _weights():
+    z = np.load(os.path.join(ROOT, "tests", "golden", "material_jelly.npz"))
+    W = {t: [torch.from_numpy(z[f"param_{t}.{l}.fc.weight"]).float() for l in ("layers.0", "layers.1", "final_layer")]
+         for t in ("elastic", "plastic")}
+    return W, float(z["alpha"])
+
+
+def _problem(n, G):
+    d = make_cloud(n, G, seed=21, lo=0.25, hi=0.75, perturb_F=0.02, stress_scale=0.0)
+    d["C"] *= 0.1
+    gen = torch.Generator().manual_seed(5)
+    g = [torch.randn(n, 3, generator=gen), torch.randn(n, 3, generator=gen),
+         torch.randn(n, 3, 3, generator=gen), torch.randn(n, 3, 3, generator=gen)]
+    return d, g
+
+
+def _reference(dev, n, G, S, dt):
+    from neuma_b200 import ops
+    from neuma_b200.pipeline import FusedFrame
+    W, alpha = _weights()
+    d, g = _problem(n, G)
+    dd = {k: t.to(dev) for k, t in d.items()}
+    cc = ops.mpm_const(G, dt, 1, (0.0, -9.8, 0.0), 6e-7, "noslip")
+    eng = FusedFrame(n, cc, (dd["vol"], dd["rho"], dd["clip"], dd["enabled"]), [w.to(dev) for w in W["elastic"]],
+                     [w.to(dev) for w in W["plastic"]], alpha, S, dev, use_graphs=False)
+    eng.load_state(dd["x"], dd["v"], dd["C"], dd["F"])
+    out = [t.clone() for t in eng.sim_forward()]
+    eng.zero_weight_grads()
+    g0 = [t.clone() for t in eng.sim_backward(*[t.to(dev) for t in g])]
+    return out, g0, [t.clone() for t in eng.gWe + eng.gWp]
+
+
+def _slab_run(rank, world, port, n, G, S, dt, q):
+    from neuma_b200.slab import SlabRollout
+    if world > 1:
+        os.environ["MASTER_ADDR"] = "127.0.0.1"
+        os.environ["MASTER_PORT"] = str(port)
+        torch.cuda.set_device(rank)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    dev = torch.device("cuda", rank)
+    try:
+        W, alpha = _weights()
+        d, g = _problem(n, G)
+        sim = SlabRollout(G, dt, W["elastic"], W["plastic"], alpha, S, dev)
+        sim.distribute(d["x"], d["v"], d["C"], d["F"], d["vol"], d["rho"], d["clip"], d["enabled"])
+        out = sim.forward()
+        assert sim.drift_ok()
+        ids = sim.ids
+        g0 = sim.backward(*[t.to(dev)[ids] for t in g])
+        res = [sim.gather_global(t, n).cpu() for t in list(out) + list(g0)]
+        gW = [t.cpu() for t in sim.gWe + sim.gWp]
+        counts = sim.n
+        # frame boundary: particles change owner, slabs re-balance; a second frame still runs
+        sim.repartition(n)
+        sim.forward()
+        torch.cuda.synchronize(dev)
+        if q is not None:
+            if rank == 0:
+                q.put((res, gW, counts))
+            else:
+                q.put(counts)
+        return res, gW, counts
+    finally:
+        if world > 1:
+            dist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _check(res, gW, ref):
+    out_ref, g0_ref, gW_ref = ref
+    for a, b, name in zip(res[:4], out_ref, "xvCF"):
+        assert rel_err(a, b) < 1e-4, name                       # north_star: x/v/F within 1e-4 rel
+    for a, b, name in zip(res[4:], g0_ref, ["gx", "gv", "gC", "gF"]):
+        assert rel_err(a, b) < 5e-4, name
+    for a, b in zip(gW, gW_ref):
+        assert rel_err(a, b) < 1e-3
+
+
+def test_slab_world1_matches_fused_frame(cuda_dev):
+    n, G, S, dt = 20000, 64, 3, 2.5e-4
+    ref = _reference(cuda_dev, n, G, S, dt)
+    res, gW, counts = _slab_run(0, 1, 0, n, G, S, dt, None)
+    assert counts == n
+    _check(res, gW, ref)
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_slab_multi_gpu_matches_single(cuda_dev, world):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    n, G, S, dt = 40000, 64, 3, 2.5e-4
+    ref = _reference(cuda_dev, n, G, S, dt)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_slab_run, args=(r, world, port, n, G, S, dt, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    main = [g_ for g_ in got if isinstance(g_, tuple)][0]
+    total = main[2] + sum(g_ for g_ in got if not isinstance(g_, tuple))
+    assert total == n
+    _check(main[0], main[1], ref)
