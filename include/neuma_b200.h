@@ -251,9 +251,10 @@ int neuma_constitutive_bwd_staged(neuma_ctx* ctx, int kind, int n, int hidden, c
  * neuma_constitutive_reduce_partials adds the slot sum into gW0/gW1/gW2 and zeroes the
  * slots.  A rollout calls the first 2 x S times per frame and the second once. */
 int neuma_constitutive_partials_floats(neuma_ctx* ctx);
+/* accumulate_gF != 0: gF += dL/dF instead of overwriting it */
 int neuma_constitutive_bwd_partials(neuma_ctx* ctx, int kind, int n, int hidden, const float* F,
                                     const void* staged, float alpha, const float* gout, float* gF,
-                                    float* gWpart, void* stream);
+                                    int accumulate_gF, float* gWpart, void* stream);
 int neuma_constitutive_reduce_partials(neuma_ctx* ctx, int hidden, float* gWpart, float* gW0,
                                        float* gW1, float* gW2, void* stream);
 

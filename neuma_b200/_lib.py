@@ -78,7 +78,7 @@ SIGNATURES = {
     "neuma_constitutive_fwd_staged": [_P, _I, _I, _I, _P, _P, _F, _P, _P],
     "neuma_constitutive_bwd_staged": [_P, _I, _I, _I, _P, _P, _F, _P, _P, _P, _P, _P, _P],
     "neuma_constitutive_partials_floats": [_P],
-    "neuma_constitutive_bwd_partials": [_P, _I, _I, _I, _P, _P, _F, _P, _P, _P, _P],
+    "neuma_constitutive_bwd_partials": [_P, _I, _I, _I, _P, _P, _F, _P, _P, _I, _P, _P],
     "neuma_constitutive_reduce_partials": [_P, _I, _P, _P, _P, _P, _P],
     "neuma_bind_spmm": [_P, _I, _I, _P, _P, _P, _I, _P, _P, _I, _P],
     "neuma_deform_cov": [_P, _I, _P, _P, _P, _P],

@@ -5,17 +5,20 @@
 //   InvariantFullMetaPlasticity.forward   modules/nclaw/material/meta.py:468-489
 // and the Warp batch_svd / SVDFunction of modules/nclaw/warp/svd.py:9-96.
 //
-// Structure (warp-specialised, one persistent CTA per SM):
-//   * NPIPE independent tile pipelines per CTA.  A pipeline = 128 compute threads = the 128
-//     particles of a tile = the 128 TMEM lanes; one thread owns one particle row for the
-//     SVD / invariants, the GELU epilogues between the GEMMs, and the polar recombination.
-//   * ONE extra warp issues every tcgen05.mma of the CTA.  Pipelines hand it work through
-//     mbarriers (full[p]: "operands of my next GEMM are in shared memory"; done[p] /
-//     wdone[p]: tcgen05.commit of the forward-or-data-gradient / weight-gradient GEMMs), it
-//     polls the pipelines and serves whichever is ready, so one pipeline's CUDA-core phase
-//     overlaps the others' tensor-core phase.  A single issuing thread also makes the
-//     weight-gradient accumulators (shared by the pipelines, resident in TMEM for the whole
-//     kernel) well ordered.
+// Structure (one persistent CTA per SM):
+//   * NPIPE independent tile pipelines per CTA.  A pipeline = 128 threads = the 128 particles
+//     of a tile = the 128 TMEM lanes; one thread owns one particle row for the SVD /
+//     invariants, the GELU epilogues between the GEMMs, and the polar recombination.  A
+//     pipeline synchronises on its own named barrier, its first warp issues the tcgen05.mma
+//     of the pipeline's next GEMM (forward and data-gradient GEMMs: nothing else of that
+//     pipeline can run until they finish anyway) and everybody waits on the commit mbarrier.
+//     While one pipeline waits for the tensor core the others run their CUDA-core phases.
+//   * Backward only: ONE extra warp issues every weight-gradient GEMM of the CTA.  The
+//     accumulators are shared by the pipelines and stay in TMEM for the whole kernel, so a
+//     single issuing thread keeps them well ordered; the pipelines hand it work through
+//     mbarriers (wfull[p]: "both operand tiles are in shared memory", wdone[p]:
+//     tcgen05.commit, after which the pipeline may overwrite the tiles) and never wait for
+//     the weight gradients themselves.
 //   * The three Linear layers -- and, in the backward, their data-gradient and
 //     weight-gradient GEMMs -- are tcgen05.mma kind::f16 on bf16 operands in shared memory
 //     with fp32 accumulators in TMEM.  Every fp32 value is split into NS bf16 terms
@@ -48,7 +51,7 @@
 // Developer instrumentation (tools/phase_timing.py builds a copy with -DNEUMA_PHASE_TIMING):
 // thread 0 of CTA 0 accumulates clock64() deltas per phase of its pipeline.
 #ifdef NEUMA_PHASE_TIMING
-__device__ long long g_phase_cycles[32];
+__device__ long long g_phase_cycles[64];
 #define PHASE_T0() long long pt__ = clock64()
 #define PHASE(i)                                             \
   do {                                                       \
@@ -69,8 +72,14 @@ constexpr int H = 64;      // hidden width (layer_widths: [64, 64] in every ship
 constexpr int NF = 13;     // 3 + 9 + 1 invariants
 constexpr int TP = 128;    // particles per tile = TMEM lanes = rows of every GEMM
 constexpr int KF = 16;     // invariants (13) and MLP head (9) padded to one bf16 K step
-constexpr int NS_FWD = 3, NS_BWD = 2;      // bf16 splits per fp32 value
-constexpr int NPIPE_FWD = 3, NPIPE_BWD = 2;  // tile pipelines per CTA
+#ifndef NEUMA_NS_FWD
+#define NEUMA_NS_FWD 3
+#endif
+#ifndef NEUMA_NPIPE_FWD
+#define NEUMA_NPIPE_FWD 3
+#endif
+constexpr int NS_FWD = NEUMA_NS_FWD, NS_BWD = 2;          // bf16 splits per fp32 value
+constexpr int NPIPE_FWD = NEUMA_NPIPE_FWD, NPIPE_BWD = 2;  // tile pipelines per CTA
 
 struct Kinematics {
   Mat3 F, U, V, R;
@@ -192,24 +201,24 @@ stage_weights_kernel(const float* __restrict__ W0, const float* __restrict__ W1,
   if (e < N0) {
     r = e / KF; k = e % KF; R = H;
     x = (k < NF) ? W0[r * NF + k] : 0.f;
-    off3 = WImg<3>::OFF_W0; off2 = WImg<2>::OFF_W0; split = W0_SPLIT;
+    off3 = WImg<NS_FWD>::OFF_W0; off2 = WImg<NS_BWD>::OFF_W0; split = W0_SPLIT;
   } else if (e < N0 + N1) {
     const int f = e - N0;
     r = f / H; k = f % H; R = H;
     x = W1[r * H + k];
-    off3 = WImg<3>::OFF_W1; off2 = WImg<2>::OFF_W1; split = W1_SPLIT;
+    off3 = WImg<NS_FWD>::OFF_W1; off2 = WImg<NS_BWD>::OFF_W1; split = W1_SPLIT;
   } else {
     const int f = e - N0 - N1;
     r = f / H; k = f % H; R = KF;
     x = (r < 9) ? W2[r * H + k] : 0.f;
-    off3 = WImg<3>::OFF_W2; off2 = WImg<2>::OFF_W2; split = W2_SPLIT;
+    off3 = WImg<NS_FWD>::OFF_W2; off2 = WImg<NS_BWD>::OFF_W2; split = W2_SPLIT;
   }
   const size_t o = (((size_t)(k >> 3) * R + r) * 8 + (k & 7)) * 2;
 #pragma unroll
   for (int t = 0; t < 3; ++t) {
     const uint16_t h = (uint16_t)(pack_bf16x2(x, 0.f) & 0xFFFFu);
-    *reinterpret_cast<uint16_t*>(staged + STAGED_OFF_FWD + off3 + t * split + o) = h;
-    if (t < 2) *reinterpret_cast<uint16_t*>(staged + STAGED_OFF_BWD + off2 + t * split + o) = h;
+    if (t < NS_FWD) *reinterpret_cast<uint16_t*>(staged + STAGED_OFF_FWD + off3 + t * split + o) = h;
+    if (t < NS_BWD) *reinterpret_cast<uint16_t*>(staged + STAGED_OFF_BWD + off2 + t * split + o) = h;
     x -= __uint_as_float((uint32_t)h << 16);
   }
 }
@@ -290,13 +299,21 @@ __device__ __forceinline__ bool mbar_test(uint32_t mbar, uint32_t parity) {
   return done != 0;
 }
 struct PipeSync {
-  uint32_t full, done, wdone;  // shared-memory addresses of the pipeline's mbarriers
+  uint32_t done, wfull, wdone;  // shared-memory addresses of the pipeline's mbarriers
+  uint32_t bar_id;              // named barrier of the pipeline (1 + p), 128 threads
   uint32_t ph_done, ph_wdone;
-  // my smem operand writes / TMEM reads of this phase are finished: hand over to the MMA warp
+  // my smem operand writes / TMEM accesses of this phase are finished; returns once every
+  // thread of the pipeline got here
   __device__ __forceinline__ void publish() const {
     umma::fence_async_smem();
     umma::fence_before_sync();
-    mbar_arrive(full);
+    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(TP) : "memory");
+  }
+  // non-blocking hand-over to a dedicated issuing warp polling wfull
+  __device__ __forceinline__ void publish_async() const {
+    umma::fence_async_smem();
+    umma::fence_before_sync();
+    mbar_arrive(wfull);
   }
   __device__ __forceinline__ void wait_done() {
     umma::mbar_wait(done, ph_done);
@@ -363,19 +380,19 @@ __device__ __forceinline__ Mat3 head_to_sym(const float (&o)[16]) {
 // ---- block prologue: barriers, TMEM, weight image
 struct Bars {
   uint64_t w;  // weight image landed (cp.async.bulk complete_tx)
-  uint64_t full[3], done[3], wdone[3];
+  uint64_t done[4], wfull[4], wdone[4];
 };
 template <int NPIPE>
 __device__ __forceinline__ uint32_t block_setup(Bars* bars, uint32_t* tmem_slot, uint8_t* sm_w,
                                                 const uint8_t* __restrict__ staged, uint32_t w_bytes,
-                                                uint32_t tmem_cols, int mma_warp) {
+                                                uint32_t tmem_cols) {
   const int warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
     umma::mbar_init(umma::smem_u32(&bars->w), 1);
 #pragma unroll
     for (int p = 0; p < NPIPE; ++p) {
-      umma::mbar_init(umma::smem_u32(&bars->full[p]), TP);
       umma::mbar_init(umma::smem_u32(&bars->done[p]), 1);
+      umma::mbar_init(umma::smem_u32(&bars->wfull[p]), TP);
       umma::mbar_init(umma::smem_u32(&bars->wdone[p]), 1);
     }
     umma::fence_mbar_init();
@@ -384,7 +401,7 @@ __device__ __forceinline__ uint32_t block_setup(Bars* bars, uint32_t* tmem_slot,
   umma::fence_before_sync();
   __syncthreads();
   umma::fence_after_sync();
-  if (warp == mma_warp && (threadIdx.x & 31) == 0) {
+  if (threadIdx.x == 0) {
     const uint32_t bar = umma::smem_u32(&bars->w);
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(w_bytes) : "memory");
     constexpr uint32_t CH = 12288;
@@ -411,15 +428,15 @@ constitutive_fwd_kernel(int kind, int n, const float* __restrict__ F, const uint
   __shared__ Bars bars;
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5;
-  const uint32_t tmem = block_setup<NPIPE>(&bars, &tmem_slot, sm, staged + STAGED_OFF_FWD, W::BYTES,
-                                           FWD_TMEM_COLS, NPIPE * 4);
+  const uint32_t tmem = block_setup<NPIPE>(&bars, &tmem_slot, sm, staged + STAGED_OFF_FWD, W::BYTES, FWD_TMEM_COLS);
   const uint32_t smem = umma::smem_u32(sm);
   const int tiles = (n + TP - 1) / TP;
   const int chains = gridDim.x * NPIPE;
   constexpr uint32_t ID64 = umma::idesc_bf16(TP, H, 0, 0), ID16 = umma::idesc_bf16(TP, KF, 0, 0);
 
   if (warp == NPIPE * 4) {
-    // ---------------- MMA warp
+    // ---------------- MMA warp (forward kernel: one dedicated issuing warp serves the pipelines'
+    // wfull[p] requests in arrival order; measured ~8% faster here than per-pipeline issue)
     const Desc w0 = desc_kmajor(smem + W::OFF_W0, W0_SPLIT, H), w1 = desc_kmajor(smem + W::OFF_W1, W1_SPLIT, H),
                w2 = desc_kmajor(smem + W::OFF_W2, W2_SPLIT, KF);
     int njobs[NPIPE], job[NPIPE];
@@ -438,7 +455,7 @@ constitutive_fwd_kernel(int kind, int n, const float* __restrict__ F, const uint
 #pragma unroll
       for (int p = 0; p < NPIPE; ++p) {
         if (job[p] >= njobs[p]) continue;
-        uint32_t ok = mbar_test(umma::smem_u32(&bars.full[p]), ph[p]) ? 1u : 0u;
+        uint32_t ok = mbar_test(umma::smem_u32(&bars.wfull[p]), ph[p]) ? 1u : 0u;
         ok = __shfl_sync(0xffffffffu, ok, 0);
         if (!ok) continue;
         ph[p] ^= 1u;
@@ -461,7 +478,7 @@ constitutive_fwd_kernel(int kind, int n, const float* __restrict__ F, const uint
     const int p = warp >> 2, r = tid & (TP - 1);
     uint8_t* const pm = sm + W::BYTES + p * P::BYTES;
     const uint32_t tacc = tmem + ((uint32_t)((warp & 3) * 32) << 16) + p * FWD_PIPE_COLS;
-    PipeSync ps{umma::smem_u32(&bars.full[p]), umma::smem_u32(&bars.done[p]), umma::smem_u32(&bars.wdone[p]), 0u, 0u};
+    PipeSync ps{umma::smem_u32(&bars.done[p]), umma::smem_u32(&bars.wfull[p]), 0u, (uint32_t)(1 + p), 0u, 0u};
     for (int tile = p * gridDim.x + blockIdx.x; tile < tiles; tile += chains) {
       const int pi = tile * TP + r;
       Kinematics k;
@@ -473,14 +490,14 @@ constitutive_fwd_kernel(int kind, int n, const float* __restrict__ F, const uint
         store_chunk<NS>(pm + P::OFF_FEAT, SMALL_SPLIT, 0, r, f);
         store_chunk<NS>(pm + P::OFF_FEAT, SMALL_SPLIT, 1, r, f + 8);
       }
-      ps.publish();                                            // -> h1 = feat W0^T
+      ps.publish_async();                                            // -> h1 = feat W0^T
       prefetch_row(F, pi + chains * TP, n);
       ps.wait_done();
       gelu_phase<NS, false>(tacc, pm + P::OFF_BIGA, r);
-      ps.publish();                                            // -> h2 = a1 W1^T
+      ps.publish_async();                                            // -> h2 = a1 W1^T
       ps.wait_done();
       gelu_phase<NS, false>(tacc, pm + P::OFF_BIGA, r);
-      ps.publish();                                            // -> o = a2 W2^T
+      ps.publish_async();                                            // -> o = a2 W2^T
       ps.wait_done();
       float o[16];
       umma::tmem_ld16(tacc, o);
@@ -510,7 +527,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
 constitutive_bwd_kernel(int kind, int n, const float* __restrict__ F, const uint8_t* __restrict__ staged,
                         float alpha, const float* __restrict__ gout, float* __restrict__ gF,
                         float* __restrict__ gW0, float* __restrict__ gW1, float* __restrict__ gW2,
-                        float* __restrict__ gWpart) {
+                        float* __restrict__ gWpart, int accumulate_gF) {
   constexpr int NS = NS_BWD, NPIPE = NPIPE_BWD;
   using W = WImg<NS>;
   using P = PipeBwd<NS>;
@@ -529,8 +546,7 @@ constitutive_bwd_kernel(int kind, int n, const float* __restrict__ F, const uint
 #else
 #define KPHASE(i)
 #endif
-  const uint32_t tmem = block_setup<NPIPE>(&bars, &tmem_slot, sm, staged + STAGED_OFF_BWD, W::BYTES,
-                                           BWD_TMEM_COLS, NPIPE * 4);
+  const uint32_t tmem = block_setup<NPIPE>(&bars, &tmem_slot, sm, staged + STAGED_OFF_BWD, W::BYTES, BWD_TMEM_COLS);
   KPHASE(16);
   const uint32_t smem = umma::smem_u32(sm);
   const int tiles = (n + TP - 1) / TP;
@@ -540,92 +556,67 @@ constitutive_bwd_kernel(int kind, int n, const float* __restrict__ F, const uint
   constexpr uint32_t IDW64 = umma::idesc_bf16(64, H, 1, 1), IDW16 = umma::idesc_bf16(64, KF, 1, 1);
 
   if (warp == NPIPE * 4) {
-    // ---------------- MMA warp
+    // ---------------- weight-gradient warp: serves wfull[p] in arrival order
+    if (WGRAD) {
+      int njobs[NPIPE], job[NPIPE];
+      uint32_t ph[NPIPE];
+      int remaining = 0;
+#pragma unroll
+      for (int p = 0; p < NPIPE; ++p) {
+        const int c = p * gridDim.x + blockIdx.x;
+        njobs[p] = (c < tiles) ? 3 * ((tiles - 1 - c) / chains + 1) : 0;
+        job[p] = 0;
+        ph[p] = 0;
+        remaining += njobs[p];
+      }
+      bool acc2 = false, acc1 = false, acc0 = false;  // accumulators initialised?
+      while (remaining > 0) {
+#pragma unroll
+        for (int p = 0; p < NPIPE; ++p) {
+          if (job[p] >= njobs[p]) continue;
+          uint32_t ok = mbar_test(umma::smem_u32(&bars.wfull[p]), ph[p]) ? 1u : 0u;
+          ok = __shfl_sync(0xffffffffu, ok, 0);
+          if (!ok) continue;
+          ph[p] ^= 1u;
+          umma::fence_after_sync();
+          const uint32_t pbase = smem + W::BYTES + p * P::BYTES;
+          const Desc featT = desc_mnmajor(pbase + P::OFF_FEAT, SMALL_SPLIT, TP), goT = desc_mnmajor(pbase + P::OFF_GO, SMALL_SPLIT, TP),
+                     bigaT = desc_mnmajor(pbase + P::OFF_BIGA, BIG_SPLIT, TP), bigbT = desc_mnmajor(pbase + P::OFF_BIGB, BIG_SPLIT, TP);
+          const int j = job[p] % 3;
+          if (j == 0) {         // dW2^T += a2^T go
+            gemm_split<NS, 8>(tmem + COL_GW2T, bigbT, goT, IDW16, acc2);
+            acc2 = true;
+          } else if (j == 1) {  // dW1 += g2^T a1
+            gemm_split<NS, 8>(tmem + COL_GW1, bigbT, bigaT, IDW64, acc1);
+            acc1 = true;
+          } else {              // dW0 += g1^T feat
+            gemm_split<NS, 8>(tmem + COL_GW0, bigaT, featT, IDW16, acc0);
+            acc0 = true;
+          }
+          umma::commit(umma::smem_u32(&bars.wdone[p]));
+          ++job[p];
+          --remaining;
+        }
+      }
+    }
+  } else {
+    // ---------------- pipeline p, particle row r; the pipeline's first warp issues its GEMMs
+    const int p = warp >> 2, r = tid & (TP - 1);
+    const bool issuer = (warp & 3) == (p & 3);  // issuers of different pipelines sit on different SM sub-partitions
+    uint8_t* const pm = sm + W::BYTES + p * P::BYTES;
+    const uint32_t pbase = smem + W::BYTES + p * P::BYTES;
+    const uint32_t tp = tmem + p * BWD_PIPE_COLS;
+    const uint32_t tl = tp + ((uint32_t)((warp & 3) * 32) << 16);
     const Desc w0 = desc_kmajor(smem + W::OFF_W0, W0_SPLIT, H), w1 = desc_kmajor(smem + W::OFF_W1, W1_SPLIT, H),
                w2 = desc_kmajor(smem + W::OFF_W2, W2_SPLIT, KF);
     // the same images read transposed: B operands of the data-gradient GEMMs
     const Desc w0t = desc_mnmajor(smem + W::OFF_W0, W0_SPLIT, H), w1t = desc_mnmajor(smem + W::OFF_W1, W1_SPLIT, H),
                w2t = desc_mnmajor(smem + W::OFF_W2, W2_SPLIT, KF);
-    int njobs[NPIPE], job[NPIPE];
-    uint32_t ph[NPIPE];
-    int remaining = 0;
-#pragma unroll
-    for (int p = 0; p < NPIPE; ++p) {
-      const int c = p * gridDim.x + blockIdx.x;
-      njobs[p] = (c < tiles) ? 6 * ((tiles - 1 - c) / chains + 1) : 0;
-      job[p] = 0;
-      ph[p] = 0;
-      remaining += njobs[p];
-    }
-    bool acc2 = false, acc1 = false, acc0 = false;  // weight-gradient accumulators initialised?
-    umma::mbar_wait(umma::smem_u32(&bars.w), 0);
-    while (remaining > 0) {
-#pragma unroll
-      for (int p = 0; p < NPIPE; ++p) {
-        if (job[p] >= njobs[p]) continue;
-        uint32_t ok = mbar_test(umma::smem_u32(&bars.full[p]), ph[p]) ? 1u : 0u;
-        ok = __shfl_sync(0xffffffffu, ok, 0);
-        if (!ok) continue;
-        ph[p] ^= 1u;
-        umma::fence_after_sync();
-        const uint32_t pbase = smem + W::BYTES + p * P::BYTES;
-        const Desc feat = desc_kmajor(pbase + P::OFF_FEAT, SMALL_SPLIT, TP), go = desc_kmajor(pbase + P::OFF_GO, SMALL_SPLIT, TP),
-                   biga = desc_kmajor(pbase + P::OFF_BIGA, BIG_SPLIT, TP), bigb = desc_kmajor(pbase + P::OFF_BIGB, BIG_SPLIT, TP);
-        const Desc featT = desc_mnmajor(pbase + P::OFF_FEAT, SMALL_SPLIT, TP), goT = desc_mnmajor(pbase + P::OFF_GO, SMALL_SPLIT, TP),
-                   bigaT = desc_mnmajor(pbase + P::OFF_BIGA, BIG_SPLIT, TP), bigbT = desc_mnmajor(pbase + P::OFF_BIGB, BIG_SPLIT, TP);
-        const uint32_t tp = tmem + p * BWD_PIPE_COLS;
-        const uint32_t dbar = umma::smem_u32(&bars.done[p]), wbar = umma::smem_u32(&bars.wdone[p]);
-        switch (job[p] % 6) {
-          case 0:  // h1 = feat W0^T
-            gemm_split<NS, 1>(tp + COL_H1, feat, w0, ID64, false);
-            umma::commit(dbar);
-            break;
-          case 1:  // h2 = a1 W1^T
-            gemm_split<NS, 4>(tp + COL_H2, biga, w1, ID64, false);
-            umma::commit(dbar);
-            break;
-          case 2:  // o = a2 W2^T
-            gemm_split<NS, 4>(tp + COL_S, bigb, w2, ID16, false);
-            umma::commit(dbar);
-            break;
-          case 3:  // dL/da2 = go W2 ; dW2^T += a2^T go
-            gemm_split<NS, 1>(tp + COL_S, go, w2t, ID64_BT, false);
-            umma::commit(dbar);
-            if (WGRAD) {
-              gemm_split<NS, 8>(tmem + COL_GW2T, bigbT, goT, IDW16, acc2);
-              acc2 = true;
-              umma::commit(wbar);
-            }
-            break;
-          case 4:  // dL/da1 = g2 W1 ; dW1 += g2^T a1
-            gemm_split<NS, 4>(tp + COL_S, bigb, w1t, ID64_BT, false);
-            umma::commit(dbar);
-            if (WGRAD) {
-              gemm_split<NS, 8>(tmem + COL_GW1, bigbT, bigaT, IDW64, acc1);
-              acc1 = true;
-              umma::commit(wbar);
-            }
-            break;
-          default:  // dL/dfeat = g1 W0 ; dW0 += g1^T feat
-            gemm_split<NS, 4>(tp + COL_S, biga, w0t, ID16_BT, false);
-            umma::commit(dbar);
-            if (WGRAD) {
-              gemm_split<NS, 8>(tmem + COL_GW0, bigaT, featT, IDW16, acc0);
-              acc0 = true;
-              umma::commit(wbar);
-            }
-            break;
-        }
-        ++job[p];
-        --remaining;
-      }
-    }
-  } else {
-    // ---------------- compute threads: pipeline p, particle row r
-    const int p = warp >> 2, r = tid & (TP - 1);
-    uint8_t* const pm = sm + W::BYTES + p * P::BYTES;
-    const uint32_t tl = tmem + ((uint32_t)((warp & 3) * 32) << 16) + p * BWD_PIPE_COLS;
-    PipeSync ps{umma::smem_u32(&bars.full[p]), umma::smem_u32(&bars.done[p]), umma::smem_u32(&bars.wdone[p]), 0u, 0u};
+    const Desc feat = desc_kmajor(pbase + P::OFF_FEAT, SMALL_SPLIT, TP), go = desc_kmajor(pbase + P::OFF_GO, SMALL_SPLIT, TP),
+               biga = desc_kmajor(pbase + P::OFF_BIGA, BIG_SPLIT, TP), bigb = desc_kmajor(pbase + P::OFF_BIGB, BIG_SPLIT, TP);
+    const uint32_t dbar = umma::smem_u32(&bars.done[p]), wfull = umma::smem_u32(&bars.wfull[p]);
+    PipeSync ps{dbar, wfull, umma::smem_u32(&bars.wdone[p]), (uint32_t)(1 + p), 0u, 0u};
+    if (issuer) umma::mbar_wait(umma::smem_u32(&bars.w), 0);  // weight image has landed
     bool first = true;
     PHASE_T0();
     for (int tile = p * gridDim.x + blockIdx.x; tile < tiles; tile += chains, first = false) {
@@ -644,19 +635,34 @@ constitutive_bwd_kernel(int kind, int n, const float* __restrict__ F, const uint
         store_chunk<NS>(pm + P::OFF_FEAT, SMALL_SPLIT, 0, r, f);
         store_chunk<NS>(pm + P::OFF_FEAT, SMALL_SPLIT, 1, r, f + 8);
       }
-      ps.publish();                                              // job 0
+      ps.publish();
+      if (issuer) {                                              // h1 = feat W0^T
+        umma::fence_after_sync();
+        gemm_split<NS, 1>(tp + COL_H1, feat, w0, ID64, false);
+        umma::commit(dbar);
+      }
       prefetch_row(gout, pi, n);
       prefetch_row(F, pi + chains * TP, n);
       PHASE(1);
       ps.wait_done();
       PHASE(2);
       gelu_phase<NS, true>(tl + COL_H1, pm + P::OFF_BIGA, r);    // a1; gelu'(h1) stays in TMEM
-      ps.publish();                                              // job 1
+      ps.publish();
+      if (issuer) {                                              // h2 = a1 W1^T
+        umma::fence_after_sync();
+        gemm_split<NS, 4>(tp + COL_H2, biga, w1, ID64, false);
+        umma::commit(dbar);
+      }
       PHASE(3);
       ps.wait_done();
       PHASE(4);
       gelu_phase<NS, true>(tl + COL_H2, pm + P::OFF_BIGB, r);    // a2; gelu'(h2)
-      ps.publish();                                              // job 2
+      ps.publish();
+      if (issuer) {                                              // o = a2 W2^T
+        umma::fence_after_sync();
+        gemm_split<NS, 4>(tp + COL_S, bigb, w2, ID16, false);
+        umma::commit(dbar);
+      }
       PHASE(5);
       ps.wait_done();
       PHASE(6);
@@ -690,17 +696,35 @@ constitutive_bwd_kernel(int kind, int n, const float* __restrict__ F, const uint
         store_chunk<NS>(pm + P::OFF_GO, SMALL_SPLIT, 0, r, g9);
         store_chunk<NS>(pm + P::OFF_GO, SMALL_SPLIT, 1, r, g9 + 8);
       }
-      ps.publish();                                              // job 3
+      ps.publish();
+      if (WGRAD) mbar_arrive(wfull);                             // -> dW2^T += a2^T go
+      if (issuer) {                                              // dL/da2 = go W2
+        umma::fence_after_sync();
+        gemm_split<NS, 1>(tp + COL_S, go, w2t, ID64_BT, false);
+        umma::commit(dbar);
+      }
       PHASE(7);
       ps.wait_done();
       PHASE(8);
       grad_phase<NS>(tl + COL_S, tl + COL_H2, pm + P::OFF_BIGB, r, ps, WGRAD);   // g2 over a2 (after dW2)
-      ps.publish();                                              // job 4
+      ps.publish();
+      if (WGRAD) mbar_arrive(wfull);                             // -> dW1 += g2^T a1
+      if (issuer) {                                              // dL/da1 = g2 W1
+        umma::fence_after_sync();
+        gemm_split<NS, 4>(tp + COL_S, bigb, w1t, ID64_BT, false);
+        umma::commit(dbar);
+      }
       PHASE(9);
       ps.wait_done();
       PHASE(10);
       grad_phase<NS>(tl + COL_S, tl + COL_H1, pm + P::OFF_BIGA, r, ps, WGRAD);   // g1 over a1 (after dW1)
-      ps.publish();                                              // job 5
+      ps.publish();
+      if (WGRAD) mbar_arrive(wfull);                             // -> dW0 += g1^T feat
+      if (issuer) {                                              // dL/dfeat = g1 W0
+        umma::fence_after_sync();
+        gemm_split<NS, 4>(tp + COL_S, biga, w0t, ID16_BT, false);
+        umma::commit(dbar);
+      }
       PHASE(11);
       ps.wait_done();
       PHASE(12);
@@ -745,6 +769,11 @@ constitutive_bwd_kernel(int kind, int n, const float* __restrict__ F, const uint
           const Mat3 t = mat3_mul_nt(mat3_mul(k.U, K), k.V);
 #pragma unroll
           for (int i = 0; i < 9; ++i) gFt.m[i] += t.m[i];
+        }
+        if (accumulate_gF) {  // dL/dF += ... (the caller's gF already holds the MPM substep's part)
+          const Mat3 prev = mat3_load(gF + (size_t)pi * 9);
+#pragma unroll
+          for (int i = 0; i < 9; ++i) gFt.m[i] += prev.m[i];
         }
         mat3_store(gF + (size_t)pi * 9, gFt);
       }
@@ -898,20 +927,32 @@ svd3_bwd_kernel(int n, const float* __restrict__ U, const float* __restrict__ si
   mat3_store(gA + (size_t)p * 9, mat3_mul(mat3_mul(u, inner), vh));
 }
 
-// gW += sum over the CTA slots of the partial buffer; the slots are zeroed for the next frame
+// gW += sum over the CTA slots of the partial buffer; the slots are zeroed for the next frame.
+// Block = 32 consecutive elements x 8 slot lanes (independent loads in flight), smem tree at the end.
 __global__ void __launch_bounds__(256)
 reduce_partials_kernel(int slots, float* __restrict__ part, float* __restrict__ gW0,
                        float* __restrict__ gW1, float* __restrict__ gW2) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= GW_FLOATS) return;
+  __shared__ float red[8][32];
+  const int lane = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int e = blockIdx.x * 32 + lane;
   float acc = 0.f;
-  for (int sidx = 0; sidx < slots; ++sidx) {
-    acc += part[(size_t)sidx * GW_FLOATS + e];
-    part[(size_t)sidx * GW_FLOATS + e] = 0.f;
+  if (e < GW_FLOATS) {
+#pragma unroll 4
+    for (int sidx = sl; sidx < slots; sidx += 8) {
+      float* q = part + (size_t)sidx * GW_FLOATS + e;
+      acc += *q;
+      *q = 0.f;
+    }
   }
-  if (e < GW_OFF0) gW1[e] += acc;
-  else if (e < GW_OFF2) gW0[e - GW_OFF0] += acc;
-  else gW2[e - GW_OFF2] += acc;
+  red[sl][lane] = acc;
+  __syncthreads();
+  if (sl == 0 && e < GW_FLOATS) {
+#pragma unroll
+    for (int i = 1; i < 8; ++i) acc += red[i][lane];
+    if (e < GW_OFF0) gW1[e] += acc;
+    else if (e < GW_OFF2) gW0[e - GW_OFF0] += acc;
+    else gW2[e - GW_OFF2] += acc;
+  }
 }
 
 bool g_attr_set = false;
@@ -966,7 +1007,7 @@ int neuma_debug_phase_cycles(long long* out_host, int reset) {
   cudaDeviceSynchronize();
   if (out_host) cudaMemcpyFromSymbol(out_host, g_phase_cycles, sizeof(g_phase_cycles));
   if (reset) {
-    long long z[32] = {0};
+    long long z[64] = {0};
     z[24] = 0x7fffffffffffffffLL;
     cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z));
   }
@@ -1011,10 +1052,10 @@ int neuma_constitutive_bwd_staged(neuma_ctx* ctx, int kind, int n, int hidden, c
   cudaStream_t st = (cudaStream_t)stream;
   if (wgrad)
     constitutive_bwd_kernel<true><<<grid, BWD_THREADS, BWD_SMEM, st>>>(
-        kind, n, F, (const uint8_t*)staged, alpha, gout, gF, gW0, gW1, gW2, nullptr);
+        kind, n, F, (const uint8_t*)staged, alpha, gout, gF, gW0, gW1, gW2, nullptr, 0);
   else
     constitutive_bwd_kernel<false><<<grid, BWD_THREADS, BWD_SMEM, st>>>(
-        kind, n, F, (const uint8_t*)staged, alpha, gout, gF, gW0, gW1, gW2, nullptr);
+        kind, n, F, (const uint8_t*)staged, alpha, gout, gF, gW0, gW1, gW2, nullptr, 0);
   NEUMA_LAUNCH_CHECK(ctx, "constitutive_bwd_kernel");
   return 0;
 }
@@ -1023,7 +1064,7 @@ int neuma_constitutive_partials_floats(neuma_ctx* ctx) { return ctx ? ctx->num_s
 
 int neuma_constitutive_bwd_partials(neuma_ctx* ctx, int kind, int n, int hidden, const float* F,
                                     const void* staged, float alpha, const float* gout, float* gF,
-                                    float* gWpart, void* stream) {
+                                    int accumulate_gF, float* gWpart, void* stream) {
   if (int r = check_args(ctx, kind, hidden)) return r;
   if (!gWpart) return neuma_fail_msg(ctx, "neuma_constitutive_bwd_partials: gWpart is NULL");
   if (n <= 0) return 0;
@@ -1031,7 +1072,7 @@ int neuma_constitutive_bwd_partials(neuma_ctx* ctx, int kind, int n, int hidden,
   const int tiles = (n + TP - 1) / TP;
   const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
   constitutive_bwd_kernel<true><<<grid, BWD_THREADS, BWD_SMEM, (cudaStream_t)stream>>>(
-      kind, n, F, (const uint8_t*)staged, alpha, gout, gF, nullptr, nullptr, nullptr, gWpart);
+      kind, n, F, (const uint8_t*)staged, alpha, gout, gF, nullptr, nullptr, nullptr, gWpart, accumulate_gF);
   NEUMA_LAUNCH_CHECK(ctx, "constitutive_bwd_kernel");
   return 0;
 }
@@ -1041,8 +1082,8 @@ int neuma_constitutive_reduce_partials(neuma_ctx* ctx, int hidden, float* gWpart
   if (int r = check_args(ctx, 0, hidden)) return r;
   if (!gWpart || !gW0 || !gW1 || !gW2)
     return neuma_fail_msg(ctx, "neuma_constitutive_reduce_partials: NULL argument");
-  reduce_partials_kernel<<<(GW_FLOATS + 255) / 256, 256, 0, (cudaStream_t)stream>>>(ctx->num_sms, gWpart,
-                                                                                   gW0, gW1, gW2);
+  reduce_partials_kernel<<<(GW_FLOATS + 31) / 32, 256, 0, (cudaStream_t)stream>>>(ctx->num_sms, gWpart,
+                                                                                 gW0, gW1, gW2);
   NEUMA_LAUNCH_CHECK(ctx, "reduce_partials_kernel");
   return 0;
 }

@@ -21,6 +21,7 @@
 #include "mpm_common.cuh"
 #include <cub/device/device_radix_sort.cuh>
 #include <limits.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -477,6 +478,16 @@ planes_add_kernel(float4* __restrict__ dst, const float4* __restrict__ src, size
 
 inline int node_pass_blocks(neuma_ctx* ctx) { return ctx->num_sms * 8; }
 
+// threads per block of the per-particle kernels (NEUMA_MPM_BLOCK overrides; tuned in profiles/)
+inline int pblock(int dflt) {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("NEUMA_MPM_BLOCK");
+    v = e ? atoi(e) : 0;
+  }
+  return v > 0 ? v : dflt;
+}
+
 int check_slab(neuma_ctx* ctx, const neuma_mpm_const* c) {
   if (!ctx || !c) return 2;
   if (c->num_grids <= 0 || c->nz <= 0 || c->z_off < 0 || c->z_off + c->nz > c->num_grids + 4)
@@ -515,7 +526,8 @@ int neuma_mpm_p2g_to(neuma_ctx* ctx, const neuma_mpm_const* c, int n, const floa
                      const int32_t* enabled, float* grid, void* stream) {
   if (int r = check_slab(ctx, c)) return r;
   if (n <= 0) return 0;
-  p2g_to_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(*c, n, x, v, C, stress, vol, rho,
+  const int pb = pblock(256);
+  p2g_to_kernel<<<(n + pb - 1) / pb, pb, 0, (cudaStream_t)stream>>>(*c, n, x, v, C, stress, vol, rho,
                                                                     enabled, (float4*)grid);
   NEUMA_LAUNCH_CHECK(ctx, "p2g_to_kernel");
   return 0;
@@ -537,12 +549,13 @@ int neuma_mpm_g2p_from(neuma_ctx* ctx, const neuma_mpm_const* c, int n, const fl
   if (int r = check_slab(ctx, c)) return r;
   if (n <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
+  const int pb = pblock(256);
   if (box_next)
-    g2p_from_kernel<true><<<(n + 255) / 256, 256, 0, st>>>(*c, n, x, F, clip_bound, enabled,
+    g2p_from_kernel<true><<<(n + pb - 1) / pb, pb, 0, st>>>(*c, n, x, F, clip_bound, enabled,
                                                            (const float4*)grid_v, x2, v2, C2, F2,
                                                            box_next);
   else
-    g2p_from_kernel<false><<<(n + 255) / 256, 256, 0, st>>>(*c, n, x, F, clip_bound, enabled,
+    g2p_from_kernel<false><<<(n + pb - 1) / pb, pb, 0, st>>>(*c, n, x, F, clip_bound, enabled,
                                                             (const float4*)grid_v, x2, v2, C2, F2,
                                                             nullptr);
   NEUMA_LAUNCH_CHECK(ctx, "g2p_from_kernel");
@@ -571,7 +584,8 @@ int neuma_mpm_bwd_scatter(neuma_ctx* ctx, const neuma_mpm_const* c, int n, const
   if (n <= 0) return 0;
   if (!v2 || !gx2 || !gv2 || !gC2 || !gF2 || !adj)
     return neuma_fail_msg(ctx, "neuma_mpm_bwd_scatter: NULL argument");
-  bwd_scatter_adj_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+  const int pb = pblock(256);
+  bwd_scatter_adj_kernel<<<(n + pb - 1) / pb, pb, 0, (cudaStream_t)stream>>>(
       *c, n, x, F, clip_bound, enabled, v2, gx2, gv2, gC2, gF2, (float4*)adj);
   NEUMA_LAUNCH_CHECK(ctx, "bwd_scatter_adj_kernel");
   return 0;
@@ -591,12 +605,13 @@ int neuma_mpm_bwd_node_gather(neuma_ctx* ctx, const neuma_mpm_const* c, int n, c
   cudaStream_t st = (cudaStream_t)stream;
   bwd_node_kernel<<<node_pass_blocks(ctx), 256, 0, st>>>(*c, box, (const float4*)grid_v, (float4*)adj);
   NEUMA_LAUNCH_CHECK(ctx, "bwd_node_kernel");
+  const int pb = pblock(128) > 128 ? 128 : pblock(128);
   if (C2)
-    bwd_gather_v_kernel<true><<<(n + 127) / 128, 128, 0, st>>>(
+    bwd_gather_v_kernel<true><<<(n + pb - 1) / pb, pb, 0, st>>>(
         *c, n, x, v, C, F, stress, vol, rho, clip_bound, enabled, v2, C2, gx2, gv2, gC2, gF2,
         (const float4*)grid_v, (const float4*)adj, gx, gv, gC, gF, gstress);
   else
-    bwd_gather_v_kernel<false><<<(n + 127) / 128, 128, 0, st>>>(
+    bwd_gather_v_kernel<false><<<(n + pb - 1) / pb, pb, 0, st>>>(
         *c, n, x, v, C, F, stress, vol, rho, clip_bound, enabled, v2, C2, gx2, gv2, gC2, gF2,
         (const float4*)grid_v, (const float4*)adj, gx, gv, gC, gF, gstress);
   NEUMA_LAUNCH_CHECK(ctx, "bwd_gather_v_kernel");

@@ -383,9 +383,10 @@ def constitutive_partials(like: torch.Tensor) -> torch.Tensor:
     return torch.zeros(nfl, dtype=torch.float32, device=like.device)
 
 
-def constitutive_bwd_partials(kind: int, F, staged, alpha: float, gout, gF, gWpart, hidden: int = 64) -> None:
+def constitutive_bwd_partials(kind: int, F, staged, alpha: float, gout, gF, gWpart, hidden: int = 64,
+                              accumulate_gF: bool = False) -> None:
     _ctx(F).call("neuma_constitutive_bwd_partials", int(kind), F.shape[0], hidden, ptr(F), ptr(staged),
-                 C.c_float(alpha), ptr(gout), ptr(gF), ptr(gWpart), _stream(F))
+                 C.c_float(alpha), ptr(gout), ptr(gF), int(accumulate_gF), ptr(gWpart), _stream(F))
 
 
 def constitutive_reduce_partials(gWpart, gW0, gW1, gW2, hidden: int = 64) -> None:

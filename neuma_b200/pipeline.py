@@ -111,9 +111,8 @@ class FusedFrame:
                                 gx2, gv2, gC2, self.gFtrial, self.grid[s], self.adj[s], self.box[s],
                                 gx, gv, gC, gF, self.gstress)
             # elasticity: stress[s] = E(F[s]);  dL/dF[s] += E'(F[s])^T gstress
-            ops.constitutive_bwd_partials(self.kind_e, self.F[s], self.We_st, 0.0, self.gstress, self.gF_e,
-                                          self.gWe_part)
-            gF.add_(self.gF_e)
+            ops.constitutive_bwd_partials(self.kind_e, self.F[s], self.We_st, 0.0, self.gstress, gF,
+                                          self.gWe_part, accumulate_gF=True)
             cur, nxt = nxt, cur
         ops.constitutive_reduce_partials(self.gWe_part, *self.gWe)
         ops.constitutive_reduce_partials(self.gWp_part, *self.gWp)

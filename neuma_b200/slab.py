@@ -251,9 +251,8 @@ class SlabRollout:
                                     self.rho, self.clip, self.enabled, self.v[s + 1], self.C[s + 1], gx2, gv2, gC2,
                                     self.gFtrial, self.grid[s], self.adj[s], self.box[s], gxo, gvo, gCo, gFo,
                                     self.gstress)
-            ops.constitutive_bwd_partials(self.kind_e, self.F[s], self.We_st, 0.0, self.gstress, self.gF_e,
-                                          self.gWe_part)
-            gFo.add_(self.gF_e)
+            ops.constitutive_bwd_partials(self.kind_e, self.F[s], self.We_st, 0.0, self.gstress, gFo,
+                                          self.gWe_part, accumulate_gF=True)
             cur, nxt = nxt, cur
         ops.constitutive_reduce_partials(self.gWe_part, *self.gWe)
         ops.constitutive_reduce_partials(self.gWp_part, *self.gWp)

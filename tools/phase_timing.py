@@ -38,7 +38,7 @@ for wg in (True, False):
     R = 1
     for _ in range(R):
         ops.constitutive_bwd_staged(0, F, st, 0.0, g, gF, *(gW if wg else (None, None, None)))
-    out = (ctypes.c_longlong * 32)()
+    out = (ctypes.c_longlong * 64)()
     lib.neuma_debug_phase_cycles(out, 1)
     tot = sum(out[i] for i in range(16))
     print(f"--- WGRAD={wg}: total {tot / R:.0f} cycles per launch for pipeline 0 of CTA 0")
@@ -46,5 +46,7 @@ for wg in (True, False):
         print(f"   {nm:22s} {out[i] / R:9.0f}  {out[i] / tot * 100:5.1f}%")
     print(f"   globaltimer: first CTA start -> last CTA end {(out[25] - out[24]) / 1e3:.2f} us; CTA0 start->end "
           f"{(out[28] - out[24]) / 1e3:.2f} us, {out[27] - out[26]} cycles => {(out[27] - out[26]) / max(out[28] - out[24], 1):.3f} GHz")
+    print("   MMA warp (CTA 0): issue cycles per job type (sum over jobs) " + ", ".join(f"J{j}={out[32 + j] / R:.0f}" for j in range(6))
+          + f"; jobs={out[40] / R:.0f}; warp lifetime {out[41] / R:.0f} cycles")
     for i, nm in zip(range(16, 21), ["setup", "main loop", "final sync wait", "GW readout+atomics", "sync+dealloc"]):
         print(f"   kernel: {nm:22s} {out[i] / R:9.0f}")
