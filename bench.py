@@ -255,6 +255,14 @@ def run_gpu(args):
     box_tmp = torch.zeros(8, dtype=torch.int32, device=dev)
     kt["grid_clear"] = event_time_us(lambda: ops.mpm_box_clear(cc, box_s, grid_s, None, box_tmp), it, wm, flush)
     kt["p2g"] = event_time_us(lambda: ops.mpm_p2g_to(cc, xs, vs, Cs, st, sx[0], sx[1], sx[3], grid_s), it, wm, flush)
+    def _clear_p2g():
+        ops.mpm_box_clear(cc, box_s, grid_s, None, box_tmp)
+        ops.mpm_p2g_to(cc, xs, vs, Cs, st, sx[0], sx[1], sx[3], grid_s)
+    kt["clear+p2g"] = event_time_us(_clear_p2g, it, wm, flush)          # one timed region: the metric's t(clear + P2G)
+
+    def _mpm_fwd():
+        ops.mpm_rollout_fwd(cc, xs, vs, Cs, Fs, st, *sx, outb, grid_s, adj_s, box_s, box_tmp)
+    kt["mpm_substep_fwd"] = event_time_us(_mpm_fwd, it, wm, flush)
     kt["grid_op"] = event_time_us(lambda: ops.mpm_grid_op_box(cc, box_s, grid_s, adj_s), it, wm, flush)
     kt["g2p"] = event_time_us(lambda: ops.mpm_g2p_from(cc, xs, Fs, sx[2], sx[3], grid_s, outb, box_tmp), it, wm, flush)
     # leave a valid (v, m) grid and a zeroed adjoint target in the slot for the backward timing
@@ -289,7 +297,7 @@ def run_gpu(args):
                 "render_bwd": _ms(lambda: eng.render_backward(dimg))}
     nr = ops.raster_binning(x0, 50 * 50)[0].shape[0]
     per_frame_us = {"constitutive_bwd": 2 * S * kt["constitutive_bwd"], "constitutive_fwd": 2 * S * kt["constitutive_fwd"],
-                    "mpm_fwd(clear+p2g+grid_op+g2p)": S * (kt["grid_clear"] + kt["p2g"] + kt["grid_op"] + kt["g2p"]),
+                    "mpm_fwd(clear+p2g+grid_op+g2p)": S * kt["mpm_substep_fwd"],
                     "mpm_substep_bwd": S * kt["mpm_substep_bwd"], "raster_fwd": kt["raster_fwd"],
                     "raster_bwd": kt["raster_bwd"]}
     peaks = {}
@@ -300,22 +308,28 @@ def run_gpu(args):
     tf_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
     peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
     p2g_bytes = 108 * n + 44 * Ng                              # clear 28 Ng + P2G 108 Np + 16 Ng
-    p2g_gbs = p2g_bytes / (kt["grid_clear"] + kt["p2g"]) / 1e3
+    p2g_gbs = p2g_bytes / kt["clear+p2g"] / 1e3
     fwd_bytes = 260 * n + 84 * Ng
-    mpm_fwd_gbs = fwd_bytes / (kt["grid_clear"] + kt["p2g"] + kt["grid_op"] + kt["g2p"]) / 1e3
+    mpm_fwd_gbs = fwd_bytes / kt["mpm_substep_fwd"] / 1e3
     dominant = max(per_frame_us, key=per_frame_us.get)
+    traffic = {}
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath))
     if dominant.startswith("constitutive"):
         # fused SVD + 13-64-64-9 MLP (+ LoRA merged); bwd = recompute + dgrad + wgrad = 3 x 5504 MAC / particle
         macs = 5504 * (3 if dominant.endswith("bwd") else 1)
         achieved = 2.0 * macs * n / (kt[dominant] * 1e-6) / 1e12
         roof = {"kernel": dominant + "_kernel", "bound": "tensor", "achieved": achieved, "peak": tf_peak,
-                "unit": "TFLOP/s", "frac": achieved / tf_peak, "traffic": None,
-                "note": "tcgen05 kind::f16 bf16x3 (6 bf16 products per fp32 MAC, counted as ONE MAC here); "
+                "unit": "TFLOP/s", "frac": achieved / tf_peak,
+                "traffic": traffic.get(dominant + "_kernel", {}).get("dram_bytes_per_launch"),
+                "note": "tcgen05 kind::f16, fp32 split into bf16 terms (forward x3 = 6 products, backward x2 = 3 products per "
+                        "fp32 MAC, counted as ONE MAC here); "
                         "SVD/GELU/split CUDA-core work bounds the kernel, not the tensor pipe; peak = sustained bf16 "
                         + peak_src}
     else:
         roof = {"kernel": "grid_clear+p2g", "bound": "hbm", "achieved": p2g_gbs, "peak": hbm_peak, "unit": "GB/s",
-                "frac": p2g_gbs / hbm_peak, "traffic": None, "note": "dense-grid algorithmic bytes (SURVEY 8d) over a box-sparse clear + P2G: the real traffic is "
+                "frac": p2g_gbs / hbm_peak, "traffic": traffic.get("box_clear+p2g_to", {}).get("dram_bytes_per_launch"), "note": "dense-grid algorithmic bytes (SURVEY 8d) over a box-sparse clear + P2G: the real traffic is "
                         "smaller, so the fraction can exceed 1; peak " + peak_src}
     line = {
         "metric": "sim+render fwd+bwd frames/sec at 100k particles/128^3 grid; P2G HBM GB/s",

@@ -1,7 +1,8 @@
 """Sim -> render glue: mirror of /root/reference/modules/tune/utils.py
-    diff_rasterization      :323-421
-    compute_bindings_xyz    :424-448
-    compute_bindings_F      :451-472
+    diff_rasterization            :323-421
+    compute_bindings_xyz          :424-448
+    compute_bindings_F            :451-472
+    preprocess_for_rasterization  :475-523   (multi-object scenes, experiments/inference.py:326)
 and the two pixel losses of modules/d3gs/utils/loss_utils.py:17-24.
 """
 from __future__ import annotations
@@ -111,6 +112,30 @@ def diff_rasterization(x: Tensor, deform_grad: Optional[Tensor], gaussians, view
                                        opacities=opacity, scales=None, rotations=None,
                                        cov3D_precomp=cov3D_deformed)
     return rendered_image
+
+
+def preprocess_for_rasterization(obj_gaussians, obj_deform_grad, obj_kernels_prev, obj_particles_curr,
+                                 obj_particles_prev, obj_bindings, obj_scalings):
+    """tune/utils.py:475-523: per object, move the kernels with their bound particles and average the
+    particles' deformation gradients, then concatenate everything diff_rasterization needs
+    (pass the result as x=pack["means3D"], deform_grad=pack["deform_grad"], gaussians=None,
+    guassians_cov=pack["cov3D"], ..., as experiments/inference.py:326-345 does)."""
+    obj_x = [compute_bindings_xyz(p_curr, p_prev, k_prev, b)
+             for p_curr, p_prev, k_prev, b in zip(obj_particles_curr, obj_particles_prev, obj_kernels_prev, obj_bindings)]
+    obj_F = [compute_bindings_F(dg, b) for dg, b in zip(obj_deform_grad, obj_bindings)]
+    obj_cov, obj_opa, obj_shs = [], [], []
+    for gaussians, scaling in zip(obj_gaussians, obj_scalings):
+        obj_cov.append(gaussians.get_covariance(scaling_modifier=scaling))
+        obj_opa.append(gaussians.get_opacity)
+        obj_shs.append(gaussians.get_features)
+    return {
+        "means3D": torch.cat(obj_x, dim=0),
+        "deform_grad": torch.cat(obj_F, dim=0),
+        "cov3D": torch.cat(obj_cov, dim=0),
+        "opacity": torch.cat(obj_opa, dim=0),
+        "shs": torch.cat(obj_shs, dim=0),
+        "active_sh_degree": obj_gaussians[0].active_sh_degree,
+    }
 
 
 def l1_loss(network_output: Tensor, gt: Tensor) -> Tensor:

@@ -194,3 +194,26 @@ class InvariantFullMetaPlasticity(_InvariantFullMeta):
 
     def _alpha(self) -> float:
         return self.alpha
+
+
+class ComposeMaterial(nn.Module):
+    """Per-object section dispatch for multi-object scenes: mirror of
+    modules/nclaw/material/preset.py:12-27 (used by experiments/inference.py:265-270 and the
+    viewer).  `materials[i]` is evaluated on the i-th contiguous slice of `sections[i]`
+    particles; empty sections are skipped; results are concatenated in order."""
+
+    def __init__(self, materials, sections) -> None:
+        super().__init__()
+        self.materials = nn.ModuleList(materials)
+        self.sections = sections
+
+    def update_sections(self, sections) -> None:
+        self.sections = sections
+
+    def forward(self, F: Tensor) -> Tensor:
+        outs = []
+        for m, f in zip(self.materials, torch.split(F, list(self.sections), dim=0)):
+            if f.numel() == 0:
+                continue
+            outs.append(m(f.contiguous()))
+        return torch.cat(outs, dim=0)
