@@ -44,8 +44,8 @@ class FusedFrame:
         self.sort = bool(sort)
         self.perm = torch.arange(n, device=device, dtype=torch.int32)   # sorted slot -> caller index
         self.inv = self.perm.clone()                                    # caller index -> sorted slot
-        self.We = [w.detach().contiguous() for w in We]
-        self.Wp = [w.detach().contiguous() for w in Wp]
+        self.We = [w.detach().clone().contiguous() for w in We]     # engine-owned static buffers (set_weights)
+        self.Wp = [w.detach().clone().contiguous() for w in Wp]
         # tensor-core operand images of the weights, refreshed by set_weights()
         self.We_st = ops.constitutive_stage(*self.We)
         self.Wp_st = ops.constitutive_stage(*self.Wp)
@@ -120,14 +120,22 @@ class FusedFrame:
             for a, b in zip(self.g[0], self.g[1]):
                 a.copy_(b)
 
-    def _capture(self, fn):
+    def _capture(self, fn, pre=None):
+        """`pre` re-establishes what `fn` consumes (the backward eats the zeroed adjoint grids the
+        forward leaves behind: ONE backward per forward)."""
+        if pre is not None:
+            pre()
         fn()                                  # warm-up: grows the library workspaces outside capture
         torch.cuda.synchronize(self.dev)
         side = torch.cuda.Stream(self.dev)
         side.wait_stream(torch.cuda.current_stream(self.dev))
         with torch.cuda.stream(side):
+            if pre is not None:
+                pre()
             fn()
         torch.cuda.current_stream(self.dev).wait_stream(side)
+        if pre is not None:
+            pre()
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             fn()
@@ -174,6 +182,8 @@ class FusedFrame:
         return tuple(self._to_caller(t[S]) for t in (self.x, self.v, self.C, self.F))
 
     def sim_backward(self, gx, gv, gC, gF):
+        """Reverse pass of the LAST sim_forward(): call it once per forward (it consumes the zeroed
+        adjoint grids the forward's node pass prepared)."""
         for dst, src in zip(self.g[0], (gx, gv, gC, gF)):
             if src is None:
                 dst.zero_()
@@ -185,7 +195,7 @@ class FusedFrame:
             if self._g_bwd is None:
                 keep = [t.clone() for t in self.g[0]]
                 keep_w = [t.clone() for t in self.gWe + self.gWp]
-                self._g_bwd = self._capture(self._sim_backward)
+                self._g_bwd = self._capture(self._sim_backward, pre=self._sim_forward)
                 for dst, src in zip(self.g[0], keep):
                     dst.copy_(src)
                 for dst, src in zip(self.gWe + self.gWp, keep_w):

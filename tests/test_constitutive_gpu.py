@@ -122,3 +122,33 @@ def test_constitutive_large_and_ragged(cuda_dev):
         out = ops.constitutive_fwd(ops.KIND_PLASTIC, F.to(cuda_dev), *Wd, alpha=1e-3)
         ref = CO.plasticity(F.double(), W, 1e-3)
         assert rel_err(out, ref) < 1e-4
+
+
+@pytest.mark.parametrize("n", [1, 130, 3000, 19000, 100_003])
+def test_staged_and_partials_paths_match_atomics_path(cuda_dev, n):
+    """the rollout entry points (staged weights, per-CTA gradient partials, gF accumulation)
+    against the plain entry points, for grids smaller and larger than the SM count"""
+    from neuma_b200 import ops
+    torch.manual_seed(n)
+    g = load_gold("jelly")
+    W, _ = weights_and_lora(g, "plastic")
+    Wd = [w.float().to(cuda_dev) for w in W]
+    F = (torch.eye(3) + 0.05 * torch.randn(n, 3, 3)).to(cuda_dev)
+    gout = torch.randn(n, 3, 3, device=cuda_dev)
+    alpha = 1e-3
+    out_ref = ops.constitutive_fwd(ops.KIND_PLASTIC, F, *Wd, alpha=alpha)
+    gF_ref, *gW_ref = ops.constitutive_bwd(ops.KIND_PLASTIC, F, *Wd, alpha, gout)
+    st = ops.constitutive_stage(*Wd)
+    out = torch.empty_like(F)
+    ops.constitutive_fwd_staged(ops.KIND_PLASTIC, F, st, alpha, out)
+    assert torch.equal(out, out_ref)
+    part = ops.constitutive_partials(F)
+    gF = torch.full_like(F, 2.0)
+    gW = [torch.zeros_like(w) for w in Wd]
+    for rep in range(2):                                   # two calls accumulate, one reduce
+        ops.constitutive_bwd_partials(ops.KIND_PLASTIC, F, st, alpha, gout, gF, part, accumulate_gF=(rep == 1))
+    ops.constitutive_reduce_partials(part, *gW)
+    assert rel_err(gF, 2 * gF_ref) < 1e-5                  # second call accumulated onto the first
+    for a, b in zip(gW, gW_ref):
+        assert rel_err(a, 2 * b) < 1e-4
+    assert float(part.abs().max()) == 0.0                  # slots are zeroed by the reduce
