@@ -339,7 +339,7 @@ def run_gpu(args):
         "config": {"workload": WORKLOAD, "particles": n, "grid": G, "gaussians": K, "image": [IMAGE, IMAGE],
                    "sh_degree": 3, "substeps_per_frame": S, "views": 1, "dt": spec["dt"],
                    "instances_rendered": int(nr),
-                   "mode": "fwd+bwd (l2 loss -> dL/dW_eff, dL/dstate0)", "weights": "jelly_0300 + LoRA r16 merged",
+                   "mode": "fwd+bwd (l2 loss -> dL/dW_eff, dL/dstate0)", "weights": os.path.basename(GOLD)[9:-4] + "_0300 + LoRA r16 merged",
                    "l2": "flushed between timed steps (256 MiB write)", "parallelism": f"replicas x{world}"},
         "p2g_hbm_gbs": p2g_gbs, "p2g_hbm_frac_of_measured_peak": p2g_gbs / hbm_peak,
         "mpm_fwd_substep_gbs": mpm_fwd_gbs,
@@ -507,6 +507,7 @@ def run_reference(args):
 
 
 def main():
+    global WORKLOAD, GOLD
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -514,9 +515,14 @@ def main():
     ap.add_argument("--substeps", type=int, default=20, help="MPM substeps per rendered frame (S)")
     ap.add_argument("--impl", default="neuma_b200", choices=["neuma_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default=WORKLOAD, choices=["bouncyball-50k-64", "jellyduck-100k-128", "claycat-200k-128"],
+                    help="parity-test configs of BASELINE.json for the record; the headline is jellyduck-100k-128")
     ap.add_argument("--slab", action="store_true",
                     help="BASELINE config 5: 1M particles / 256^3 MPM fwd+bwd, Z-slab sharded over the ranks")
     args = ap.parse_args()
+    WORKLOAD = args.workload
+    if WORKLOAD.startswith("claycat"):       # plasticine_0300 weights
+        GOLD = os.path.join(ROOT, "tests", "golden", "material_plasticine.npz")
     if args.impl == "reference":
         args.steps = min(args.steps, 5)         # each step is a ~10-20 s CPU sample
         args.warmup = min(args.warmup, 1)
