@@ -264,6 +264,14 @@ int neuma_constitutive_reduce_partials(neuma_ctx* ctx, int hidden, float* gWpart
 int neuma_bind_spmm(neuma_ctx* ctx, int K, int Np, const int32_t* rowptr, const int32_t* col,
                     const float* w, int ncol, const float* in, float* out, int transpose,
                     void* stream);
+/* gaussian_binding_with_clip_v1, modules/d3gs/utils/binding_utils.py:199-285: for
+ * every kernel k the particles with d^T Sigma^-1 d <= threshold (chi2.ppf(confidence, 3)), the
+ * `max_particles` (<= 16) nearest of them in that metric.  counts[K] = number inside (uncapped),
+ * cols[K, max_particles] = selected particle ids in ascending distance, -1 padded; pvals (may be
+ * NULL) the distances.  The weights are uniform 1/n (binding_utils.py:265-274). */
+int neuma_bind_build(neuma_ctx* ctx, int K, int Np, const float* means, const float* cov6,
+                     const float* x, float threshold, int max_particles, int32_t* counts,
+                     int32_t* cols, float* pvals, void* stream);
 /* deform_cov_by_F, modules/d3gs/utils/simulation_utils.py:25-48 */
 int neuma_deform_cov(neuma_ctx* ctx, int K, const float* cov6, const float* F, float* out6,
                      void* stream);

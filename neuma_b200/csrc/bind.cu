@@ -51,9 +51,101 @@ deform_cov_kernel(int K, const float* __restrict__ cov6, const float* __restrict
   o[3] = R(1, 1); o[4] = R(1, 2); o[5] = R(2, 2);
 }
 
+// ---------------------------------------------------------------- binding construction
+// gaussian_binding_with_clip_v1, modules/d3gs/utils/binding_utils.py:199-285: for every kernel k
+// the particles with Mahalanobis distance p = d^T Sigma^-1 d <= chi2 (test_point_in_gaussians_with_
+// inv_cov_warp, :88-120), at most `max_p` of them, those with the smallest p.  The reference runs
+// a Python loop of K launches over all Np particles and fills a dense K x Np matrix; here one
+// warp owns one kernel, streams the particles once and keeps per-lane sorted candidate lists
+// that are merged with warp shuffles at the end.
+constexpr int BIND_MAX = 16;
+
+__global__ void __launch_bounds__(256)
+bind_build_kernel(int K, int Np, const float* __restrict__ means, const float* __restrict__ cov6,
+                  const float* __restrict__ x, float threshold, int max_p, int* __restrict__ counts,
+                  int* __restrict__ cols, float* __restrict__ pvals) {
+  const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (k >= K) return;
+  // Sigma^-1 (compute_inv_cov, binding_utils.py:22-45): adjugate / determinant of the symmetric 3x3
+  const float* c = cov6 + (size_t)k * 6;
+  const float a00 = c[0], a01 = c[1], a02 = c[2], a11 = c[3], a12 = c[4], a22 = c[5];
+  const float c00 = a11 * a22 - a12 * a12, c01 = a02 * a12 - a01 * a22, c02 = a01 * a12 - a02 * a11;
+  const float c11 = a00 * a22 - a02 * a02, c12 = a01 * a02 - a00 * a12, c22 = a00 * a11 - a01 * a01;
+  const float idet = 1.0f / (a00 * c00 + a01 * c01 + a02 * c02);
+  const float i00 = c00 * idet, i01 = c01 * idet, i02 = c02 * idet, i11 = c11 * idet, i12 = c12 * idet,
+              i22 = c22 * idet;
+  const float m0 = means[3 * k], m1 = means[3 * k + 1], m2 = means[3 * k + 2];
+  float bp[BIND_MAX];
+  int bi[BIND_MAX];
+#pragma unroll
+  for (int i = 0; i < BIND_MAX; ++i) { bp[i] = 3.0e38f; bi[i] = -1; }
+  int inside = 0;
+  for (int q = lane; q < Np; q += 32) {
+    const float d0 = x[3 * q] - m0, d1 = x[3 * q + 1] - m1, d2 = x[3 * q + 2] - m2;
+    const float p1 = d0 * i00 + d1 * i01 + d2 * i02;
+    const float p2 = d0 * i01 + d1 * i11 + d2 * i12;
+    const float p3 = d0 * i02 + d1 * i12 + d2 * i22;
+    const float pv = p1 * d0 + p2 * d1 + p3 * d2;
+    if (pv <= threshold) {
+      ++inside;
+      if (pv < bp[BIND_MAX - 1]) {  // sorted insert (rare path: a kernel holds a few dozen particles)
+        float cp = pv;
+        int ci = q;
+#pragma unroll
+        for (int i = 0; i < BIND_MAX; ++i) {
+          if (cp < bp[i]) {
+            const float tp = bp[i]; bp[i] = cp; cp = tp;
+            const int ti = bi[i]; bi[i] = ci; ci = ti;
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) inside += __shfl_xor_sync(0xffffffffu, inside, o);
+  if (lane == 0) counts[k] = inside;
+  // merge: max_p rounds of "smallest head over the 32 lanes"
+  for (int r = 0; r < max_p; ++r) {
+    float hp = bp[0];
+    int hl = lane;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float op = __shfl_xor_sync(0xffffffffu, hp, o);
+      const int ol = __shfl_xor_sync(0xffffffffu, hl, o);
+      if (op < hp || (op == hp && ol < hl)) { hp = op; hl = ol; }
+    }
+    const int widx = __shfl_sync(0xffffffffu, bi[0], hl);
+    if (lane == 0) {
+      cols[(size_t)k * max_p + r] = (hp < 3.0e38f) ? widx : -1;
+      if (pvals) pvals[(size_t)k * max_p + r] = hp;
+    }
+    if (lane == hl) {  // pop
+#pragma unroll
+      for (int i = 0; i + 1 < BIND_MAX; ++i) { bp[i] = bp[i + 1]; bi[i] = bi[i + 1]; }
+      bp[BIND_MAX - 1] = 3.0e38f;
+      bi[BIND_MAX - 1] = -1;
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" {
+
+int neuma_bind_build(neuma_ctx* ctx, int K, int Np, const float* means, const float* cov6,
+                     const float* x, float threshold, int max_particles, int32_t* counts,
+                     int32_t* cols, float* pvals, void* stream) {
+  if (!ctx) return 2;
+  if (max_particles < 1 || max_particles > BIND_MAX)
+    return neuma_fail_msg(ctx, "neuma_bind_build: max_particles must be in [1, 16]");
+  if (K <= 0) return 0;
+  const long long threads = (long long)K * 32;
+  bind_build_kernel<<<(int)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      K, Np, means, cov6, x, threshold, max_particles, counts, cols, pvals);
+  NEUMA_LAUNCH_CHECK(ctx, "bind_build_kernel");
+  return 0;
+}
 
 int neuma_bind_spmm(neuma_ctx* ctx, int K, int Np, const int32_t* rowptr, const int32_t* col,
                     const float* w, int ncol, const float* in, float* out, int transpose,

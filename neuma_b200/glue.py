@@ -3,6 +3,7 @@
     compute_bindings_xyz          :424-448
     compute_bindings_F            :451-472
     preprocess_for_rasterization  :475-523   (multi-object scenes, experiments/inference.py:326)
+and gaussian_binding_with_clip_v1 of modules/d3gs/utils/binding_utils.py:199-285
 and the two pixel losses of modules/d3gs/utils/loss_utils.py:17-24.
 """
 from __future__ import annotations
@@ -136,6 +137,25 @@ def preprocess_for_rasterization(obj_gaussians, obj_deform_grad, obj_kernels_pre
         "shs": torch.cat(obj_shs, dim=0),
         "active_sh_degree": obj_gaussians[0].active_sh_degree,
     }
+
+
+def gaussian_binding_with_clip_v1(gaussians, particles: Tensor, confidence: float = 0.95, max_particles: int = 10):
+    """modules/d3gs/utils/binding_utils.py:199-285 on the GPU in one launch (the reference loops over
+    the K kernels in Python).  Returns the K x Np weight matrix as a torch.sparse_coo_tensor -- what
+    the reference stores in bindings.pt (tune/utils.py:297-318) -- instead of its dense intermediate
+    (20 GB at 50k x 100k).  Uniform weights 1/n over the <= max_particles nearest particles inside the
+    chi2_3(confidence) ellipsoid (binding_utils.py:265-274)."""
+    from scipy.stats import chi2
+    means = gaussians.get_xyz.detach().float().contiguous()
+    cov6 = gaussians.get_covariance().detach().float().reshape(-1, 6).contiguous()
+    x = particles.detach().float().contiguous()
+    counts, cols, _ = ops.bind_build(means, cov6, x, float(chi2.ppf(confidence, 3)), max_particles)
+    n_sel = counts.clamp(max=max_particles)
+    assert int(n_sel.min()) > 0, "a kernel has no particle inside its confidence ellipsoid (binding_utils.py:281)"
+    keep = cols >= 0
+    rows = torch.arange(means.shape[0], device=x.device).unsqueeze(1).expand_as(cols)[keep]
+    w = (1.0 / n_sel.float()).unsqueeze(1).expand_as(cols)[keep]
+    return torch.sparse_coo_tensor(torch.stack([rows, cols[keep].long()]), w, (means.shape[0], x.shape[0])).coalesce()
 
 
 def l1_loss(network_output: Tensor, gt: Tensor) -> Tensor:

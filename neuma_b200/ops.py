@@ -413,3 +413,15 @@ def mpm_bwd_node_gather(c: MPMConstC, x, v, Cm, F, stress, vol, rho, clip_bound,
                  ptr(stress), ptr(vol), ptr(rho), ptr(clip_bound), ptr(enabled), ptr(v2), ptr(C2), ptr(gx2),
                  ptr(gv2), ptr(gC2), ptr(gF2), ptr(grid_v), ptr(adj), ptr(box), ptr(gx), ptr(gv), ptr(gC), ptr(gF),
                  ptr(gstress), _stream(x))
+
+
+def bind_build(means: torch.Tensor, cov6: torch.Tensor, x: torch.Tensor, threshold: float, max_particles: int = 10):
+    """(counts[K], cols[K, max_particles] (-1 padded, ascending distance), pvals) -- see neuma_bind_build."""
+    means, cov6, x = map(_f32, (means, cov6, x))
+    K = means.shape[0]
+    counts = torch.empty(K, dtype=torch.int32, device=x.device)
+    cols = torch.empty(K, max_particles, dtype=torch.int32, device=x.device)
+    pvals = torch.empty(K, max_particles, dtype=torch.float32, device=x.device)
+    _ctx(x).call("neuma_bind_build", K, x.shape[0], ptr(means), ptr(cov6), ptr(x), C.c_float(threshold),
+                 int(max_particles), ptr(counts), ptr(cols), ptr(pvals), _stream(x))
+    return counts, cols, pvals
