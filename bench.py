@@ -294,7 +294,7 @@ def run_gpu(args):
     frame_ms = {"sim_fwd_graph": _ms(lambda: eng.sim_forward()),
                 "sim_bwd_graph": _ms(lambda: eng.sim_backward(*gz)),
                 "render_fwd": _ms(lambda: eng.render_forward(de_x_prev, k_prev)),
-                "render_bwd": _ms(lambda: eng.render_backward(dimg))}
+                "render_bwd": _ms(lambda: eng.render_backward(dimg, accumulate_into_state_grad=True))}
     nr = ops.raster_binning(x0, 50 * 50)[0].shape[0]
     per_frame_us = {"constitutive_bwd": 2 * S * kt["constitutive_bwd"], "constitutive_fwd": 2 * S * kt["constitutive_fwd"],
                     "mpm_fwd(clear+p2g+grid_op+g2p)": S * kt["mpm_substep_fwd"],

@@ -264,6 +264,20 @@ int neuma_constitutive_reduce_partials(neuma_ctx* ctx, int hidden, float* gWpart
 int neuma_bind_spmm(neuma_ctx* ctx, int K, int Np, const int32_t* rowptr, const int32_t* col,
                     const float* w, int ncol, const float* in, float* out, int transpose,
                     void* stream);
+/* The whole sim -> render hand-over of a frame in one launch:
+ * denormalize_points_helper_func (nclaw/utils.py:110-118) + compute_bindings_xyz + compute_bindings_F
+ * (tune/utils.py:424-472) + deform_cov_by_F (simulation_utils.py:25-48).  `slot` (may be NULL)
+ * maps a caller-order particle index to its row in x / F; center_host / size_host: float[3] on
+ * the HOST (NULL = 0 / 1); Fk_out may be NULL.  The second entry is the transpose for
+ * dL/dmeans3D -> dL/dx (accumulates into gx, which the caller zero-fills). */
+int neuma_particles_to_gaussians(neuma_ctx* ctx, int K, const int32_t* rowptr, const int32_t* col,
+                                 const float* w, const int32_t* slot, const float* x, const float* F,
+                                 const float* center_host, const float* size_host,
+                                 const float* de_x_prev, const float* k_prev, const float* cov6,
+                                 float* means3D, float* cov_out, float* Fk_out, void* stream);
+int neuma_gaussians_to_particles(neuma_ctx* ctx, int K, const int32_t* rowptr, const int32_t* col,
+                                 const float* w, const int32_t* slot, const float* g_means3D,
+                                 const float* size_host, float* gx, void* stream);
 /* gaussian_binding_with_clip_v1, modules/d3gs/utils/binding_utils.py:199-285: for
  * every kernel k the particles with d^T Sigma^-1 d <= threshold (chi2.ppf(confidence, 3)), the
  * `max_particles` (<= 16) nearest of them in that metric.  counts[K] = number inside (uncapped),

@@ -81,6 +81,8 @@ SIGNATURES = {
     "neuma_constitutive_bwd_partials": [_P, _I, _I, _I, _P, _P, _F, _P, _P, _I, _P, _P],
     "neuma_constitutive_reduce_partials": [_P, _I, _P, _P, _P, _P, _P],
     "neuma_bind_spmm": [_P, _I, _I, _P, _P, _P, _I, _P, _P, _I, _P],
+    "neuma_particles_to_gaussians": [_P, _I] + [_P] * 15,
+    "neuma_gaussians_to_particles": [_P, _I] + [_P] * 8,
     "neuma_bind_build": [_P, _I, _I, _P, _P, _P, _F, _I, _P, _P, _P, _P],
     "neuma_deform_cov": [_P, _I, _P, _P, _P, _P],
     "neuma_raster_fwd": [_P, _RP, _I, _I] + [_P] * 8,

@@ -51,6 +51,76 @@ deform_cov_kernel(int K, const float* __restrict__ cov6, const float* __restrict
   o[3] = R(1, 1); o[4] = R(1, 2); o[5] = R(2, 2);
 }
 
+// ---------------------------------------------------------------- particles -> Gaussians, fused
+// One kernel for the whole sim -> render hand-over of a frame (tune/utils.py:424-472 +
+// nclaw/utils.py:110-118 + simulation_utils.py:25-48):
+//   de_x      = (x - center) / size                         denormalize_points_helper_func
+//   means3D_k = k_prev_k + sum_e w_e (de_x[c_e] - de_x_prev[c_e])     compute_bindings_xyz
+//   F_k       = sum_e w_e F[c_e]                                       compute_bindings_F
+//   cov'_k    = F_k Sigma_k F_k^T                                      deform_cov_by_F
+// `slot` (may be NULL) maps a caller-order particle index to its row in x / F (the engine keeps
+// the particles in cell order); de_x_prev is in caller order.
+struct Vec3 {
+  float v[3];
+};
+__global__ void __launch_bounds__(128)
+particles_to_gaussians_kernel(int K, const int* __restrict__ rowptr, const int* __restrict__ col,
+                              const float* __restrict__ w, const int* __restrict__ slot,
+                              const float* __restrict__ x, const float* __restrict__ F, Vec3 center,
+                              Vec3 size, const float* __restrict__ de_x_prev,
+                              const float* __restrict__ k_prev, const float* __restrict__ cov6,
+                              float* __restrict__ means3D, float* __restrict__ cov_out,
+                              float* __restrict__ Fk_out) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  float dx[3] = {0.f, 0.f, 0.f};
+  Mat3 Fk;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) Fk.m[i] = 0.f;
+  for (int e = rowptr[k]; e < rowptr[k + 1]; ++e) {
+    const int c = col[e];
+    const int r = slot ? slot[c] : c;
+    const float we = w[e];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+      dx[a] += we * ((x[3 * (size_t)r + a] - center.v[a]) / size.v[a] - de_x_prev[3 * (size_t)c + a]);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Fk.m[i] += we * F[9 * (size_t)r + i];
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) means3D[3 * (size_t)k + a] = k_prev[3 * (size_t)k + a] + dx[a];
+  const float* c6 = cov6 + (size_t)k * 6;
+  Mat3 S;
+  S(0, 0) = c6[0]; S(0, 1) = c6[1]; S(0, 2) = c6[2];
+  S(1, 0) = c6[1]; S(1, 1) = c6[3]; S(1, 2) = c6[4];
+  S(2, 0) = c6[2]; S(2, 1) = c6[4]; S(2, 2) = c6[5];
+  const Mat3 R = mat3_mul_nt(mat3_mul(Fk, S), Fk);
+  float* o = cov_out + (size_t)k * 6;
+  o[0] = R(0, 0); o[1] = R(0, 1); o[2] = R(0, 2);
+  o[3] = R(1, 1); o[4] = R(1, 2); o[5] = R(2, 2);
+  if (Fk_out) mat3_store(Fk_out + (size_t)k * 9, Fk);
+}
+
+// the transpose: dL/dmeans3D [K,3] -> dL/dx accumulated into gx [Np,3] (rows = slot[c]; the caller
+// zero-fills).  cov' carries no gradient.
+__global__ void __launch_bounds__(128)
+gaussians_to_particles_kernel(int K, const int* __restrict__ rowptr, const int* __restrict__ col,
+                              const float* __restrict__ w, const int* __restrict__ slot,
+                              const float* __restrict__ g_means3D, Vec3 size, float* __restrict__ gx) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  float g[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) g[a] = g_means3D[3 * (size_t)k + a] / size.v[a];
+  for (int e = rowptr[k]; e < rowptr[k + 1]; ++e) {
+    const int c = col[e];
+    const int r = slot ? slot[c] : c;
+    const float we = w[e];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) atomicAdd(gx + 3 * (size_t)r + a, we * g[a]);
+  }
+}
+
 // ---------------------------------------------------------------- binding construction
 // gaussian_binding_with_clip_v1, modules/d3gs/utils/binding_utils.py:199-285: for every kernel k
 // the particles with Mahalanobis distance p = d^T Sigma^-1 d <= chi2 (test_point_in_gaussians_with_
@@ -132,6 +202,34 @@ bind_build_kernel(int K, int Np, const float* __restrict__ means, const float* _
 }  // namespace
 
 extern "C" {
+
+int neuma_particles_to_gaussians(neuma_ctx* ctx, int K, const int32_t* rowptr, const int32_t* col,
+                                 const float* w, const int32_t* slot, const float* x, const float* F,
+                                 const float* center_host, const float* size_host,
+                                 const float* de_x_prev, const float* k_prev, const float* cov6,
+                                 float* means3D, float* cov_out, float* Fk_out, void* stream) {
+  if (!ctx) return 2;
+  if (K <= 0) return 0;
+  Vec3 c, s;
+  for (int a = 0; a < 3; ++a) { c.v[a] = center_host ? center_host[a] : 0.f; s.v[a] = size_host ? size_host[a] : 1.f; }
+  particles_to_gaussians_kernel<<<(K + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      K, rowptr, col, w, slot, x, F, c, s, de_x_prev, k_prev, cov6, means3D, cov_out, Fk_out);
+  NEUMA_LAUNCH_CHECK(ctx, "particles_to_gaussians_kernel");
+  return 0;
+}
+
+int neuma_gaussians_to_particles(neuma_ctx* ctx, int K, const int32_t* rowptr, const int32_t* col,
+                                 const float* w, const int32_t* slot, const float* g_means3D,
+                                 const float* size_host, float* gx, void* stream) {
+  if (!ctx) return 2;
+  if (K <= 0) return 0;
+  Vec3 s;
+  for (int a = 0; a < 3; ++a) s.v[a] = size_host ? size_host[a] : 1.f;
+  gaussians_to_particles_kernel<<<(K + 127) / 128, 128, 0, (cudaStream_t)stream>>>(K, rowptr, col, w, slot,
+                                                                                  g_means3D, s, gx);
+  NEUMA_LAUNCH_CHECK(ctx, "gaussians_to_particles_kernel");
+  return 0;
+}
 
 int neuma_bind_build(neuma_ctx* ctx, int K, int Np, const float* means, const float* cov6,
                      const float* x, float threshold, int max_particles, int32_t* counts,

@@ -425,3 +425,27 @@ def bind_build(means: torch.Tensor, cov6: torch.Tensor, x: torch.Tensor, thresho
     _ctx(x).call("neuma_bind_build", K, x.shape[0], ptr(means), ptr(cov6), ptr(x), C.c_float(threshold),
                  int(max_particles), ptr(counts), ptr(cols), ptr(pvals), _stream(x))
     return counts, cols, pvals
+
+
+def _host3(t, default):
+    vals = [float(v) for v in (t.detach().cpu().reshape(-1).tolist() if torch.is_tensor(t) else (t if t is not None else [default] * 3))]
+    return (C.c_float * 3)(*vals)
+
+
+def particles_to_gaussians(rowptr, col, w, slot, x, F, center, size, de_x_prev, k_prev, cov6, want_Fk: bool = False):
+    """means3D [K,3], deformed cov [K,6] (, F_k [K,3,3]) from the particle state in one launch."""
+    K = rowptr.shape[0] - 1
+    means3D = torch.empty(K, 3, device=x.device, dtype=torch.float32)
+    cov = torch.empty(K, 6, device=x.device, dtype=torch.float32)
+    Fk = torch.empty(K, 3, 3, device=x.device, dtype=torch.float32) if want_Fk else None
+    _ctx(x).call("neuma_particles_to_gaussians", K, ptr(rowptr), ptr(col), ptr(w), ptr(slot), ptr(x), ptr(F),
+                 _host3(center, 0.0), _host3(size, 1.0), ptr(de_x_prev), ptr(k_prev), ptr(cov6), ptr(means3D), ptr(cov),
+                 ptr(Fk), _stream(x))
+    return means3D, cov, Fk
+
+
+def gaussians_to_particles(rowptr, col, w, slot, g_means3D, size, gx_out) -> None:
+    """gx_out [Np,3] += B^T g_means3D / size (rows through `slot`); the caller zero-fills gx_out."""
+    K = rowptr.shape[0] - 1
+    _ctx(g_means3D).call("neuma_gaussians_to_particles", K, ptr(rowptr), ptr(col), ptr(w), ptr(slot), ptr(g_means3D),
+                         _host3(size, 1.0), ptr(gx_out), _stream(g_means3D))

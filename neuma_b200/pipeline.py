@@ -74,6 +74,8 @@ class FusedFrame:
         self.gWp_part = ops.constitutive_partials(self.x)
         self.center = torch.zeros(3, **f) if center is None else center.to(**f)
         self.size = torch.ones(3, **f) if size is None else size.to(**f)
+        self._center_h = [float(v) for v in self.center.cpu().tolist()]      # kernel parameters
+        self._size_h = [float(v) for v in self.size.cpu().tolist()]
         self.use_graphs = use_graphs
         self._g_fwd = self._g_bwd = None
         self._ctx = ops._ctx(self.x)
@@ -171,24 +173,30 @@ class FusedFrame:
             return out
         return t
 
-    def sim_forward(self):
+    def sim_forward(self, return_state: bool = True):
         if not self.use_graphs:
             self._sim_forward()
         else:
             if self._g_fwd is None:
                 self._g_fwd = self._capture(self._sim_forward)   # slot 0 (state, box) is read-only: replay-safe
             self._g_fwd.replay()
+        if not return_state:
+            return None
         S = self.S
         return tuple(self._to_caller(t[S]) for t in (self.x, self.v, self.C, self.F))
 
     def sim_backward(self, gx, gv, gC, gF):
         """Reverse pass of the LAST sim_forward(): call it once per forward (it consumes the zeroed
-        adjoint grids the forward's node pass prepared)."""
+        adjoint grids the forward's node pass prepared).  Gradients in / out in the caller's order."""
         for dst, src in zip(self.g[0], (gx, gv, gC, gF)):
             if src is None:
                 dst.zero_()
             else:
                 self._to_sorted(src, out=dst)
+        return self._run_backward()
+
+    def _run_backward(self, want_g0: bool = True):
+        """self.g[0] holds dL/d(state[S]) in the engine's (cell) order."""
         if not self.use_graphs:
             self._sim_backward()
         else:
@@ -201,7 +209,7 @@ class FusedFrame:
                 for dst, src in zip(self.gWe + self.gWp, keep_w):
                     dst.copy_(src)
             self._g_bwd.replay()
-        return [self._to_caller(t) for t in self.g[0]]
+        return [self._to_caller(t) for t in self.g[0]] if want_g0 else None
 
     def set_weights(self, We=None, Wp=None) -> None:
         """New (LoRA-merged) weights, e.g. after an optimiser step: copied into the engine's static
@@ -219,39 +227,44 @@ class FusedFrame:
 
     # ------------------------------------------------------------------ sim -> render
     def render_forward(self, de_x_prev: torch.Tensor, k_prev: torch.Tensor):
-        """bindings + covariance deformation + rasterization of the frame's final state."""
+        """particles -> Gaussians (denormalise, both bindings, covariance deformation: ONE launch,
+        SURVEY 8f.4) + rasterization of the frame's final state."""
         b, gs, S = self.bind, self.gs, self.S
-        de_x = (self._to_caller(self.x[S]) - self.center) / self.size
-        self._delta = de_x - de_x_prev
-        means3D = k_prev + ops.bind_spmm(b.rowptr, b.col, b.w, self._delta, self.n)
-        Fk = ops.bind_spmm(b.rowptr, b.col, b.w, self._to_caller(self.F[S]).reshape(self.n, 9), self.n)
-        cov = ops.deform_cov(gs["cov6"], Fk)
+        means3D, cov, _ = ops.particles_to_gaussians(b.rowptr, b.col, b.w, self.inv if self.sort else None,
+                                                     self.x[S], self.F[S], self._center_h, self._size_h,
+                                                     de_x_prev, k_prev, gs["cov6"])
         image, radii = ops.raster_fwd(self.settings, means3D, gs["shs"], None, gs["opac"], cov)
         self._render_saved = (means3D, cov, radii)
-        return image, means3D, de_x
+        return image, means3D
 
-    def render_backward(self, dL_dimage: torch.Tensor):
-        """dL/dimage -> dL/dx of the frame's final state (cov3D carries no gradient)."""
+    def render_backward(self, dL_dimage: torch.Tensor, accumulate_into_state_grad: bool = False):
+        """dL/dimage -> dL/dmeans3D [K,3] (cov3D carries no gradient).  With
+        accumulate_into_state_grad the transpose binding adds it straight into the engine's
+        dL/dx buffer (cell order), ready for _run_backward()."""
         b, gs = self.bind, self.gs
         means3D, cov, radii = self._render_saved
         g3, _g2, *_ = ops.raster_bwd(self.settings, means3D, gs["shs"], None, gs["opac"], cov, radii, dL_dimage)
-        gde = ops.bind_spmm(b.rowptr, b.col, b.w, g3, self.n, transpose=True)
-        return gde / self.size
+        if accumulate_into_state_grad:
+            ops.gaussians_to_particles(b.rowptr, b.col, b.w, self.inv if self.sort else None, g3, self._size_h,
+                                       self.g[0][0])
+        return g3
 
     # ------------------------------------------------------------------ one frame, forward + backward
-    def frame_fwd_bwd(self, gt: torch.Tensor, de_x_prev, k_prev, g_state_next=None):
+    def frame_fwd_bwd(self, gt: torch.Tensor, de_x_prev, k_prev, g_state_next=None, want_g0: bool = True):
         """S substeps + render + l2 loss, then the full reverse pass.  Returns
-        (loss, dL/d(state at frame start))."""
-        self.sim_forward()
-        image, means3D, de_x = self.render_forward(de_x_prev, k_prev)
+        (loss, dL/d(state at frame start)).  de_x_prev / k_prev / g_state_next / the result are in
+        the caller's particle order."""
+        self.sim_forward(return_state=False)
+        image, means3D = self.render_forward(de_x_prev, k_prev)
         diff = image - gt
         loss = (diff * diff).mean()
         dL_dimage = diff * (2.0 / diff.numel())
-        gx = self.render_backward(dL_dimage)
-        if g_state_next is not None:
-            gx = gx + g_state_next[0]
-            gv, gC, gF = g_state_next[1:]
-        else:
-            gv = gC = gF = None
-        g0 = self.sim_backward(gx, gv, gC, gF)
-        return loss, g0
+        for i, dst in enumerate(self.g[0]):                     # dL/d(state[S]) in the engine's order
+            src = None if g_state_next is None else g_state_next[i]
+            if src is None:
+                dst.zero_()
+            else:
+                self._to_sorted(src, out=dst)
+        self.render_backward(dL_dimage, accumulate_into_state_grad=True)
+        return loss, self._run_backward(want_g0)
+

@@ -82,3 +82,40 @@ def test_binding_construction_matches_reference_rule(cuda_dev):
             kth = torch.sort(p[k]).values[9]
             assert torch.all(p[k][sel] <= kth * (1 + eps))
         assert torch.allclose(vals[rows == k], torch.full((len(sel),), 1.0 / len(sel)))
+
+
+def test_fused_particles_to_gaussians_and_transpose(cuda_dev):
+    """one launch == denormalise + compute_bindings_xyz + compute_bindings_F + deform_cov_by_F
+    (tune/utils.py:424-472, simulation_utils.py:25-48), with the engine's cell-order indirection."""
+    from neuma_b200 import ops, synthetic as S
+    torch.manual_seed(1)
+    Np, G = 5000, 32
+    x = 0.3 + 0.4 * torch.rand(Np, 3)
+    g = S.make_gaussians(x, 900, G, seed=7)
+    K = g["K"]
+    F = torch.eye(3) + 0.1 * torch.randn(Np, 3, 3)
+    x_prev = x + 0.01 * torch.randn(Np, 3)
+    center, size = torch.tensor([0.1, -0.2, 0.05]), torch.tensor([1.5, 0.7, 2.0])
+    de_prev = (x_prev - center) / size
+    perm = torch.randperm(Np)                       # engine row i holds caller particle perm[i]
+    slot = torch.empty(Np, dtype=torch.int64)
+    slot[perm] = torch.arange(Np)
+    dev = lambda t: t.to(cuda_dev)
+    means3D, cov, Fk = ops.particles_to_gaussians(dev(g["rowptr"]), dev(g["col"]), dev(g["w"]), dev(slot.int()),
+                                                  dev(x[perm].contiguous()), dev(F[perm].contiguous()), center, size,
+                                                  dev(de_prev), dev(g["xyz"]), dev(g["cov6"]), want_Fk=True)
+    B = torch.sparse_csr_tensor(g["rowptr"].long(), g["col"].long(), g["w"].double(), (K, Np)).to_sparse_coo()
+    de = ((x - center) / size).double()
+    ref_m = g["xyz"].double() + torch.sparse.mm(B, de - de_prev.double())
+    ref_F = torch.sparse.mm(B, F.double().reshape(Np, 9)).reshape(K, 3, 3)
+    c = g["cov6"].double()
+    Sig = torch.stack([c[:, 0], c[:, 1], c[:, 2], c[:, 1], c[:, 3], c[:, 4], c[:, 2], c[:, 4], c[:, 5]], -1).reshape(K, 3, 3)
+    R = ref_F @ Sig @ ref_F.transpose(1, 2)
+    ref_cov = torch.stack([R[:, 0, 0], R[:, 0, 1], R[:, 0, 2], R[:, 1, 1], R[:, 1, 2], R[:, 2, 2]], -1)
+    assert rel_err(means3D, ref_m) < 1e-5 and rel_err(Fk, ref_F) < 1e-5 and rel_err(cov, ref_cov) < 1e-5
+    # transpose: dL/dmeans3D -> dL/dx in engine rows
+    gm = torch.randn(K, 3)
+    gx = torch.zeros(Np, 3, device=cuda_dev)
+    ops.gaussians_to_particles(dev(g["rowptr"]), dev(g["col"]), dev(g["w"]), dev(slot.int()), dev(gm), size, gx)
+    ref_gx = torch.sparse.mm(B.t(), gm.double()) / size.double()
+    assert rel_err(gx.cpu()[slot], ref_gx) < 1e-5
