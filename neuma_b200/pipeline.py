@@ -77,6 +77,7 @@ class FusedFrame:
         self._center_h = [float(v) for v in self.center.cpu().tolist()]      # kernel parameters
         self._size_h = [float(v) for v in self.size.cpu().tolist()]
         self.use_graphs = use_graphs
+        self._side = torch.cuda.Stream(device)
         self._g_fwd = self._g_bwd = None
         self._ctx = ops._ctx(self.x)
         # per-substep packed grids ((mv, m) -> (v, m) in place), adjoint scatter targets, boxes
@@ -88,13 +89,20 @@ class FusedFrame:
     # ------------------------------------------------------------------ sim
     def _sim_forward(self) -> None:
         c = self.c
+        main = torch.cuda.current_stream(self.dev)
         for s in range(self.S):
-            ctx = self._ctx
+            # the box clear of this substep's grid slot runs on a side branch next to the elasticity
+            # kernel (both only need the previous substep's G2P): one kernel boundary less on the path
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                ops.mpm_box_clear(c, self.box[s], self.grid[s], None, self.box[s + 1])
             ops.constitutive_fwd_staged(self.kind_e, self.F[s], self.We_st, 0.0, self.stress[s])
-            ops.mpm_rollout_fwd(c, self.x[s], self.v[s], self.C[s], self.F[s], self.stress[s], self.vol, self.rho,
-                                self.clip, self.enabled,
-                                (self.x[s + 1], self.v[s + 1], self.C[s + 1], self.Ftrial[s]),
-                                self.grid[s], self.adj[s], self.box[s], self.box[s + 1])
+            main.wait_stream(self._side)
+            ops.mpm_p2g_to(c, self.x[s], self.v[s], self.C[s], self.stress[s], self.vol, self.rho, self.enabled,
+                           self.grid[s])
+            ops.mpm_grid_op_box(c, self.box[s], self.grid[s], self.adj[s])
+            ops.mpm_g2p_from(c, self.x[s], self.F[s], self.clip, self.enabled, self.grid[s],
+                             (self.x[s + 1], self.v[s + 1], self.C[s + 1], self.Ftrial[s]), self.box[s + 1])
             ops.constitutive_fwd_staged(ops.KIND_PLASTIC, self.Ftrial[s], self.Wp_st, self.alpha, self.F[s + 1])
 
     def _sim_backward(self) -> None:
