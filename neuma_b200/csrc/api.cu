@@ -28,6 +28,15 @@ int neuma_ensure_scratch(neuma_ctx* ctx, size_t bytes) {
   return 0;
 }
 
+bool neuma_pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("NEUMA_PDL");
+    v = (e && e[0] == '1') ? 1 : 0;  // off by default: measured -1.7 % forward, +3 % backward (profiles/r01s)
+  }
+  return v != 0;
+}
+
 int neuma_ensure_wstage(neuma_ctx* ctx, size_t bytes) {
   if (bytes <= ctx->wstage_bytes) return 0;
   if (ctx->wstage) cudaFree(ctx->wstage);

@@ -54,6 +54,43 @@ static inline int neuma_fail_msg(neuma_ctx* ctx, const char* what) {
     (ctx)->launches++;                                           \
   } while (0)
 
+// ---- programmatic dependent launch (griddepcontrol, sm_90+) -----------------------------
+// The rollout is a chain of ~260 short dependent kernels per frame.  Kernels launched with
+// neuma_launch() carry the programmatic-stream-serialization attribute: the next kernel of
+// the stream is scheduled as soon as every CTA of this one has started (launch_dependents at
+// the top), runs its prologue (barrier init, TMEM allocation, index math) while this one
+// drains, and blocks in pdl_wait() until this grid has completed and its writes are visible.
+// Semantics are those of ordinary stream order.  OFF unless NEUMA_PDL=1: on the B200 it bought
+// 1.7 % on the forward graph and cost 3 % on the backward one (early-resident dependents compete
+// with the persistent constitutive CTAs), see profiles/r01s_pdl_ab.txt.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue() {
+  pdl_launch_dependents();
+  pdl_wait();
+}
+#endif
+bool neuma_pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t neuma_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = neuma_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 int neuma_ensure_grid(neuma_ctx* ctx, size_t nodes);
 int neuma_ensure_scratch(neuma_ctx* ctx, size_t bytes);
 int neuma_ensure_wstage(neuma_ctx* ctx, size_t bytes);

@@ -387,6 +387,7 @@ __device__ __forceinline__ uint32_t block_setup(Bars* bars, uint32_t* tmem_slot,
                                                 const uint8_t* __restrict__ staged, uint32_t w_bytes,
                                                 uint32_t tmem_cols) {
   const int warp = threadIdx.x >> 5;
+  pdl_launch_dependents();
   if (threadIdx.x == 0) {
     umma::mbar_init(umma::smem_u32(&bars->w), 1);
 #pragma unroll
@@ -401,6 +402,8 @@ __device__ __forceinline__ uint32_t block_setup(Bars* bars, uint32_t* tmem_slot,
   umma::fence_before_sync();
   __syncthreads();
   umma::fence_after_sync();
+  // everything above overlapped the previous kernel's tail; from here on we read its outputs
+  pdl_wait();
   if (threadIdx.x == 0) {
     const uint32_t bar = umma::smem_u32(&bars->w);
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(w_bytes) : "memory");
@@ -1032,8 +1035,8 @@ int neuma_constitutive_fwd_staged(neuma_ctx* ctx, int kind, int n, int hidden, c
   if (int r = set_attrs(ctx)) return r;
   const int tiles = (n + TP - 1) / TP;
   const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
-  constitutive_fwd_kernel<<<grid, FWD_THREADS, FWD_SMEM, (cudaStream_t)stream>>>(
-      kind, n, F, (const uint8_t*)staged, alpha, out);
+  NEUMA_CUDA(ctx, neuma_launch(constitutive_fwd_kernel, dim3(grid), dim3(FWD_THREADS), FWD_SMEM, (cudaStream_t)stream,
+                               kind, n, F, (const uint8_t*)staged, alpha, out));
   NEUMA_LAUNCH_CHECK(ctx, "constitutive_fwd_kernel");
   return 0;
 }
@@ -1071,8 +1074,9 @@ int neuma_constitutive_bwd_partials(neuma_ctx* ctx, int kind, int n, int hidden,
   if (int r = set_attrs(ctx)) return r;
   const int tiles = (n + TP - 1) / TP;
   const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
-  constitutive_bwd_kernel<true><<<grid, BWD_THREADS, BWD_SMEM, (cudaStream_t)stream>>>(
-      kind, n, F, (const uint8_t*)staged, alpha, gout, gF, nullptr, nullptr, nullptr, gWpart, accumulate_gF);
+  NEUMA_CUDA(ctx, neuma_launch(constitutive_bwd_kernel<true>, dim3(grid), dim3(BWD_THREADS), BWD_SMEM,
+                               (cudaStream_t)stream, kind, n, F, (const uint8_t*)staged, alpha, gout, gF,
+                               (float*)nullptr, (float*)nullptr, (float*)nullptr, gWpart, accumulate_gF));
   NEUMA_LAUNCH_CHECK(ctx, "constitutive_bwd_kernel");
   return 0;
 }

@@ -117,6 +117,7 @@ __device__ __forceinline__ size_t box_node(const neuma_mpm_const& c, const BoxIt
 __global__ void __launch_bounds__(256)
 box_clear_kernel(neuma_mpm_const c, const int32_t* __restrict__ box, float4* __restrict__ g0,
                  float4* __restrict__ g1, int32_t* __restrict__ box_reset) {
+  pdl_prologue();
   if (box_reset && blockIdx.x == 0 && threadIdx.x < 8)
     box_reset[threadIdx.x] = threadIdx.x < 3 ? INT_MAX : (threadIdx.x < 6 ? INT_MIN : 0);
   const BoxIter it = box_iter(c, load_box(box));
@@ -135,6 +136,7 @@ p2g_to_kernel(neuma_mpm_const c, int n, const float* __restrict__ x, const float
               const float* __restrict__ C, const float* __restrict__ stress,
               const float* __restrict__ vol, const float* __restrict__ rho,
               const int* __restrict__ enabled, float4* __restrict__ grid) {
+  pdl_prologue();
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
   if (enabled[p] == 0) return;
@@ -148,6 +150,7 @@ constexpr uint32_t NEG_ZERO = 0x80000000u;
 __global__ void __launch_bounds__(256)
 grid_op_box_kernel(neuma_mpm_const c, const int32_t* __restrict__ box, float4* __restrict__ grid,
                    float4* __restrict__ adj) {
+  pdl_prologue();
   const BoxIter it = box_iter(c, load_box(box));
   const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < it.total;
@@ -175,6 +178,7 @@ g2p_from_kernel(neuma_mpm_const c, int n, const float* __restrict__ x, const flo
                 const float* __restrict__ clip, const int* __restrict__ enabled,
                 const float4* __restrict__ grid, float* __restrict__ x2, float* __restrict__ v2,
                 float* __restrict__ C2, float* __restrict__ F2, int32_t* __restrict__ box_next) {
+  pdl_prologue();
   __shared__ int sbox[6];
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   const bool active = p < n && enabled[p] != 0;
@@ -245,6 +249,7 @@ bwd_scatter_adj_kernel(neuma_mpm_const c, int n, const float* __restrict__ x,
                        const float* __restrict__ gx2, const float* __restrict__ gv2,
                        const float* __restrict__ gC2, const float* __restrict__ gF2,
                        float4* __restrict__ gadj) {
+  pdl_prologue();
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
   if (enabled[p] == 0) return;
@@ -277,6 +282,7 @@ bwd_scatter_adj_kernel(neuma_mpm_const c, int n, const float* __restrict__ x,
 __global__ void __launch_bounds__(256)
 bwd_node_kernel(neuma_mpm_const c, const int32_t* __restrict__ box,
                 const float4* __restrict__ grid, float4* __restrict__ adj) {
+  pdl_prologue();
   const BoxIter it = box_iter(c, load_box(box));
   const float gdt[3] = {c.gravity[0] * c.dt, c.gravity[1] * c.dt, c.gravity[2] * c.dt};
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < it.total;
@@ -314,6 +320,7 @@ bwd_gather_v_kernel(neuma_mpm_const c, int n, const float* __restrict__ x,
                     const float4* __restrict__ grid, const float4* __restrict__ gadj,
                     float* __restrict__ gx, float* __restrict__ gv, float* __restrict__ gC,
                     float* __restrict__ gF, float* __restrict__ gstress) {
+  pdl_prologue();
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
   if (enabled[p] == 0) {
@@ -515,8 +522,8 @@ int neuma_mpm_box_from_x(neuma_ctx* ctx, const neuma_mpm_const* c, int n, const 
 int neuma_mpm_box_clear(neuma_ctx* ctx, const neuma_mpm_const* c, const int32_t* box, float* grid0,
                         float* grid1, int32_t* box_reset, void* stream) {
   if (int r = check_slab(ctx, c)) return r;
-  box_clear_kernel<<<node_pass_blocks(ctx), 256, 0, (cudaStream_t)stream>>>(
-      *c, box, (float4*)grid0, (float4*)grid1, box_reset);
+  NEUMA_CUDA(ctx, neuma_launch(box_clear_kernel, dim3(node_pass_blocks(ctx)), dim3(256), 0, (cudaStream_t)stream,
+                               *c, box, (float4*)grid0, (float4*)grid1, box_reset));
   NEUMA_LAUNCH_CHECK(ctx, "box_clear_kernel");
   return 0;
 }
@@ -527,8 +534,8 @@ int neuma_mpm_p2g_to(neuma_ctx* ctx, const neuma_mpm_const* c, int n, const floa
   if (int r = check_slab(ctx, c)) return r;
   if (n <= 0) return 0;
   const int pb = pblock(256);
-  p2g_to_kernel<<<(n + pb - 1) / pb, pb, 0, (cudaStream_t)stream>>>(*c, n, x, v, C, stress, vol, rho,
-                                                                    enabled, (float4*)grid);
+  NEUMA_CUDA(ctx, neuma_launch(p2g_to_kernel, dim3((n + pb - 1) / pb), dim3(pb), 0, (cudaStream_t)stream, *c, n, x,
+                               v, C, stress, vol, rho, enabled, (float4*)grid));
   NEUMA_LAUNCH_CHECK(ctx, "p2g_to_kernel");
   return 0;
 }
@@ -536,8 +543,8 @@ int neuma_mpm_p2g_to(neuma_ctx* ctx, const neuma_mpm_const* c, int n, const floa
 int neuma_mpm_grid_op_box(neuma_ctx* ctx, const neuma_mpm_const* c, const int32_t* box, float* grid,
                           float* adj_to_clear, void* stream) {
   if (int r = check_slab(ctx, c)) return r;
-  grid_op_box_kernel<<<node_pass_blocks(ctx), 256, 0, (cudaStream_t)stream>>>(
-      *c, box, (float4*)grid, (float4*)adj_to_clear);
+  NEUMA_CUDA(ctx, neuma_launch(grid_op_box_kernel, dim3(node_pass_blocks(ctx)), dim3(256), 0, (cudaStream_t)stream,
+                               *c, box, (float4*)grid, (float4*)adj_to_clear));
   NEUMA_LAUNCH_CHECK(ctx, "grid_op_box_kernel");
   return 0;
 }
@@ -550,14 +557,9 @@ int neuma_mpm_g2p_from(neuma_ctx* ctx, const neuma_mpm_const* c, int n, const fl
   if (n <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   const int pb = pblock(256);
-  if (box_next)
-    g2p_from_kernel<true><<<(n + pb - 1) / pb, pb, 0, st>>>(*c, n, x, F, clip_bound, enabled,
-                                                           (const float4*)grid_v, x2, v2, C2, F2,
-                                                           box_next);
-  else
-    g2p_from_kernel<false><<<(n + pb - 1) / pb, pb, 0, st>>>(*c, n, x, F, clip_bound, enabled,
-                                                            (const float4*)grid_v, x2, v2, C2, F2,
-                                                            nullptr);
+  NEUMA_CUDA(ctx, neuma_launch(box_next ? g2p_from_kernel<true> : g2p_from_kernel<false>, dim3((n + pb - 1) / pb),
+                               dim3(pb), 0, st, *c, n, x, F, clip_bound, enabled, (const float4*)grid_v, x2, v2, C2,
+                               F2, box_next));
   NEUMA_LAUNCH_CHECK(ctx, "g2p_from_kernel");
   return 0;
 }
@@ -585,8 +587,8 @@ int neuma_mpm_bwd_scatter(neuma_ctx* ctx, const neuma_mpm_const* c, int n, const
   if (!v2 || !gx2 || !gv2 || !gC2 || !gF2 || !adj)
     return neuma_fail_msg(ctx, "neuma_mpm_bwd_scatter: NULL argument");
   const int pb = pblock(256);
-  bwd_scatter_adj_kernel<<<(n + pb - 1) / pb, pb, 0, (cudaStream_t)stream>>>(
-      *c, n, x, F, clip_bound, enabled, v2, gx2, gv2, gC2, gF2, (float4*)adj);
+  NEUMA_CUDA(ctx, neuma_launch(bwd_scatter_adj_kernel, dim3((n + pb - 1) / pb), dim3(pb), 0, (cudaStream_t)stream,
+                               *c, n, x, F, clip_bound, enabled, v2, gx2, gv2, gC2, gF2, (float4*)adj));
   NEUMA_LAUNCH_CHECK(ctx, "bwd_scatter_adj_kernel");
   return 0;
 }
@@ -603,17 +605,13 @@ int neuma_mpm_bwd_node_gather(neuma_ctx* ctx, const neuma_mpm_const* c, int n, c
   if (!v2 || !gx2 || !gv2 || !gC2 || !gF2 || !grid_v || !adj || !box)
     return neuma_fail_msg(ctx, "neuma_mpm_bwd_node_gather: NULL argument");
   cudaStream_t st = (cudaStream_t)stream;
-  bwd_node_kernel<<<node_pass_blocks(ctx), 256, 0, st>>>(*c, box, (const float4*)grid_v, (float4*)adj);
+  NEUMA_CUDA(ctx, neuma_launch(bwd_node_kernel, dim3(node_pass_blocks(ctx)), dim3(256), 0, st, *c, box,
+                               (const float4*)grid_v, (float4*)adj));
   NEUMA_LAUNCH_CHECK(ctx, "bwd_node_kernel");
   const int pb = pblock(128) > 128 ? 128 : pblock(128);
-  if (C2)
-    bwd_gather_v_kernel<true><<<(n + pb - 1) / pb, pb, 0, st>>>(
-        *c, n, x, v, C, F, stress, vol, rho, clip_bound, enabled, v2, C2, gx2, gv2, gC2, gF2,
-        (const float4*)grid_v, (const float4*)adj, gx, gv, gC, gF, gstress);
-  else
-    bwd_gather_v_kernel<false><<<(n + pb - 1) / pb, pb, 0, st>>>(
-        *c, n, x, v, C, F, stress, vol, rho, clip_bound, enabled, v2, C2, gx2, gv2, gC2, gF2,
-        (const float4*)grid_v, (const float4*)adj, gx, gv, gC, gF, gstress);
+  NEUMA_CUDA(ctx, neuma_launch(C2 ? bwd_gather_v_kernel<true> : bwd_gather_v_kernel<false>, dim3((n + pb - 1) / pb),
+                               dim3(pb), 0, st, *c, n, x, v, C, F, stress, vol, rho, clip_bound, enabled, v2, C2, gx2,
+                               gv2, gC2, gF2, (const float4*)grid_v, (const float4*)adj, gx, gv, gC, gF, gstress));
   NEUMA_LAUNCH_CHECK(ctx, "bwd_gather_v_kernel");
   return 0;
 }
