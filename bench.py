@@ -205,11 +205,19 @@ def run_gpu(args):
     hgw = [torch.empty_like(w, device="cpu").pin_memory() for w in eng.gWe + eng.gWp]
     dgt = torch.empty_like(gt)
 
+    copy_stream = torch.cuda.Stream(dev)
+    gt_ready = torch.cuda.Event()
+
     def step_e2e():
+        # the GT image is not needed before the loss: its H2D copy runs on a copy stream under the
+        # simulation (finetune.py:386 does it synchronously per frame); the state copy cannot overlap
         eng.load_state(hx, hv, hC, hF)
-        dgt.copy_(hgt, non_blocking=True)
+        copy_stream.wait_stream(torch.cuda.current_stream(dev))   # after the state copy: it owns the link first
+        with torch.cuda.stream(copy_stream):
+            dgt.copy_(hgt, non_blocking=True)
+            gt_ready.record(copy_stream)
         eng.zero_weight_grads()
-        loss_, _ = eng.frame_fwd_bwd(dgt, de_x_prev, k_prev)
+        loss_, _ = eng.frame_fwd_bwd(dgt, de_x_prev, k_prev, gt_ready=gt_ready)
         hloss.copy_(loss_, non_blocking=True)
         for h_, w_ in zip(hgw, eng.gWe + eng.gWp):
             h_.copy_(w_, non_blocking=True)

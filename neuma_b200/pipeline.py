@@ -66,7 +66,6 @@ class FusedFrame:
                    torch.zeros(n, 3, 3, **f)] for _ in range(2)]
         self.gstress = torch.empty(n, 3, 3, **f)
         self.gFtrial = torch.empty(n, 3, 3, **f)
-        self.gF_e = torch.empty(n, 3, 3, **f)
         self.gWe = [torch.zeros_like(w) for w in self.We]
         self.gWp = [torch.zeros_like(w) for w in self.Wp]
         # per-CTA partial sums of the weight gradients (no atomics in the 2 x S backward calls)
@@ -258,12 +257,16 @@ class FusedFrame:
         return g3
 
     # ------------------------------------------------------------------ one frame, forward + backward
-    def frame_fwd_bwd(self, gt: torch.Tensor, de_x_prev, k_prev, g_state_next=None, want_g0: bool = True):
+    def frame_fwd_bwd(self, gt: torch.Tensor, de_x_prev, k_prev, g_state_next=None, want_g0: bool = True,
+                      gt_ready: Optional[torch.cuda.Event] = None):
         """S substeps + render + l2 loss, then the full reverse pass.  Returns
         (loss, dL/d(state at frame start)).  de_x_prev / k_prev / g_state_next / the result are in
-        the caller's particle order."""
+        the caller's particle order.  gt_ready: event after which `gt` is valid (a host->device copy
+        of the ground-truth image issued on another stream overlaps the simulation)."""
         self.sim_forward(return_state=False)
         image, means3D = self.render_forward(de_x_prev, k_prev)
+        if gt_ready is not None:
+            torch.cuda.current_stream(self.dev).wait_event(gt_ready)
         diff = image - gt
         loss = (diff * diff).mean()
         dL_dimage = diff * (2.0 / diff.numel())

@@ -195,7 +195,6 @@ class SlabRollout:
         self.g = [[torch.zeros(n, 3, **f), torch.zeros(n, 3, **f), torch.zeros(n, 3, 3, **f),
                    torch.zeros(n, 3, 3, **f)] for _ in range(2)]
         self.gstress = torch.empty(n, 3, 3, **f); self.gFtrial = torch.empty(n, 3, 3, **f)
-        self.gF_e = torch.empty(n, 3, 3, **f)
         ops.mpm_box_from_x(self.c, self.x[0], self.enabled, self.box[0])
         self._scratch = {}
 
