@@ -390,7 +390,8 @@ def run_slab(args):
     spec = S.WORKLOADS[name]
     p = S.make_particles(spec, 42)
     w = load_weights()
-    sim = SlabRollout(spec["G"], spec["dt"], w["elastic"], w["plastic"], w["alpha"], args.substeps, dev)
+    sim = SlabRollout(spec["G"], spec["dt"], w["elastic"], w["plastic"], w["alpha"], args.substeps, dev,
+                      halo=args.halo)
     sim.distribute(p["x"], p["v"], p["C"], p["F"], p["vol"], p["rho"], p["clip"], p["enabled"])
     gen = torch.Generator(device="cpu").manual_seed(7)
     g = [torch.randn(sim.n, 3, generator=gen).to(dev), None, None, torch.randn(sim.n, 3, 3, generator=gen).to(dev)]
@@ -432,7 +433,8 @@ def run_slab(args):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": name, "particles": spec["n"], "grid": spec["G"], "substeps_per_frame": args.substeps,
                        "dt": spec["dt"], "parallelism": f"z-slab x{world}", "slab_bounds": sim.plan.b,
-                       "particles_per_rank": counts, "halo_k": sim.k,
+                       "particles_per_rank": counts, "halo_k": sim.k, "halo": args.halo if world > 1 else "none",
+                       "cuda_graphs": sim.use_graphs,
                        "l2": "working set (particles + per-substep grids) far larger than L2"},
             "substeps_per_s": 1000.0 / ms * args.substeps, "halo_bytes_per_frame": halo_bytes, "drift_ok": ok}))
     if world > 1:
@@ -525,6 +527,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default=WORKLOAD, choices=["bouncyball-50k-64", "jellyduck-100k-128", "claycat-200k-128"],
                     help="parity-test configs of BASELINE.json for the record; the headline is jellyduck-100k-128")
+    ap.add_argument("--halo", default="peer", choices=["peer", "nccl"],
+                    help="--slab halo exchange: NVLink peer-memory pushes inside CUDA graphs, or NCCL send/recv (eager)")
     ap.add_argument("--slab", action="store_true",
                     help="BASELINE config 5: 1M particles / 256^3 MPM fwd+bwd, Z-slab sharded over the ranks")
     args = ap.parse_args()

@@ -137,15 +137,61 @@ def exchange_sum(planes: torch.Tensor, plan: SlabPlan, rank: int, group=None, ad
             add(view, buf)
 
 
+class PeerHalo:
+    """The summing halo exchange over NVLink PEER MEMORY instead of NCCL send/recv: every rank owns a
+    mailbox in torch symmetric memory; a rank PUSHES its shared planes straight into the neighbour's
+    mailbox (cudaMemcpyAsync to a peer pointer over NVLink / NVSwitch), raises the neighbour's DATA
+    flag, waits for its own, adds the mailbox into its grid (neuma_mpm_planes_add) and raises ACK so
+    the neighbour may push again.  Everything is stream work -- copies, flag kernels, the add -- so
+    the whole S-substep rollout INCLUDING its 2 S exchanges is captured into one CUDA graph per
+    direction (NCCL point-to-point under capture hangs on this stack; measured)."""
+    DATA, ACK = 1, 2
+
+    def __init__(self, G: int, k: int, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = dist.group.WORLD if group is None else group
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self.npl, self.G = 2 + 2 * k, int(G)
+        self.shape = (2, self.npl, self.G, self.G, 4)          # [from lower | from upper][planes][y][x][4]
+        self.box = symm_mem.empty(self.shape, dtype=torch.float32, device=device)
+        self.hdl = symm_mem.rendezvous(self.box, self.group)
+        self.peer = {nb: self.hdl.get_buffer(nb, self.shape, torch.float32, 0)
+                     for nb in (self.rank - 1, self.rank + 1) if 0 <= nb < self.world}
+        for nb in self.peer:                                    # every mailbox starts out free
+            self.hdl.put_signal(nb, self.ACK)
+        self.hdl.barrier(0)
+
+    def exchange(self, planes: torch.Tensor, plan: SlabPlan, add) -> None:
+        z_off, _ = plan.local_planes(self.rank)
+        views = {}
+        for up in (False, True):
+            ov = plan.overlap(self.rank, up)
+            if ov is None:
+                continue
+            nb = self.rank + 1 if up else self.rank - 1
+            view = planes[ov[0] - z_off: ov[0] - z_off + ov[1]]
+            views[nb] = (view, up)
+            self.hdl.wait_signal(nb, self.ACK)                  # the neighbour consumed my previous push
+            # I am the neighbour's LOWER side when it sits above me
+            self.peer[nb][0 if up else 1, : ov[1]].copy_(view)
+            self.hdl.put_signal(nb, self.DATA)
+        for nb, (view, up) in views.items():
+            self.hdl.wait_signal(nb, self.DATA)
+            add(view, self.box[1 if up else 0, : view.shape[0]])
+            self.hdl.put_signal(nb, self.ACK)
+
+
 class SlabRollout:
     """S-substep differentiable rollout (elasticity -> MPM -> plasticity) of this rank's slab.
 
     Same kernels and per-substep saved grids as neuma_b200.pipeline.FusedFrame, plus the halo
-    exchange.  Launches are eager (the NCCL send/recv pairs sit between the kernels)."""
+    exchange: halo="peer" (default) pushes the shared planes through NVLink peer memory
+    (PeerHalo) and replays forward / backward as CUDA graphs; halo="nccl" uses send/recv pairs
+    with eager launches."""
 
     def __init__(self, G: int, dt: float, We, Wp, alpha: float, substeps: int, device, group=None,
                  bound: int = 1, gravity=(0.0, -9.8, 0.0), eps: float = 6e-7, bc: str = "noslip",
-                 halo_k: int = 1, elastic_kind: int = 0):
+                 halo_k: int = 1, elastic_kind: int = 0, halo: str = "peer", use_graphs: Optional[bool] = None):
         from . import ops
         self.ops = ops
         self.G, self.dt, self.S, self.dev, self.group = int(G), float(dt), int(substeps), device, group
@@ -165,6 +211,14 @@ class SlabRollout:
         self.plan: Optional[SlabPlan] = None
         self.n = 0
         self._scratch: dict = {}
+        if halo not in ("peer", "nccl"):
+            raise ValueError("halo must be 'peer' or 'nccl'")
+        self._peer = PeerHalo(G, self.k, device, group) if (halo == "peer" and self.world > 1) else None
+        # graphs need capturable communication: peer memory yes, NCCL send/recv no
+        self.use_graphs = (halo == "peer" or self.world == 1) if use_graphs is None else bool(use_graphs)
+        if self.use_graphs and self._peer is None and self.world > 1:
+            raise ValueError("CUDA graphs need halo='peer' (NCCL send/recv is not capturable here)")
+        self._graphs: dict = {}
 
     # ------------------------------------------------------------------ distribution
     def distribute(self, x, v, C, F, vol, rho, clip, enabled) -> None:
@@ -197,6 +251,7 @@ class SlabRollout:
         self.gstress = torch.empty(n, 3, 3, **f); self.gFtrial = torch.empty(n, 3, 3, **f)
         ops.mpm_box_from_x(self.c, self.x[0], self.enabled, self.box[0])
         self._scratch = {}
+        self._graphs = {}                              # buffers were re-allocated: captured graphs are stale
 
     def _overlap_views(self, planes: torch.Tensor) -> List[torch.Tensor]:
         z_off, _ = self.plan.local_planes(self.rank)
@@ -208,10 +263,45 @@ class SlabRollout:
         return out
 
     def _exchange(self, planes: torch.Tensor) -> None:
-        exchange_sum(planes, self.plan, self.rank, self.group, add=self.ops.mpm_planes_add, scratch=self._scratch)
+        if self.world == 1:
+            return
+        if self._peer is not None:
+            self._peer.exchange(planes, self.plan, self.ops.mpm_planes_add)
+        else:
+            exchange_sum(planes, self.plan, self.rank, self.group, add=self.ops.mpm_planes_add, scratch=self._scratch)
+
+    def _run(self, key: str, body) -> None:
+        """eager, or captured once into a CUDA graph (kernels, peer copies and flag kernels) and
+        replayed: at 8 ranks a slab's kernels are short enough to be launch-bound."""
+        if not self.use_graphs:
+            body()
+            return
+        g = self._graphs.get(key)
+        if g is None:
+            if key == "bwd":
+                keep = [t.clone() for t in self.g[0]]
+            body()                                   # warm-up on the current stream: workspaces, scratch
+            torch.cuda.synchronize(self.dev)
+            if key == "bwd":                         # the warm-up consumed the adjoint grids / upstream grads
+                self._forward_body()
+                for dst, src in zip(self.g[0], keep):
+                    dst.copy_(src)
+                for t in (self.gWe_part, self.gWp_part):
+                    t.zero_()
+                torch.cuda.synchronize(self.dev)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                body()
+            self._graphs[key] = g
+        g.replay()
 
     # ------------------------------------------------------------------ rollout
     def forward(self):
+        self._run("fwd", self._forward_body)
+        S = self.S
+        return self.x[S], self.v[S], self.C[S], self.F[S]
+
+    def _forward_body(self) -> None:
         ops, c = self.ops, self.c
         for s in range(self.S):
             ops.constitutive_fwd_staged(self.kind_e, self.F[s], self.We_st, 0.0, self.stress[s])
@@ -225,8 +315,6 @@ class SlabRollout:
             ops.mpm_g2p_from(c, self.x[s], self.F[s], self.clip, self.enabled, self.grid[s],
                              (self.x[s + 1], self.v[s + 1], self.C[s + 1], self.Ftrial[s]), self.box[s + 1])
             ops.constitutive_fwd_staged(ops.KIND_PLASTIC, self.Ftrial[s], self.Wp_st, self.alpha, self.F[s + 1])
-        S = self.S
-        return self.x[S], self.v[S], self.C[S], self.F[S]
 
     def backward(self, gx, gv, gC, gF):
         """dL/d(local state[S]) -> dL/d(local state[0]); gWe / gWp hold the ALL-REDUCED weight gradients."""
@@ -235,6 +323,20 @@ class SlabRollout:
             dst.zero_() if src is None else dst.copy_(src)
         for t in self.gWe + self.gWp:
             t.zero_()
+        self._run("bwd", self._backward_body)
+        ops.constitutive_reduce_partials(self.gWe_part, *self.gWe)
+        ops.constitutive_reduce_partials(self.gWp_part, *self.gWp)
+        if self.world > 1:
+            flat = torch.cat([t.reshape(-1) for t in self.gWe + self.gWp])
+            dist.all_reduce(flat, group=self.group)
+            o = 0
+            for t in self.gWe + self.gWp:
+                t.copy_(flat[o:o + t.numel()].view_as(t))
+                o += t.numel()
+        return self.g[self.S % 2]
+
+    def _backward_body(self) -> None:
+        ops, c = self.ops, self.c
         cur, nxt = 0, 1
         for s in reversed(range(self.S)):
             gx2, gv2, gC2, gF_next = self.g[cur]
@@ -253,16 +355,6 @@ class SlabRollout:
             ops.constitutive_bwd_partials(self.kind_e, self.F[s], self.We_st, 0.0, self.gstress, gFo,
                                           self.gWe_part, accumulate_gF=True)
             cur, nxt = nxt, cur
-        ops.constitutive_reduce_partials(self.gWe_part, *self.gWe)
-        ops.constitutive_reduce_partials(self.gWp_part, *self.gWp)
-        if self.world > 1:
-            flat = torch.cat([t.reshape(-1) for t in self.gWe + self.gWp])
-            dist.all_reduce(flat, group=self.group)
-            o = 0
-            for t in self.gWe + self.gWp:
-                t.copy_(flat[o:o + t.numel()].view_as(t))
-                o += t.numel()
-        return self.g[cur]
 
     # ------------------------------------------------------------------ ownership
     def drift_ok(self) -> bool:

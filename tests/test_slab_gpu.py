@@ -48,7 +48,7 @@ def _reference(dev, n, G, S, dt):
     return out, g0, [t.clone() for t in eng.gWe + eng.gWp]
 
 
-def _slab_run(rank, world, port, n, G, S, dt, q):
+def _slab_run(rank, world, port, n, G, S, dt, q, halo="peer"):
     from neuma_b200.slab import SlabRollout
     if world > 1:
         os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -59,7 +59,7 @@ def _slab_run(rank, world, port, n, G, S, dt, q):
     try:
         W, alpha = _weights()
         d, g = _problem(n, G)
-        sim = SlabRollout(G, dt, W["elastic"], W["plastic"], alpha, S, dev)
+        sim = SlabRollout(G, dt, W["elastic"], W["plastic"], alpha, S, dev, halo=halo)
         sim.distribute(d["x"], d["v"], d["C"], d["F"], d["vol"], d["rho"], d["clip"], d["enabled"])
         out = sim.forward()
         assert sim.drift_ok()
@@ -109,8 +109,10 @@ def test_slab_world1_matches_fused_frame(cuda_dev):
     _check(res, gW, ref)
 
 
-@pytest.mark.parametrize("world", [2, 4])
-def test_slab_multi_gpu_matches_single(cuda_dev, world):
+@pytest.mark.parametrize("world,halo", [(2, "peer"), (2, "nccl"), (4, "peer")])
+def test_slab_multi_gpu_matches_single(cuda_dev, world, halo):
+    """halo="peer": NVLink peer-memory pushes + flag kernels, whole rollout replayed as CUDA graphs;
+    halo="nccl": send/recv pairs, eager launches"""
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     n, G, S, dt = 40000, 64, 3, 2.5e-4
@@ -118,7 +120,7 @@ def test_slab_multi_gpu_matches_single(cuda_dev, world):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_slab_run, args=(r, world, port, n, G, S, dt, q)) for r in range(world)]
+    procs = [ctx.Process(target=_slab_run, args=(r, world, port, n, G, S, dt, q, halo)) for r in range(world)]
     for p in procs:
         p.start()
     got = [q.get(timeout=300) for _ in range(world)]
