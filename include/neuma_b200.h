@@ -195,6 +195,19 @@ int neuma_mpm_bwd_node_gather(neuma_ctx* ctx, const neuma_mpm_const* c, int n, c
 /* dst += src over `nodes` packed float4 nodes: the receiving side of the Z-slab halo exchange
  * (a slab's overlap planes are one contiguous block in the plane-major layout) */
 int neuma_mpm_planes_add(neuma_ctx* ctx, float* dst, const float* src, size_t nodes, void* stream);
+/* The summing halo exchange over NVLink PEER memory, two kernels per neighbour (no NCCL, CUDA-graph
+ * capturable): neuma_halo_push copies `nodes` float4 nodes into the neighbour's mailbox (a peer
+ * pointer) once the neighbour has acknowledged the previous exchange (my_ack_flag, written by the
+ * neighbour), then stores the exchange number into the neighbour's data flag;
+ * neuma_halo_add_ack waits for its own data flag, adds its mailbox into `dst` and acknowledges.
+ * Flags and my_seq / done counters are int32, zero-initialised once; flags carry monotonically
+ * increasing exchange numbers. */
+int neuma_halo_push(neuma_ctx* ctx, const float* src, float* peer_mailbox, size_t nodes,
+                    int32_t* peer_data_flag, const int32_t* my_ack_flag, int32_t* my_seq, int32_t* done,
+                    void* stream);
+int neuma_halo_add_ack(neuma_ctx* ctx, float* dst, const float* mailbox, size_t nodes,
+                       const int32_t* my_data_flag, int32_t* peer_ack_flag, int32_t* my_seq, int32_t* done,
+                       void* stream);
 /* permutation that puts the particles in cell (Morton) order of their stencil base:
  * perm[i] = index of the i-th particle in that order.  Not capturable (may grow the ctx
  * scratch). */

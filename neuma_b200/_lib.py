@@ -66,6 +66,8 @@ SIGNATURES = {
     "neuma_mpm_bwd_scatter": [_P, _CP, _I] + [_P] * 11,
     "neuma_mpm_bwd_node_gather": [_P, _CP, _I] + [_P] * 24,
     "neuma_mpm_planes_add": [_P, _P, _P, C.c_size_t, _P],
+    "neuma_halo_push": [_P, _P, _P, C.c_size_t, _P, _P, _P, _P, _P],
+    "neuma_halo_add_ack": [_P, _P, _P, C.c_size_t, _P, _P, _P, _P, _P],
     "neuma_mpm_cell_order": [_P, _CP, _I, _P, _P, _P],
     "neuma_gather_rows": [_P, _I, _I, _P, _P, _P, _P],
     "neuma_invert_perm": [_P, _I, _P, _P, _P],

@@ -483,6 +483,73 @@ planes_add_kernel(float4* __restrict__ dst, const float4* __restrict__ src, size
   }
 }
 
+// ---- halo exchange over NVLink peer memory, two kernels per neighbour --------------
+// Flags live in symmetric memory and carry monotonically increasing exchange numbers, so nothing
+// is ever reset and the kernels -- pointers only, no per-launch scalars -- replay from a CUDA graph.
+__device__ __forceinline__ int ld_acquire_sys(const int* p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(int* p, int v) {
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// push my shared planes into the neighbour's mailbox, then publish exchange number `seq` in ITS
+// data flag.  Waits first until the neighbour has acknowledged exchange seq-1 (mailbox free).
+__global__ void __launch_bounds__(256)
+halo_push_kernel(const float4* __restrict__ src, float4* __restrict__ peer_mailbox, size_t n,
+                 int* __restrict__ peer_data_flag, const int* __restrict__ my_ack_flag,
+                 int* __restrict__ my_seq, int* __restrict__ done) {
+  __shared__ int s_seq;
+  if (threadIdx.x == 0) {
+    const int seq = *reinterpret_cast<volatile int*>(my_seq) + 1;
+    while (ld_acquire_sys(my_ack_flag) < seq - 1) __nanosleep(64);
+    s_seq = seq;
+  }
+  __syncthreads();
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    peer_mailbox[i] = src[i];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // the block that finishes last has seen every other block's fence: it publishes
+    if (atomicAdd(done, 1) == (int)gridDim.x - 1) {
+      *done = 0;
+      *my_seq = s_seq;
+      __threadfence_system();
+      st_release_sys(peer_data_flag, s_seq);
+    }
+  }
+}
+// wait for the neighbour's push number seq, add the mailbox into my planes, acknowledge
+__global__ void __launch_bounds__(256)
+halo_add_ack_kernel(float4* __restrict__ dst, const float4* mailbox, size_t n,
+                    const int* __restrict__ my_data_flag, int* __restrict__ peer_ack_flag,
+                    int* __restrict__ my_seq, int* __restrict__ done) {
+  __shared__ int s_seq;
+  if (threadIdx.x == 0) {
+    const int seq = *reinterpret_cast<volatile int*>(my_seq) + 1;
+    while (ld_acquire_sys(my_data_flag) < seq) __nanosleep(64);
+    s_seq = seq;
+  }
+  __syncthreads();
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float4 a = dst[i];
+    const float4 b = __ldcv(mailbox + i);  // written by the peer GPU: never from a stale L1 line
+    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    dst[i] = a;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (atomicAdd(done, 1) == (int)gridDim.x - 1) {
+      *done = 0;
+      *my_seq = s_seq;
+      __threadfence_system();
+      st_release_sys(peer_ack_flag, s_seq);   // the mailbox may be overwritten
+    }
+  }
+}
+
 inline int node_pass_blocks(neuma_ctx* ctx) { return ctx->num_sms * 8; }
 
 // threads per block of the per-particle kernels (NEUMA_MPM_BLOCK overrides; tuned in profiles/)
@@ -638,6 +705,32 @@ int neuma_mpm_planes_add(neuma_ctx* ctx, float* dst, const float* src, size_t no
   if (b > (size_t)ctx->num_sms * 8) b = (size_t)ctx->num_sms * 8;
   planes_add_kernel<<<(int)b, 256, 0, (cudaStream_t)stream>>>((float4*)dst, (const float4*)src, nodes);
   NEUMA_LAUNCH_CHECK(ctx, "planes_add_kernel");
+  return 0;
+}
+
+int neuma_halo_push(neuma_ctx* ctx, const float* src, float* peer_mailbox, size_t nodes,
+                    int32_t* peer_data_flag, const int32_t* my_ack_flag, int32_t* my_seq, int32_t* done,
+                    void* stream) {
+  if (!ctx) return 2;
+  if (nodes == 0) return 0;
+  size_t b = (nodes + 255) / 256;
+  if (b > (size_t)ctx->num_sms * 2) b = (size_t)ctx->num_sms * 2;   // all blocks co-resident: they spin
+  halo_push_kernel<<<(int)b, 256, 0, (cudaStream_t)stream>>>((const float4*)src, (float4*)peer_mailbox, nodes,
+                                                              peer_data_flag, my_ack_flag, my_seq, done);
+  NEUMA_LAUNCH_CHECK(ctx, "halo_push_kernel");
+  return 0;
+}
+
+int neuma_halo_add_ack(neuma_ctx* ctx, float* dst, const float* mailbox, size_t nodes,
+                       const int32_t* my_data_flag, int32_t* peer_ack_flag, int32_t* my_seq, int32_t* done,
+                       void* stream) {
+  if (!ctx) return 2;
+  if (nodes == 0) return 0;
+  size_t b = (nodes + 255) / 256;
+  if (b > (size_t)ctx->num_sms * 2) b = (size_t)ctx->num_sms * 2;
+  halo_add_ack_kernel<<<(int)b, 256, 0, (cudaStream_t)stream>>>((float4*)dst, (const float4*)mailbox, nodes,
+                                                                 my_data_flag, peer_ack_flag, my_seq, done);
+  NEUMA_LAUNCH_CHECK(ctx, "halo_add_ack_kernel");
   return 0;
 }
 

@@ -449,3 +449,13 @@ def gaussians_to_particles(rowptr, col, w, slot, g_means3D, size, gx_out) -> Non
     K = rowptr.shape[0] - 1
     _ctx(g_means3D).call("neuma_gaussians_to_particles", K, ptr(rowptr), ptr(col), ptr(w), ptr(slot), ptr(g_means3D),
                          _host3(size, 1.0), ptr(gx_out), _stream(g_means3D))
+
+
+def halo_push(src, peer_mailbox, peer_data_flag, my_ack_flag, my_seq, done) -> None:
+    _ctx(src).call("neuma_halo_push", ptr(src), ptr(peer_mailbox), C.c_size_t(src.numel() // 4), ptr(peer_data_flag),
+                   ptr(my_ack_flag), ptr(my_seq), ptr(done), _stream(src))
+
+
+def halo_add_ack(dst, mailbox, my_data_flag, peer_ack_flag, my_seq, done) -> None:
+    _ctx(dst).call("neuma_halo_add_ack", ptr(dst), ptr(mailbox), C.c_size_t(dst.numel() // 4), ptr(my_data_flag),
+                   ptr(peer_ack_flag), ptr(my_seq), ptr(done), _stream(dst))

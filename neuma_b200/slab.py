@@ -138,47 +138,60 @@ def exchange_sum(planes: torch.Tensor, plan: SlabPlan, rank: int, group=None, ad
 
 
 class PeerHalo:
-    """The summing halo exchange over NVLink PEER MEMORY instead of NCCL send/recv: every rank owns a
-    mailbox in torch symmetric memory; a rank PUSHES its shared planes straight into the neighbour's
-    mailbox (cudaMemcpyAsync to a peer pointer over NVLink / NVSwitch), raises the neighbour's DATA
-    flag, waits for its own, adds the mailbox into its grid (neuma_mpm_planes_add) and raises ACK so
-    the neighbour may push again.  Everything is stream work -- copies, flag kernels, the add -- so
-    the whole S-substep rollout INCLUDING its 2 S exchanges is captured into one CUDA graph per
-    direction (NCCL point-to-point under capture hangs on this stack; measured)."""
-    DATA, ACK = 1, 2
+    """The summing halo exchange over NVLink PEER MEMORY instead of NCCL send/recv, two of our own
+    kernels per neighbour (csrc/mpm_rollout.cu):
+
+      neuma_halo_push     waits until the neighbour has acknowledged the previous exchange, copies my
+                          shared planes straight into the neighbour's mailbox (stores to a peer
+                          pointer over NVLink / NVSwitch) and publishes the exchange number in the
+                          neighbour's data flag (st.release.sys);
+      neuma_halo_add_ack  waits for my data flag (ld.acquire.sys), adds my mailbox into my grid and
+                          acknowledges in the neighbour's ack flag.
+
+    Mailboxes and flags live in torch symmetric memory (peer-mapped allocations); flags carry
+    monotonically increasing exchange numbers kept in device counters, so the kernels take only
+    pointers and the whole S-substep rollout INCLUDING its 2 S exchanges is captured into one CUDA
+    graph per direction (NCCL point-to-point under capture hangs on this stack; measured)."""
 
     def __init__(self, G: int, k: int, device, group=None):
         import torch.distributed._symmetric_memory as symm_mem
+        from . import ops
+        self.ops = ops
         self.group = dist.group.WORLD if group is None else group
         self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
         self.npl, self.G = 2 + 2 * k, int(G)
         self.shape = (2, self.npl, self.G, self.G, 4)          # [from lower | from upper][planes][y][x][4]
         self.box = symm_mem.empty(self.shape, dtype=torch.float32, device=device)
         self.hdl = symm_mem.rendezvous(self.box, self.group)
-        self.peer = {nb: self.hdl.get_buffer(nb, self.shape, torch.float32, 0)
-                     for nb in (self.rank - 1, self.rank + 1) if 0 <= nb < self.world}
-        for nb in self.peer:                                    # every mailbox starts out free
-            self.hdl.put_signal(nb, self.ACK)
-        self.hdl.barrier(0)
+        # flags written by the neighbours: [data from lower, data from upper, ack from lower, ack from upper]
+        self.flags = symm_mem.empty((8,), dtype=torch.int32, device=device)
+        self.fhdl = symm_mem.rendezvous(self.flags, self.group)
+        self.flags.zero_()
+        # local counters: [seq push->lower, seq push->upper, seq recv<-lower, seq recv<-upper, done x4]
+        self.cnt = torch.zeros(8, dtype=torch.int32, device=device)
+        torch.cuda.synchronize(device)
+        self.hdl.barrier(0)                                    # every rank's flags are zero before anyone pushes
+        nbs = [nb for nb in (self.rank - 1, self.rank + 1) if 0 <= nb < self.world]
+        self.peer_box = {nb: self.hdl.get_buffer(nb, self.shape, torch.float32, 0) for nb in nbs}
+        self.peer_flags = {nb: self.fhdl.get_buffer(nb, (8,), torch.int32, 0) for nb in nbs}
 
-    def exchange(self, planes: torch.Tensor, plan: SlabPlan, add) -> None:
-        z_off, _ = plan.local_planes(self.rank)
-        views = {}
+    def exchange(self, planes: torch.Tensor, plan: SlabPlan, add=None) -> None:
+        ops, z_off = self.ops, plan.local_planes(self.rank)[0]
+        todo = []
         for up in (False, True):
             ov = plan.overlap(self.rank, up)
             if ov is None:
                 continue
             nb = self.rank + 1 if up else self.rank - 1
             view = planes[ov[0] - z_off: ov[0] - z_off + ov[1]]
-            views[nb] = (view, up)
-            self.hdl.wait_signal(nb, self.ACK)                  # the neighbour consumed my previous push
-            # I am the neighbour's LOWER side when it sits above me
-            self.peer[nb][0 if up else 1, : ov[1]].copy_(view)
-            self.hdl.put_signal(nb, self.DATA)
-        for nb, (view, up) in views.items():
-            self.hdl.wait_signal(nb, self.DATA)
-            add(view, self.box[1 if up else 0, : view.shape[0]])
-            self.hdl.put_signal(nb, self.ACK)
+            u = 1 if up else 0
+            # seen from the neighbour ABOVE me I am its lower side (slot 0), and vice versa
+            ops.halo_push(view, self.peer_box[nb][1 - u, : ov[1]], self.peer_flags[nb][1 - u: 2 - u],
+                          self.flags[2 + u: 3 + u], self.cnt[u: u + 1], self.cnt[4 + u: 5 + u])
+            todo.append((nb, view, u, ov[1]))
+        for nb, view, u, npl in todo:
+            ops.halo_add_ack(view, self.box[u, :npl], self.flags[u: u + 1], self.peer_flags[nb][3 - u: 4 - u],
+                             self.cnt[2 + u: 3 + u], self.cnt[6 + u: 7 + u])
 
 
 class SlabRollout:
