@@ -257,25 +257,40 @@ class FusedFrame:
         return g3
 
     # ------------------------------------------------------------------ one frame, forward + backward
-    def frame_fwd_bwd(self, gt: torch.Tensor, de_x_prev, k_prev, g_state_next=None, want_g0: bool = True,
-                      gt_ready: Optional[torch.cuda.Event] = None):
-        """S substeps + render + l2 loss, then the full reverse pass.  Returns
-        (loss, dL/d(state at frame start)).  de_x_prev / k_prev / g_state_next / the result are in
-        the caller's particle order.  gt_ready: event after which `gt` is valid (a host->device copy
-        of the ground-truth image issued on another stream overlaps the simulation)."""
+    def final_state(self):
+        """(x, v, C, F) after the S substeps, caller order (the next frame's load_state input)."""
+        S = self.S
+        return tuple(self._to_caller(t[S]) for t in (self.x, self.v, self.C, self.F))
+
+    def frame_forward(self, gt: torch.Tensor, de_x_prev, k_prev, gt_ready: Optional[torch.cuda.Event] = None):
+        """S substeps + render + l2 loss (finetune.py:360-389).  Returns (loss, means3D): means3D is the
+        next frame's k_prev, (final_state()[0] - center) / size its de_x_prev (both enter detached,
+        tune/utils.py:441-446).  gt_ready: event after which `gt` is valid (a host->device copy of the
+        ground-truth image issued on another stream overlaps the simulation)."""
         self.sim_forward(return_state=False)
         image, means3D = self.render_forward(de_x_prev, k_prev)
         if gt_ready is not None:
             torch.cuda.current_stream(self.dev).wait_event(gt_ready)
         diff = image - gt
         loss = (diff * diff).mean()
-        dL_dimage = diff * (2.0 / diff.numel())
+        self._dL_dimage = diff * (2.0 / diff.numel())
+        return loss, means3D
+
+    def frame_backward(self, g_state_next=None, want_g0: bool = True):
+        """Reverse pass of the last frame_forward(): dL/dW_eff accumulate into gWe / gWp; returns
+        dL/d(state at frame start) in the caller's order.  g_state_next = dL/d(this frame's final
+        state) coming from the frames after it (caller order; entries may be None)."""
         for i, dst in enumerate(self.g[0]):                     # dL/d(state[S]) in the engine's order
             src = None if g_state_next is None else g_state_next[i]
             if src is None:
                 dst.zero_()
             else:
                 self._to_sorted(src, out=dst)
-        self.render_backward(dL_dimage, accumulate_into_state_grad=True)
-        return loss, self._run_backward(want_g0)
+        self.render_backward(self._dL_dimage, accumulate_into_state_grad=True)
+        return self._run_backward(want_g0)
 
+    def frame_fwd_bwd(self, gt: torch.Tensor, de_x_prev, k_prev, g_state_next=None, want_g0: bool = True,
+                      gt_ready: Optional[torch.cuda.Event] = None):
+        """frame_forward + frame_backward.  Returns (loss, dL/d(state at frame start))."""
+        loss, _ = self.frame_forward(gt, de_x_prev, k_prev, gt_ready)
+        return loss, self.frame_backward(g_state_next, want_g0)

@@ -71,3 +71,63 @@ def test_set_weights_restages(cuda_dev):
     c = eng.sim_forward()
     for x, y in zip(a, c):
         assert rel_err(x, y) < 1e-5
+
+
+def test_two_chained_frames_against_oracle(cuda_dev):
+    """finetune.py:360-414 over two rendered frames (S = 2 each) with one FusedFrame per frame:
+    loss, dL/d(state0) and dL/dW against torch autograd over the CPU oracle rollout (fp64)."""
+    from neuma_b200 import ops, synthetic as S
+    from neuma_b200.pipeline import FusedFrame
+    from oracle import mpm_oracle as MO, pipeline_oracle as PO, raster_oracle as RO
+    n, G, IM, Ssub = 1500, 32, 48, 2
+    spec, cc, d, W, alpha, settings, bind, gs, F0, gt, kxyz = _setup(cuda_dev, n=n, G=G, IM=IM)
+    center, size = torch.tensor([0.1, 0.0, 0.1]), torch.tensor([0.8, 0.9, 0.8])
+    gts = [gt, gt.flip(2)]
+    engs = [FusedFrame(n, cc, (d["vol"], d["rho"], d["clip"], d["enabled"]), W["elastic"], W["plastic"], alpha, Ssub,
+                       cuda_dev, bind=bind, gaussians=gs, settings=settings, center=center, size=size) for _ in range(2)]
+    # ---- forward through both frames, then backward in reverse order
+    state = (d["x"], d["v"], d["C"], F0)
+    de_prev = ((d["x"] - center.to(cuda_dev)) / size.to(cuda_dev)).clone()
+    k_prev = kxyz
+    losses = []
+    for e, g_ in zip(engs, gts):
+        e.load_state(*state)
+        e.zero_weight_grads()
+        loss, means3D = e.frame_forward(g_, de_prev, k_prev)
+        losses.append(loss)
+        state = e.final_state()
+        de_prev = ((state[0] - center.to(cuda_dev)) / size.to(cuda_dev)).clone()
+        k_prev = means3D.clone()
+    g1 = engs[1].frame_backward(None)
+    g0 = engs[0].frame_backward(g1)
+    total = float(losses[0] + losses[1])
+    gW = [a + b for a, b in zip(engs[0].gWe + engs[0].gWp, engs[1].gWe + engs[1].gWp)]
+    # ---- oracle
+    p = {k: v.cpu() for k, v in d.items()}
+    cam_s = RO.Settings(IM, IM, settings.tanfovx, settings.tanfovy, np.ones(3, np.float32),
+                        np.array(list(settings.viewmatrix), dtype=np.float32).reshape(4, 4),
+                        np.array(list(settings.projmatrix), dtype=np.float32).reshape(4, 4), 3,
+                        np.array(list(settings.campos), dtype=np.float32))
+    B = torch.sparse_csr_tensor(bind.rowptr.cpu().long(), bind.col.cpu().long(), bind.w.cpu().double(),
+                                (bind.n_kernels, n)).to_sparse_coo()
+    x0 = p["x"].double().requires_grad_(True)
+    v0 = p["v"].double().requires_grad_(True)
+    C0 = p["C"].double().requires_grad_(True)
+    F0d = F0.cpu().double().requires_grad_(True)
+    We = [w.cpu().double().requires_grad_(True) for w in W["elastic"]]
+    Wp = [w.cpu().double().requires_grad_(True) for w in W["plastic"]]
+    co = MO.MPMConst(num_grids=G, dt=1e-3, bound=1, eps=6e-7, bc="noslip")
+    # rollout_loss detaches the first de_x_prev from x0, exactly like the engine's caller above
+    oloss = PO.rollout_loss(co, x0, v0, C0, F0d, p["vol"], p["rho"], p["clip"], p["enabled"], We, None, Wp, None, alpha,
+                            B, kxyz.cpu(), gs["cov6"].cpu(), gs["opac"].cpu(), gs["shs"].cpu(), cam_s,
+                            [g_.cpu() for g_ in gts], Ssub, center, size)
+    og = torch.autograd.grad(oloss, [x0, v0, C0, F0d] + We + Wp)
+    assert abs(total - float(oloss.detach())) / float(oloss.detach()) < 1e-4
+    rel = lambda a, b: float((a.cpu().double() - b).norm() / (b.norm() + 1e-30))
+    errs = {name: rel(a, b) for a, b, name in zip(g0, og[:4], ["gx", "gv", "gC", "gF"])}
+    errs.update({f"gW{i}": rel(a, b) for i, (a, b) in enumerate(zip(gW, og[4:]))})
+    print("relative L2 errors vs the fp64 oracle:", {k: f"{v:.2e}" for k, v in errs.items()})
+    # fp32 device rollout (atomics, rasterizer alpha / transmittance threshold flips on a 48x48 image)
+    # against an fp64 oracle: same bound as the drop-in loop test (test_dropin_gpu.py) for the weights
+    assert max(v for k, v in errs.items() if k.startswith("gW")) < 2e-2, errs
+    assert max(v for k, v in errs.items() if not k.startswith("gW")) < 5e-2, errs
