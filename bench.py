@@ -350,6 +350,7 @@ def run_gpu(args):
                    "mode": "fwd+bwd (l2 loss -> dL/dW_eff, dL/dstate0)", "weights": os.path.basename(GOLD)[9:-4] + "_0300 + LoRA r16 merged",
                    "l2": "flushed between timed steps (256 MiB write)", "parallelism": f"replicas x{world}"},
         "p2g_hbm_gbs": p2g_gbs, "p2g_hbm_frac_of_measured_peak": p2g_gbs / hbm_peak,
+        "p2g_hbm_frac_of_nominal_8TBs": p2g_gbs / 8000.0,
         "mpm_fwd_substep_gbs": mpm_fwd_gbs,
         "kernel_us": {k: round(v, 2) for k, v in kt.items()},
         "frame_share_us": {k: round(v, 1) for k, v in per_frame_us.items()},
@@ -479,7 +480,13 @@ def cpu_sample(wl, x0, v0, C0, F0, reps: int = 1):
     ((img - wl["gt"]) ** 2).mean().backward()
     t_render = time.perf_counter() - t0
     ts = float(np.median(t_sub))
+    try:                                   # the reference's own Warp-CPU path, if it were installed
+        import warp  # noqa: F401
+        warp_ok = True
+    except Exception:
+        warp_ok = False
     return {"value": 1.0 / (S * ts + t_render), "unit": "frames/s", "cores": cores, "kind": "port",
+            "warp_importable": warp_ok,
             "sample": f"1 of {S} substeps fwd+bwd ({ts:.2f} s) + 1 render 800x800 fwd+bwd ({t_render:.2f} s), "
                       f"torch-CPU fp32 oracle, extrapolated to S={S}",
             "t_substep_s": ts, "t_render_s": t_render}
