@@ -61,6 +61,17 @@ def build_workload(substeps: int, seed: int = 42):
     return dict(spec=spec, p=p, g=g, cam=cam, gt=gt, w=load_weights(), S=substeps)
 
 
+def workload_config(wl, world: int) -> dict:
+    """The `config` object of the JSON line -- ONE function for both arms, so that the driver's
+    same_config check compares like with like."""
+    spec, g = wl["spec"], wl["g"]
+    return {"workload": WORKLOAD, "particles": spec["n"], "grid": spec["G"], "gaussians": g["K"],
+            "image": [IMAGE, IMAGE], "sh_degree": 3, "substeps_per_frame": wl["S"], "views": 1, "dt": spec["dt"],
+            "mode": "fwd+bwd (l2 loss -> dL/dW_eff, dL/dstate0)",
+            "weights": os.path.basename(GOLD)[9:-4] + "_0300 + LoRA r16 merged",
+            "l2": "flushed between timed steps (256 MiB write)", "parallelism": f"replicas x{world}"}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -242,6 +253,16 @@ def run_gpu(args):
     h2d = 4 * (hx.numel() + hv.numel() + hC.numel() + hF.numel() + hgt.numel())
     d2h = 4 * (1 + sum(h_.numel() for h_ in hgw))
 
+    # ---- BASELINE config 5 in the same invocation: the 1M / 256^3 rollout sharded by Z-slab over the
+    # ranks (strong scaling, one halo exchange per substep each way) -- the multi-GPU path of the
+    # hot path; the headline metric above stays the 100k frame (replicas: the render does not shard)
+    slab = None
+    if not args.no_slab:
+        del flush
+        torch.cuda.empty_cache()
+        slab = slab_measure(dev, world, rank, S, args.slab_steps, 3)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -259,25 +280,29 @@ def run_gpu(args):
     it, wm = 20, 3
     kt = {}
     sx = (eng.vol, eng.rho, eng.clip, eng.enabled)                 # statics in the engine's cell order
-    grid_s, adj_s, box_s = eng.grid[s0], eng.adj[s0], eng.box[s0]
+    ce = eng.c                                                     # the engine's const: compact grid slots
+    grid_s, adj_s, box_s = eng.grid[s0], eng.adj, eng.box[s0]
     box_tmp = torch.zeros(8, dtype=torch.int32, device=dev)
-    kt["grid_clear"] = event_time_us(lambda: ops.mpm_box_clear(cc, box_s, grid_s, None, box_tmp), it, wm, flush)
-    kt["p2g"] = event_time_us(lambda: ops.mpm_p2g_to(cc, xs, vs, Cs, st, sx[0], sx[1], sx[3], grid_s), it, wm, flush)
+    kt["grid_clear"] = event_time_us(lambda: ops.mpm_box_clear(ce, box_s, grid_s, None, box_tmp), it, wm, flush)
+    kt["p2g"] = event_time_us(lambda: ops.mpm_p2g_to(ce, xs, vs, Cs, st, sx[0], sx[1], sx[3], grid_s, box=box_s),
+                              it, wm, flush)
     def _clear_p2g():
-        ops.mpm_box_clear(cc, box_s, grid_s, None, box_tmp)
-        ops.mpm_p2g_to(cc, xs, vs, Cs, st, sx[0], sx[1], sx[3], grid_s)
+        ops.mpm_box_clear(ce, box_s, grid_s, None, box_tmp)
+        ops.mpm_p2g_to(ce, xs, vs, Cs, st, sx[0], sx[1], sx[3], grid_s, box=box_s)
     kt["clear+p2g"] = event_time_us(_clear_p2g, it, wm, flush)          # one timed region: the metric's t(clear + P2G)
 
     def _mpm_fwd():
-        ops.mpm_rollout_fwd(cc, xs, vs, Cs, Fs, st, *sx, outb, grid_s, adj_s, box_s, box_tmp)
+        ops.mpm_rollout_fwd(ce, xs, vs, Cs, Fs, st, *sx, outb, grid_s, None, box_s, box_tmp)
     kt["mpm_substep_fwd"] = event_time_us(_mpm_fwd, it, wm, flush)
-    kt["grid_op"] = event_time_us(lambda: ops.mpm_grid_op_box(cc, box_s, grid_s, adj_s), it, wm, flush)
-    kt["g2p"] = event_time_us(lambda: ops.mpm_g2p_from(cc, xs, Fs, sx[2], sx[3], grid_s, outb, box_tmp), it, wm, flush)
-    # leave a valid (v, m) grid and a zeroed adjoint target in the slot for the backward timing
-    ops.mpm_rollout_fwd(cc, xs, vs, Cs, Fs, st, *sx, outb, grid_s, adj_s, box_s, box_tmp)
+    kt["grid_op"] = event_time_us(lambda: ops.mpm_grid_op_box(ce, box_s, grid_s, None), it, wm, flush)
+    kt["g2p"] = event_time_us(lambda: ops.mpm_g2p_from(ce, xs, Fs, sx[2], sx[3], grid_s, outb, box_tmp, box=box_s),
+                              it, wm, flush)
+    # leave a valid (v, m) grid in the slot for the backward timing
+    ops.mpm_rollout_fwd(ce, xs, vs, Cs, Fs, st, *sx, outb, grid_s, None, box_s, box_tmp)
 
-    def _bwd():
-        ops.mpm_rollout_bwd(cc, xs, vs, Cs, Fs, st, *sx, outb[1], outb[2], *gout, grid_s, adj_s, box_s, *gouts5)
+    def _bwd():                       # as the engine runs it: clear the adjoint target over the box, then the 3 passes
+        ops.mpm_box_clear(ce, box_s, adj_s, None, None)
+        ops.mpm_rollout_bwd(ce, xs, vs, Cs, Fs, st, *sx, outb[1], outb[2], *gout, grid_s, adj_s, box_s, *gouts5)
     kt["mpm_substep_bwd"] = event_time_us(_bwd, it, wm, flush)
     kt["constitutive_fwd"] = event_time_us(lambda: ops.constitutive_fwd_staged(0, Fs, eng.We_st, 0.0, gF_), it, wm, flush)
     kt["constitutive_bwd"] = event_time_us(
@@ -344,11 +369,12 @@ def run_gpu(args):
         "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "particles": n, "grid": G, "gaussians": K, "image": [IMAGE, IMAGE],
-                   "sh_degree": 3, "substeps_per_frame": S, "views": 1, "dt": spec["dt"],
-                   "instances_rendered": int(nr),
-                   "mode": "fwd+bwd (l2 loss -> dL/dW_eff, dL/dstate0)", "weights": os.path.basename(GOLD)[9:-4] + "_0300 + LoRA r16 merged",
-                   "l2": "flushed between timed steps (256 MiB write)", "parallelism": f"replicas x{world}"},
+        "config": workload_config(wl, world),
+        "instances_rendered": int(nr),
+        "rollout_memory": {**eng.memory_bytes_per_substep(), "reference_per_particle": 528,
+                           "note": "bytes one substep keeps resident for the backward: compact particle state "
+                                   "(x,v,C,F,stress,F_trial) + one box-sized saved grid; the reference's "
+                                   "MPMCacheDiffSim pins 528 B/particle/substep (interface.py:108-123)"},
         "p2g_hbm_gbs": p2g_gbs, "p2g_hbm_frac_of_measured_peak": p2g_gbs / hbm_peak,
         "p2g_hbm_frac_of_nominal_8TBs": p2g_gbs / 8000.0,
         "mpm_fwd_substep_gbs": mpm_fwd_gbs,
@@ -363,6 +389,8 @@ def run_gpu(args):
         "clocks": clk.summary(),
         "loss": float(loss),
     }
+    if slab is not None:
+        line["slab"] = slab
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_sample(wl, x0.cpu(), v0.cpu(), C0.cpu(), F0.cpu())
     print(json.dumps(line))
@@ -371,14 +399,104 @@ def run_gpu(args):
 
 
 # --------------------------------------------------------------------------- Z-slab mode
-def run_slab(args):
-    """--slab: BASELINE config 5 (1M particles / 256^3, MPM fwd+bwd of one S-substep frame incl. the
-    constitutive nets), particles and grid sharded by Z-slab over the ranks, ONE summing NCCL halo
-    exchange per substep each way (neuma_b200/slab.py).  STRONG scaling: the cloud is fixed, ranks
-    split it.  Not the headline metric; prints its own JSON line."""
+SLAB_WORKLOAD = "block-1m-256"
+
+
+def slab_measure(dev, world: int, rank: int, substeps: int, steps: int, warmup: int, halo: str = "fused",
+                 variants: bool = True) -> dict:
+    """BASELINE config 5: 1M particles / 256^3, one S-substep frame of MPM + both constitutive nets,
+    forward + backward, particles and grid sharded by Z-slab over the ranks with ONE summing halo
+    exchange per substep each way (neuma_b200/slab.py).  STRONG scaling: the cloud is fixed.
+    Under torchrun rank 0 first times the same frame ALONE on its GPU (the N = 1 reference of the
+    speed-up), then all ranks time the sharded frame; device-timed, max over ranks."""
     import torch.distributed as dist
-    from neuma_b200 import build, synthetic as S
+    from neuma_b200 import synthetic as S
     from neuma_b200.slab import SlabRollout
+    spec = S.WORKLOADS[SLAB_WORKLOAD]
+    p = S.make_particles(spec, 42)
+    w = load_weights()
+    gen = torch.Generator(device="cpu").manual_seed(7)
+
+    def make(standalone: bool, **kw):
+        sim = SlabRollout(spec["G"], spec["dt"], w["elastic"], w["plastic"], w["alpha"], substeps, dev,
+                          halo=halo, standalone=standalone, **kw)
+        sim.distribute(p["x"], p["v"], p["C"], p["F"], p["vol"], p["rho"], p["clip"], p["enabled"])
+        g = [torch.randn(sim.n, 3, generator=gen).to(dev), None, None,
+             torch.randn(sim.n, 3, 3, generator=gen).to(dev)]
+        return sim, g
+
+    def time_ms(sim, g, sync_ranks: bool) -> float:
+        def step():
+            sim.forward()
+            sim.backward(*g)
+        for _ in range(max(warmup, 3)):
+            step()
+        torch.cuda.synchronize()
+        if sync_ranks:
+            dist.barrier()
+            torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            step()
+        b.record()
+        b.synchronize()
+        t = torch.tensor([a.elapsed_time(b)], device=dev, dtype=torch.float64)
+        if sync_ranks:
+            dist.barrier()
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / steps
+
+    out = {"workload": SLAB_WORKLOAD, "particles": spec["n"], "grid": spec["G"], "substeps_per_frame": substeps,
+           "dt": spec["dt"], "nranks": world, "scaling": "strong", "steps": steps,
+           "mode": "MPM + constitutive fwd+bwd of one S-substep frame"}
+    # ---- N = 1 reference, rank 0 alone
+    t1 = torch.zeros(1, device=dev, dtype=torch.float64)
+    if rank == 0:
+        sim1, g1 = make(True)
+        t1[0] = time_ms(sim1, g1, False)
+        del sim1, g1
+        torch.cuda.empty_cache()
+    if world > 1:
+        dist.barrier()
+        dist.broadcast(t1, 0)
+    out["ms_per_frame_n1"] = float(t1.item())
+    if world == 1:
+        out["ms_per_frame"] = out["ms_per_frame_n1"]
+        out["speedup_vs_n1"] = 1.0
+        return out
+    # ---- sharded
+    sim, g = make(False)
+    ms = time_ms(sim, g, True)
+    sim.check_drift()
+    cnt = torch.tensor([sim.n], device=dev, dtype=torch.int64)
+    allc = [torch.zeros_like(cnt) for _ in range(world)]
+    dist.all_gather(allc, cnt)
+    ov = [sim.plan.overlap(r, True) for r in range(world - 1)]
+    out.update({"ms_per_frame": ms, "speedup_vs_n1": out["ms_per_frame_n1"] / ms, "frames_per_s": 1000.0 / ms,
+                "halo": halo, "overlap": sim.overlap, "halo_k": sim.k, "cuda_graphs": sim.use_graphs,
+                "slab_bounds": sim.plan.b, "particles_per_rank": [int(c_.item()) for c_ in allc],
+                "exchanges_per_frame": 2 * substeps,
+                "halo_bytes_dense_per_frame": sum(o[1] for o in ov) * spec["G"] ** 2 * 16 * 2 * 2 * substeps})
+    if variants:
+        # where the exchange time goes: the same frame without the overlap, and without any exchange
+        # (wrong results, valid timing)
+        if sim.overlap:
+            sim.overlap, sim._graphs = False, {}
+            out["ms_per_frame_no_overlap"] = time_ms(sim, g, True)
+        sim.skip_exchange, sim._graphs = True, {}
+        ms0 = time_ms(sim, g, True)
+        out["ms_per_frame_no_exchange"] = ms0
+        ref = out.get("ms_per_frame_no_overlap", ms)
+        out["halo_us_per_exchange"] = (ref - ms0) * 1000.0 / (2 * substeps)
+        out["halo_exposed_us_per_exchange"] = (ms - ms0) * 1000.0 / (2 * substeps)
+    return out
+
+
+def run_slab(args):
+    """--slab: only the Z-slab measurement (its own JSON line; not the headline metric)."""
+    import torch.distributed as dist
+    from neuma_b200 import build
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -387,57 +505,14 @@ def run_slab(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    name = "block-1m-256"
-    spec = S.WORKLOADS[name]
-    p = S.make_particles(spec, 42)
-    w = load_weights()
-    sim = SlabRollout(spec["G"], spec["dt"], w["elastic"], w["plastic"], w["alpha"], args.substeps, dev,
-                      halo=args.halo)
-    sim.distribute(p["x"], p["v"], p["C"], p["F"], p["vol"], p["rho"], p["clip"], p["enabled"])
-    gen = torch.Generator(device="cpu").manual_seed(7)
-    g = [torch.randn(sim.n, 3, generator=gen).to(dev), None, None, torch.randn(sim.n, 3, 3, generator=gen).to(dev)]
-
-    def step():
-        sim.forward()
-        sim.backward(*g)
-
-    for _ in range(max(args.warmup, 3)):
-        step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(args.steps):
-        step()
-    b.record()
-    b.synchronize()
-    t = torch.tensor([a.elapsed_time(b)], device=dev, dtype=torch.float64)
-    cnt = torch.tensor([sim.n], device=dev, dtype=torch.int64)
-    if world > 1:
-        dist.barrier()
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        allc = [torch.zeros_like(cnt) for _ in range(world)]
-        dist.all_gather(allc, cnt)
-        counts = [int(c_.item()) for c_ in allc]
-    else:
-        counts = [sim.n]
-    ok = sim.drift_ok()
-    ms = float(t.item()) / args.steps
+    r = slab_measure(dev, world, rank, args.substeps, args.steps, args.warmup, args.halo)
     if rank == 0:
-        ov = [sim.plan.overlap(r, True) for r in range(world - 1)]
-        halo_bytes = sum(o[1] for o in ov) * spec["G"] ** 2 * 16 * 2 * 2 * args.substeps   # both ways, fwd + bwd
         print(json.dumps({
-            "metric": "MPM+constitutive fwd+bwd frames/sec, Z-slab sharded", "value": 1000.0 / ms, "unit": "frames/s",
-            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": name, "particles": spec["n"], "grid": spec["G"], "substeps_per_frame": args.substeps,
-                       "dt": spec["dt"], "parallelism": f"z-slab x{world}", "slab_bounds": sim.plan.b,
-                       "particles_per_rank": counts, "halo_k": sim.k, "halo": args.halo if world > 1 else "none",
-                       "cuda_graphs": sim.use_graphs,
-                       "l2": "working set (particles + per-substep grids) far larger than L2"},
-            "substeps_per_s": 1000.0 / ms * args.substeps, "halo_bytes_per_frame": halo_bytes, "drift_ok": ok}))
+            "metric": "MPM+constitutive fwd+bwd frames/sec, Z-slab sharded", "value": 1000.0 / r["ms_per_frame"],
+            "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": r["ms_per_frame"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": {"workload": SLAB_WORKLOAD,
+                                                             "parallelism": f"z-slab x{world}"}, "slab": r}))
     if world > 1:
         dist.destroy_process_group()
 
@@ -486,7 +561,7 @@ def cpu_sample(wl, x0, v0, C0, F0, reps: int = 1):
     except Exception:
         warp_ok = False
     return {"value": 1.0 / (S * ts + t_render), "unit": "frames/s", "cores": cores, "kind": "port",
-            "warp_importable": warp_ok,
+            "sampled": True, "warp_importable": warp_ok,
             "sample": f"1 of {S} substeps fwd+bwd ({ts:.2f} s) + 1 render 800x800 fwd+bwd ({t_render:.2f} s), "
                       f"torch-CPU fp32 oracle, extrapolated to S={S}",
             "t_substep_s": ts, "t_render_s": t_render}
@@ -514,9 +589,7 @@ def run_reference(args):
             "value": v, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1000.0 / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "particles": wl["spec"]["n"], "grid": wl["spec"]["G"],
-                       "gaussians": wl["g"]["K"], "image": [IMAGE, IMAGE], "sh_degree": 3,
-                       "substeps_per_frame": wl["S"], "views": 1},
+            "config": workload_config(wl, world),
             "cpu_baseline": {"value": v, "unit": "frames/s", "cores": base["cores"], "kind": "port",
                              "sample": base["sample"], "wall_s_per_sample": float(np.mean(secs))},
             "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -534,8 +607,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default=WORKLOAD, choices=["bouncyball-50k-64", "jellyduck-100k-128", "claycat-200k-128"],
                     help="parity-test configs of BASELINE.json for the record; the headline is jellyduck-100k-128")
-    ap.add_argument("--halo", default="peer", choices=["peer", "nccl"],
-                    help="--slab halo exchange: NVLink peer-memory pushes inside CUDA graphs, or NCCL send/recv (eager)")
+    ap.add_argument("--no-slab", action="store_true", help="skip the Z-slab (config 5) section of the line")
+    ap.add_argument("--slab-steps", type=int, default=5, help="timed frames of the Z-slab section")
+    ap.add_argument("--halo", default="fused", choices=["fused", "peer", "nccl"],
+                    help="Z-slab halo exchange: one fused windowed kernel (default), round-1 push/add kernel pairs, "
+                         "or NCCL send/recv (eager)")
     ap.add_argument("--slab", action="store_true",
                     help="BASELINE config 5: 1M particles / 256^3 MPM fwd+bwd, Z-slab sharded over the ranks")
     args = ap.parse_args()

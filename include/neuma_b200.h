@@ -41,7 +41,14 @@ typedef struct neuma_ctx neuma_ctx;
 
 /* MPMConstant, modules/nclaw/sim/mpm.py:158-167 (+ bc from :545-550).
  * z_off / nz describe the z-slab of the grid this ctx holds: grid planes
- * [z_off, z_off + nz).  Single GPU: z_off = 0, nz = num_grids. */
+ * [z_off, z_off + nz).  Single GPU: z_off = 0, nz = num_grids.
+ * The fields after nz only concern the rollout entry points (zero = the plain dense case):
+ *   compact / cap_nodes : the caller's per-substep grid buffers hold only the bounding box of
+ *       the occupied nodes (cap_nodes float4 nodes each) instead of nz*G*G nodes;
+ *   sel_mode / sel_lo_end / sel_up_start : Z-slab overlap.  Planes below sel_lo_end
+ *       and from sel_up_start on are SHARED with a neighbour rank.  sel_mode 1 restricts a
+ *       particle kernel to the particles whose stencil touches a shared plane and a node pass
+ *       to the shared planes; sel_mode 2 to the complement; 0 = everything. */
 typedef struct {
   int32_t num_grids;
   float dt;
@@ -53,7 +60,31 @@ typedef struct {
   int32_t bc;    /* 0 = noslip (mpm.py:402-429), 1 = freeslip (mpm.py:373-400) */
   int32_t z_off; /* first grid plane held by this ctx */
   int32_t nz;    /* number of grid planes held by this ctx */
+  int32_t compact;
+  int32_t cap_nodes;
+  int32_t sel_mode;
+  int32_t sel_lo_end;
+  int32_t sel_up_start;
 } neuma_mpm_const;
+
+/* One side (lower or upper z-neighbour) of the Z-slab halo exchange.  All pointers
+ * are DEVICE pointers; peer_* point into the NEIGHBOUR's memory (NVLink peer mapping).  A
+ * mailbox holds 2 slots x npl x G x G float4 nodes, a header 2 slots x 4 int32 (the sender's
+ * x0, nx, y0, ny window); flags are single int32, zero-initialised once.  planes == NULL: no
+ * neighbour on this side. */
+typedef struct {
+  float* planes;               /* my shared planes inside the grid being exchanged */
+  float* peer_mail;            /* neighbour's mailbox for what I send */
+  int32_t* peer_hdr;
+  const float* my_mail;        /* my mailbox for what that neighbour sends */
+  const int32_t* my_hdr;
+  int32_t* peer_data_flag;
+  const int32_t* my_data_flag;
+  int32_t* peer_ack_flag;
+  const int32_t* my_ack_flag;
+  int32_t npl;                 /* number of shared planes */
+  int32_t pad;
+} neuma_halo_side;
 
 /* GaussianRasterizationSettings, modules/d3gs/gaussian_renderer/__init__.py:103-116.
  * viewmatrix / projmatrix are the reference's transposed (row-vector) 4x4s
@@ -137,7 +168,10 @@ int neuma_mpm_substep_bwd(neuma_ctx* ctx, const neuma_mpm_const* c, int n,
 /* ---- MPM rollout path (MPMCacheDiffSim, modules/nclaw/sim/interface.py:108-123) --------
  * The same substep with CALLER-OWNED packed grids, one per substep of a differentiable
  * rollout, so the backward reads the forward's grid instead of recomputing P2G
- * (mpm.py:312-315).  `grid` / `adj`: nz*G*G float4 nodes, plane-major (z slowest).
+ * (mpm.py:312-315).  `grid` / `adj`: nz*G*G float4 nodes, plane-major (z slowest) -- or, with
+ * c->compact, c->cap_nodes nodes holding just the box (x-range widened to multiples of 8), z
+ * slowest inside the box; a box that does not fit raises box[6] and the substep is skipped.
+ * box[7] counts particles whose stencil left the planes [z_off, z_off + nz) (Z-slab drift).
  * `box`: int32[8] on the device = inclusive node bounding box (lo.xyz, hi.xyz, 2 pad) of
  * the occupied nodes; clears and node passes touch only the box. */
 /* box of the nodes the particles at x touch (init + reduce) */
@@ -145,12 +179,13 @@ int neuma_mpm_box_from_x(neuma_ctx* ctx, const neuma_mpm_const* c, int n, const 
                          const int32_t* enabled, int32_t* box, void* stream);
 /* grid.clear() (mpm.py:147-150) restricted to the box, on up to two grids (either may be
  * NULL); box_reset (may be NULL) is set to the empty box */
-int neuma_mpm_box_clear(neuma_ctx* ctx, const neuma_mpm_const* c, const int32_t* box, float* grid0,
+int neuma_mpm_box_clear(neuma_ctx* ctx, const neuma_mpm_const* c, int32_t* box, float* grid0,
                         float* grid1, int32_t* box_reset, void* stream);
 /* p2g (mpm.py:321-371) accumulating (mv, m) into `grid` */
 int neuma_mpm_p2g_to(neuma_ctx* ctx, const neuma_mpm_const* c, int n, const float* x, const float* v,
                      const float* C, const float* stress, const float* vol, const float* rho,
-                     const int32_t* enabled, float* grid, void* stream);
+                     const int32_t* enabled, const int32_t* box /* NULL unless c->compact */,
+                     float* grid, void* stream);
 /* grid_op_* (mpm.py:373-429) over the box, in place: (mv, m) -> (v, m); components zeroed
  * by the wall BC are stored as -0.0f.  adj_to_clear (may be NULL) is zeroed over the box. */
 int neuma_mpm_grid_op_box(neuma_ctx* ctx, const neuma_mpm_const* c, const int32_t* box, float* grid,
@@ -159,6 +194,7 @@ int neuma_mpm_grid_op_box(neuma_ctx* ctx, const neuma_mpm_const* c, const int32_
  * or a partial reduction) receives the box of the nodes the NEW positions touch */
 int neuma_mpm_g2p_from(neuma_ctx* ctx, const neuma_mpm_const* c, int n, const float* x,
                        const float* F, const float* clip_bound, const int32_t* enabled,
+                       const int32_t* box /* NULL unless c->compact */,
                        const float* grid_v, float* x2, float* v2, float* C2, float* F2,
                        int32_t* box_next, void* stream);
 /* MPMModel.forward (mpm.py:279-297) = box_clear(grid; resets box_next) + p2g_to +
@@ -167,7 +203,7 @@ int neuma_mpm_rollout_fwd(neuma_ctx* ctx, const neuma_mpm_const* c, int n, const
                           const float* v, const float* C, const float* F, const float* stress,
                           const float* vol, const float* rho, const float* clip_bound,
                           const int32_t* enabled, float* x2, float* v2, float* C2, float* F2,
-                          float* grid, float* adj, const int32_t* box, int32_t* box_next,
+                          float* grid, float* adj, int32_t* box, int32_t* box_next,
                           void* stream);
 /* MPMModel.backward (mpm.py:299-319) without the P2G recompute: grid_v is the (v, m) grid
  * neuma_mpm_rollout_fwd left, adj a zeroed (over the box) scratch grid (overwritten), C2 the
@@ -184,7 +220,8 @@ int neuma_mpm_rollout_bwd(neuma_ctx* ctx, const neuma_mpm_const* c, int n, const
 int neuma_mpm_bwd_scatter(neuma_ctx* ctx, const neuma_mpm_const* c, int n, const float* x,
                           const float* F, const float* clip_bound, const int32_t* enabled,
                           const float* v2, const float* gx2, const float* gv2, const float* gC2,
-                          const float* gF2, float* adj, void* stream);
+                          const float* gF2, const int32_t* box /* NULL unless c->compact */,
+                          float* adj, void* stream);
 int neuma_mpm_bwd_node_gather(neuma_ctx* ctx, const neuma_mpm_const* c, int n, const float* x,
                               const float* v, const float* C, const float* F, const float* stress,
                               const float* vol, const float* rho, const float* clip_bound,
@@ -208,6 +245,12 @@ int neuma_halo_push(neuma_ctx* ctx, const float* src, float* peer_mailbox, size_
 int neuma_halo_add_ack(neuma_ctx* ctx, float* dst, const float* mailbox, size_t nodes,
                        const int32_t* my_data_flag, int32_t* peer_ack_flag, int32_t* my_seq, int32_t* done,
                        void* stream);
+/* The same exchange as ONE kernel for both neighbours (what SlabRollout uses): pushes only the
+ * x-y window `box` says my particles occupy, waits for the neighbours' pushes, adds THEIR
+ * windows, acknowledges; double-buffered mailboxes.  cnt: int32[4] local counters, zeroed once.
+ * Either side may be NULL. */
+int neuma_halo_exchange(neuma_ctx* ctx, const neuma_mpm_const* c, const neuma_halo_side* lo,
+                        const neuma_halo_side* hi, const int32_t* box, int32_t* cnt, void* stream);
 /* permutation that puts the particles in cell (Morton) order of their stencil base:
  * perm[i] = index of the i-th particle in that order.  Not capturable (may grow the ctx
  * scratch). */

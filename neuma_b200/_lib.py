@@ -20,6 +20,25 @@ class MPMConstC(C.Structure):
         ("num_grids", C.c_int32), ("dt", C.c_float), ("bound", C.c_int32),
         ("gravity", C.c_float * 3), ("dx", C.c_float), ("inv_dx", C.c_float),
         ("eps", C.c_float), ("bc", C.c_int32), ("z_off", C.c_int32), ("nz", C.c_int32),
+        ("compact", C.c_int32), ("cap_nodes", C.c_int32),
+        ("sel_mode", C.c_int32), ("sel_lo_end", C.c_int32), ("sel_up_start", C.c_int32),
+    ]
+
+    def variant(self, **kw) -> "MPMConstC":
+        """A copy with some fields replaced (the struct is passed by value per call)."""
+        c = MPMConstC.from_buffer_copy(self)
+        for k, v in kw.items():
+            setattr(c, k, v)
+        return c
+
+
+class HaloSideC(C.Structure):
+    """neuma_halo_side: one neighbour of the Z-slab halo exchange."""
+    _fields_ = [
+        ("planes", C.c_void_p), ("peer_mail", C.c_void_p), ("peer_hdr", C.c_void_p),
+        ("my_mail", C.c_void_p), ("my_hdr", C.c_void_p), ("peer_data_flag", C.c_void_p),
+        ("my_data_flag", C.c_void_p), ("peer_ack_flag", C.c_void_p), ("my_ack_flag", C.c_void_p),
+        ("npl", C.c_int32), ("pad", C.c_int32),
     ]
 
 
@@ -58,16 +77,17 @@ SIGNATURES = {
     "neuma_mpm_substep_bwd": [_P, _CP, _I] + [_P] * 20,
     "neuma_mpm_box_from_x": [_P, _CP, _I, _P, _P, _P, _P],
     "neuma_mpm_box_clear": [_P, _CP, _P, _P, _P, _P, _P],
-    "neuma_mpm_p2g_to": [_P, _CP, _I] + [_P] * 9,
+    "neuma_mpm_p2g_to": [_P, _CP, _I] + [_P] * 10,
     "neuma_mpm_grid_op_box": [_P, _CP, _P, _P, _P, _P],
-    "neuma_mpm_g2p_from": [_P, _CP, _I] + [_P] * 11,
+    "neuma_mpm_g2p_from": [_P, _CP, _I] + [_P] * 12,
     "neuma_mpm_rollout_fwd": [_P, _CP, _I] + [_P] * 18,
     "neuma_mpm_rollout_bwd": [_P, _CP, _I] + [_P] * 24,
-    "neuma_mpm_bwd_scatter": [_P, _CP, _I] + [_P] * 11,
+    "neuma_mpm_bwd_scatter": [_P, _CP, _I] + [_P] * 12,
     "neuma_mpm_bwd_node_gather": [_P, _CP, _I] + [_P] * 24,
     "neuma_mpm_planes_add": [_P, _P, _P, C.c_size_t, _P],
     "neuma_halo_push": [_P, _P, _P, C.c_size_t, _P, _P, _P, _P, _P],
     "neuma_halo_add_ack": [_P, _P, _P, C.c_size_t, _P, _P, _P, _P, _P],
+    "neuma_halo_exchange": [_P, _CP, C.POINTER(HaloSideC), C.POINTER(HaloSideC), _P, _P, _P],
     "neuma_mpm_cell_order": [_P, _CP, _I, _P, _P, _P],
     "neuma_gather_rows": [_P, _I, _I, _P, _P, _P, _P],
     "neuma_invert_perm": [_P, _I, _P, _P, _P],
@@ -145,7 +165,12 @@ class Context:
         return ctx
 
     def call(self, name: str, *args) -> None:
-        rc = getattr(self.lib, name)(self.handle, *args)
+        import torch
+        if torch.cuda.current_device() != self.device:          # allocations / launches of the library
+            with torch.cuda.device(self.device):                # belong to the ctx's device
+                rc = getattr(self.lib, name)(self.handle, *args)
+        else:
+            rc = getattr(self.lib, name)(self.handle, *args)
         if rc != 0:
             msg = self.lib.neuma_last_error(self.handle)
             raise NeumaError(f"{name} failed ({rc}): {msg.decode() if msg else ''}")

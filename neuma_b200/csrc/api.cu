@@ -59,7 +59,8 @@ int neuma_ctx_create(int device, neuma_ctx** out) {
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return 3;
   if (prop.major != 10) return 4;  // sm_100a only: there is no fallback path
-  if (cudaSetDevice(device) != cudaSuccess) return 3;
+  // the caller's current device is left as it was (entry points run on the device of the
+  // pointers / stream they are given; the Python front end makes ctx->device current per call)
   neuma_ctx* ctx = (neuma_ctx*)calloc(1, sizeof(neuma_ctx));
   if (!ctx) return 5;
   ctx->device = device;

@@ -958,17 +958,19 @@ reduce_partials_kernel(int slots, float* __restrict__ part, float* __restrict__ 
   }
 }
 
-bool g_attr_set = false;
-
 int set_attrs(neuma_ctx* ctx) {
-  if (g_attr_set) return 0;
+  if (ctx->attrs_set) return 0;
+  int cur = -1;
+  cudaGetDevice(&cur);
+  if (cur != ctx->device) NEUMA_CUDA(ctx, cudaSetDevice(ctx->device));
   NEUMA_CUDA(ctx, cudaFuncSetAttribute(constitutive_fwd_kernel,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM));
   NEUMA_CUDA(ctx, cudaFuncSetAttribute(constitutive_bwd_kernel<true>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM));
   NEUMA_CUDA(ctx, cudaFuncSetAttribute(constitutive_bwd_kernel<false>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM));
-  g_attr_set = true;
+  ctx->attrs_set = 1;
+  if (cur >= 0 && cur != ctx->device) cudaSetDevice(cur);
   return 0;
 }
 

@@ -25,6 +25,10 @@ __global__ void grid_clear_kernel(float4* __restrict__ g, size_t n) {
     g[i] = z;
 }
 
+__device__ __forceinline__ GridMap dense_map(const neuma_mpm_const& c) {
+  return GridMap{0, 0, c.z_off, c.num_grids, c.num_grids, c.nz};
+}
+
 // ------------------------------------------------------------------ P2G
 __global__ void __launch_bounds__(256)
 p2g_kernel(neuma_mpm_const c, int n, const float* __restrict__ x, const float* __restrict__ v,
@@ -34,7 +38,7 @@ p2g_kernel(neuma_mpm_const c, int n, const float* __restrict__ x, const float* _
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
   if (enabled[p] == 0) return;
-  p2g_particle(c, p, x, v, C, stress, vol[p], rho[p], grid);
+  p2g_particle(c, dense_map(c), p, x, v, C, stress, vol[p], rho[p], grid);
 }
 
 // ------------------------------------------------------------------ grid_op (dense)
@@ -62,65 +66,8 @@ g2p_kernel(neuma_mpm_const c, int n, const float* __restrict__ x, const float* _
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
   if (enabled[p] == 0) return;
-  const float px[3] = {x[3 * p], x[3 * p + 1], x[3 * p + 2]};
-  const Stencil s = make_stencil(px[0], px[1], px[2], c.inv_dx);
-  float nv[3] = {0.f, 0.f, 0.f};
-  float nC[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  const float k4 = 4.0f * c.inv_dx * c.inv_dx;
-#pragma unroll
-  for (int i = 0; i < 3; ++i)
-#pragma unroll
-    for (int j = 0; j < 3; ++j)
-#pragma unroll
-      for (int kk = 0; kk < 3; ++kk) {
-        const int ix = s.b[0] + i, iy = s.b[1] + j, iz = s.b[2] + kk;
-        if (!node_in_range(c, ix, iy, iz)) continue;
-        const float4 q = grid[node_index(c, ix, iy, iz)];
-        float gv[3];
-        if (LAZY) {
-          float pass[3], inv_m, vp[3];
-          node_velocity(c, q, ix, iy, iz, gv, pass, inv_m, vp);
-        } else {
-          gv[0] = q.x; gv[1] = q.y; gv[2] = q.z;
-        }
-        const float d[3] = {((float)i - s.f[0]) * c.dx, ((float)j - s.f[1]) * c.dx,
-                            ((float)kk - s.f[2]) * c.dx};
-        const float w = s.w[0][i] * s.w[1][j] * s.w[2][kk];
-        const float w4 = k4 * w;
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-          nv[a] += w * gv[a];
-#pragma unroll
-          for (int b = 0; b < 3; ++b) nC[3 * a + b] += w4 * (gv[a] * d[b]);
-        }
-      }
-  // F' = (I + dt C') F   (mpm.py:487)
-  float Fo[9], Fn[9];
-#pragma unroll
-  for (int i = 0; i < 9; ++i) Fo[i] = F[9 * p + i];
-#pragma unroll
-  for (int a = 0; a < 3; ++a)
-#pragma unroll
-    for (int b = 0; b < 3; ++b) {
-      float acc = 0.f;
-#pragma unroll
-      for (int k = 0; k < 3; ++k)
-        acc += ((a == k ? 1.0f : 0.0f) + c.dt * nC[3 * a + k]) * Fo[3 * k + b];
-      Fn[3 * a + b] = acc;
-    }
-  const float bnd = clip[p] * c.dx;
-#pragma unroll
-  for (int a = 0; a < 3; ++a) {
-    float nx = px[a] + c.dt * nv[a];
-    nx = fminf(fmaxf(nx, 0.0f + bnd), 1.0f - bnd);
-    x2[3 * p + a] = nx;
-    v2[3 * p + a] = nv[a];
-  }
-#pragma unroll
-  for (int i = 0; i < 9; ++i) {
-    C2[9 * p + i] = nC[i];
-    F2[9 * p + i] = Fn[i];
-  }
+  float nx3[3];
+  g2p_particle<LAZY>(c, dense_map(c), p, x, F, clip, grid, x2, v2, C2, F2, nx3);
 }
 
 // ------------------------------------------------------------------ backward
@@ -139,28 +86,10 @@ bwd_scatter_kernel(neuma_mpm_const c, int n, const float* __restrict__ x,
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
   if (enabled[p] == 0) return;
-  p2g_particle(c, p, x, v, C, stress, vol[p], rho[p], grid);
+  const GridMap gm = dense_map(c);
+  p2g_particle(c, gm, p, x, v, C, stress, vol[p], rho[p], grid);
   const G2PAdj g = g2p_adjoint_inputs(c, p, x, F, clip, v2, gx2, gv2, gC2, gF2);
-  const Stencil s = make_stencil(x[3 * p], x[3 * p + 1], x[3 * p + 2], c.inv_dx);
-  const float k4 = 4.0f * c.inv_dx * c.inv_dx;
-#pragma unroll
-  for (int i = 0; i < 3; ++i)
-#pragma unroll
-    for (int j = 0; j < 3; ++j)
-#pragma unroll
-      for (int kk = 0; kk < 3; ++kk) {
-        const int ix = s.b[0] + i, iy = s.b[1] + j, iz = s.b[2] + kk;
-        if (!node_in_range(c, ix, iy, iz)) continue;
-        const float d[3] = {((float)i - s.f[0]) * c.dx, ((float)j - s.f[1]) * c.dx,
-                            ((float)kk - s.f[2]) * c.dx};
-        const float w = s.w[0][i] * s.w[1][j] * s.w[2][kk];
-        float o[3];
-#pragma unroll
-        for (int a = 0; a < 3; ++a)
-          o[a] = w * (g.gvt[a] + k4 * (g.gCt[3 * a] * d[0] + g.gCt[3 * a + 1] * d[1] +
-                                       g.gCt[3 * a + 2] * d[2]));
-        red_add_f4(gadj + node_index(c, ix, iy, iz), o[0], o[1], o[2], 0.0f);
-      }
+  g2p_adjoint_scatter(c, gm, p, x, g, gadj);
 }
 
 // Pass 2: per particle, gather (mv, m) and dL/dv of its 27 nodes, push dL/dv
@@ -181,118 +110,11 @@ bwd_gather_kernel(neuma_mpm_const c, int n, const float* __restrict__ x,
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
   if (enabled[p] == 0) {
-    // the reference's kernels return early: no adjoint contribution
-    if (gx) for (int a = 0; a < 3; ++a) gx[3 * p + a] = 0.f;
-    if (gv) for (int a = 0; a < 3; ++a) gv[3 * p + a] = 0.f;
-    if (gC) for (int a = 0; a < 9; ++a) gC[9 * p + a] = 0.f;
-    if (gF) for (int a = 0; a < 9; ++a) gF[9 * p + a] = 0.f;
-    if (gstress) for (int a = 0; a < 9; ++a) gstress[9 * p + a] = 0.f;
+    zero_particle_grads(p, gx, gv, gC, gF, gstress);
     return;
   }
-  const float p_vol = vol[p];
-  const float p_mass = p_vol * rho[p];
-  const Stencil s = make_stencil(x[3 * p], x[3 * p + 1], x[3 * p + 2], c.inv_dx);
-  const float ks = -c.dt * p_vol * 4.0f * c.inv_dx * c.inv_dx;
-  const float k4 = 4.0f * c.inv_dx * c.inv_dx;
-  float A[9];
-#pragma unroll
-  for (int i = 0; i < 9; ++i) A[i] = ks * stress[9 * p + i] + p_mass * C[9 * p + i];
-  const float pv[3] = {p_mass * v[3 * p], p_mass * v[3 * p + 1], p_mass * v[3 * p + 2]};
-  const G2PAdj g = g2p_adjoint_inputs(c, p, x, F, clip, v2, gx2, gv2, gC2, gF2);
-
-  float acc_gmv[3] = {0.f, 0.f, 0.f};  // sum_n W g_mv
-  float gA[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  float gd[3] = {0.f, 0.f, 0.f};       // sum_n dL/d dpos_n
-  float gw[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
-  float nC[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // recomputed C'
-#pragma unroll
-  for (int i = 0; i < 3; ++i)
-#pragma unroll
-    for (int j = 0; j < 3; ++j)
-#pragma unroll
-      for (int kk = 0; kk < 3; ++kk) {
-        const int ix = s.b[0] + i, iy = s.b[1] + j, iz = s.b[2] + kk;
-        if (!node_in_range(c, ix, iy, iz)) continue;
-        const size_t ni = node_index(c, ix, iy, iz);
-        const float4 q = grid[ni];
-        const float4 ga = gadj[ni];
-        float vn[3], pass[3], inv_m, vp[3];
-        node_velocity(c, q, ix, iy, iz, vn, pass, inv_m, vp);
-        // adj(grid_op): v = mv/(m+eps) + g dt
-        const float gvn[3] = {ga.x * pass[0], ga.y * pass[1], ga.z * pass[2]};
-        const float gmv[3] = {gvn[0] * inv_m, gvn[1] * inv_m, gvn[2] * inv_m};
-        const float gm = -(vp[0] * gvn[0] + vp[1] * gvn[1] + vp[2] * gvn[2]) * inv_m;
-        const float d[3] = {((float)i - s.f[0]) * c.dx, ((float)j - s.f[1]) * c.dx,
-                            ((float)kk - s.f[2]) * c.dx};
-        const float w = s.w[0][i] * s.w[1][j] * s.w[2][kk];
-        // --- adj(G2P) terms that need v_node
-        float gCt_d[3], gCtT_v[3];
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-          gCt_d[a] = g.gCt[3 * a] * d[0] + g.gCt[3 * a + 1] * d[1] + g.gCt[3 * a + 2] * d[2];
-          gCtT_v[a] = g.gCt[a] * vn[0] + g.gCt[3 + a] * vn[1] + g.gCt[6 + a] * vn[2];
-        }
-        float gW = vn[0] * g.gvt[0] + vn[1] * g.gvt[1] + vn[2] * g.gvt[2] +
-                   k4 * (vn[0] * gCt_d[0] + vn[1] * gCt_d[1] + vn[2] * gCt_d[2]);
-        // --- adj(P2G)
-        float Ad[3], ATg[3];
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-          Ad[a] = A[3 * a] * d[0] + A[3 * a + 1] * d[1] + A[3 * a + 2] * d[2];
-          ATg[a] = A[a] * gmv[0] + A[3 + a] * gmv[1] + A[6 + a] * gmv[2];
-        }
-        gW += gmv[0] * (pv[0] + Ad[0]) + gmv[1] * (pv[1] + Ad[1]) + gmv[2] * (pv[2] + Ad[2]) +
-              gm * p_mass;
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-          acc_gmv[a] += w * gmv[a];
-          gd[a] += w * (k4 * gCtT_v[a] + ATg[a]);
-#pragma unroll
-          for (int b = 0; b < 3; ++b) {
-            gA[3 * a + b] += w * (gmv[a] * d[b]);
-            nC[3 * a + b] += (k4 * w) * (vn[a] * d[b]);
-          }
-        }
-        gw[0][i] += gW * (s.w[1][j] * s.w[2][kk]);
-        gw[1][j] += gW * (s.w[0][i] * s.w[2][kk]);
-        gw[2][kk] += gW * (s.w[0][i] * s.w[1][j]);
-      }
-  // weights -> fx: dw0/df = -(1.5 - f), dw1/df = -2 (f - 1), dw2/df = f - 0.5
-  // dpos = (offset - fx) dx -> dL/dfx -= dx * gd ;  fx = x * inv_dx - base
-  if (gx) {
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      const float f = s.f[a];
-      float gf = gw[a][0] * (-(1.5f - f)) + gw[a][1] * (-2.0f * (f - 1.0f)) + gw[a][2] * (f - 0.5f);
-      gf -= c.dx * gd[a];
-      gx[3 * p + a] = finite_or_zero(g.gxn[a] + c.inv_dx * gf);
-    }
-  }
-  if (gv) {
-#pragma unroll
-    for (int a = 0; a < 3; ++a) gv[3 * p + a] = finite_or_zero(p_mass * acc_gmv[a]);
-  }
-  if (gC) {
-#pragma unroll
-    for (int a = 0; a < 9; ++a) gC[9 * p + a] = finite_or_zero(p_mass * gA[a]);
-  }
-  if (gstress) {
-#pragma unroll
-    for (int a = 0; a < 9; ++a) gstress[9 * p + a] = finite_or_zero(ks * gA[a]);
-  }
-  if (gF) {
-    // gF = (I + dt C')^T gF'
-#pragma unroll
-    for (int a = 0; a < 3; ++a)
-#pragma unroll
-      for (int b = 0; b < 3; ++b) {
-        float acc = 0.f;
-#pragma unroll
-        for (int k = 0; k < 3; ++k)
-          acc += ((a == k ? 1.0f : 0.0f) + c.dt * nC[3 * k + a]) * gF2[9 * p + 3 * k + b];
-        gF[9 * p + 3 * a + b] = finite_or_zero(acc);
-      }
-  }
+  bwd_gather_particle<true, false>(c, dense_map(c), p, x, v, C, F, stress, vol, rho, clip, v2, nullptr, gx2,
+                                   gv2, gC2, gF2, grid, gadj, gx, gv, gC, gF, gstress);
 }
 
 // ------------------------------------------------------------------ export / halo
@@ -339,6 +161,8 @@ int check_const(neuma_ctx* ctx, const neuma_mpm_const* c) {
   if (c->num_grids <= 0 || c->nz <= 0 || c->z_off < 0 || c->z_off + c->nz > c->num_grids + 4)
     return neuma_fail_msg(ctx, "neuma_mpm: bad grid extents");
   if (c->bc != 0 && c->bc != 1) return neuma_fail_msg(ctx, "neuma_mpm: bc must be 0 or 1");
+  if (c->compact || c->sel_mode)
+    return neuma_fail_msg(ctx, "neuma_mpm: compact / sel_mode only apply to the rollout entry points");
   return neuma_ensure_grid(ctx, (size_t)c->nz * c->num_grids * c->num_grids);
 }
 

@@ -1,8 +1,10 @@
-// Device helpers shared by the MPM kernels (mpm.cu: stand-alone / per-substep entry
-// points; mpm_rollout.cu: the rollout path with caller-owned per-substep grids).
-// Arithmetic follows modules/nclaw/sim/mpm.py:321-498.
+// Device code shared by the MPM kernels (mpm.cu: stand-alone / per-substep entry points on
+// the ctx grid; mpm_rollout.cu: the rollout path with caller-owned per-substep grids).
+// Arithmetic follows modules/nclaw/sim/mpm.py:321-498.  ONE copy of every per-particle body
+// (P2G visit loop, G2P gather, adjoint scatter, adjoint gather); the kernels are thin wrappers.
 #pragma once
 #include "common.cuh"
+#include <limits.h>
 
 namespace {
 
@@ -12,12 +14,20 @@ struct Stencil {
   float w[3][3];  // w[axis][i], quadratic B-spline (mpm.py:345-354)
 };
 
+// base node of a coordinate: int(x * inv_dx - 0.5), truncation toward zero (mpm.py:337-339).
+// Explicitly un-fused (product rounded, then the subtraction), like the reference's fp32
+// expression evaluated op by op, and so that EVERY kernel (stencil, box, cell key, slab
+// selection) derives the identical integer from the same x.
+__device__ __forceinline__ int base_node(float x, float inv_dx) {
+  return (int)__fsub_rn(__fmul_rn(x, inv_dx), 0.5f);
+}
+
 __device__ __forceinline__ Stencil make_stencil(float x0, float x1, float x2, float inv_dx) {
   Stencil s;
-  const float p[3] = {x0 * inv_dx, x1 * inv_dx, x2 * inv_dx};
+  const float p[3] = {__fmul_rn(x0, inv_dx), __fmul_rn(x1, inv_dx), __fmul_rn(x2, inv_dx)};
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
-    s.b[a] = (int)(p[a] - 0.5f);  // int() truncates, it is not floor
+    s.b[a] = (int)__fsub_rn(p[a], 0.5f);  // int() truncates, it is not floor
     s.f[a] = p[a] - (float)s.b[a];
     const float wa = 1.5f - s.f[a];
     const float wb = s.f[a] - 1.0f;
@@ -29,20 +39,81 @@ __device__ __forceinline__ Stencil make_stencil(float x0, float x1, float x2, fl
   return s;
 }
 
-__device__ __forceinline__ bool node_in_range(const neuma_mpm_const& c, int ix, int iy, int iz) {
-  // The reference does not bounds-check (Warp release build): a particle at the
-  // upper clamp writes nodes G, G+1 ("latent OOB").  Here such node
-  // visits are dropped, in P2G, G2P and both adjoints alike.
-  return (unsigned)ix < (unsigned)c.num_grids && (unsigned)iy < (unsigned)c.num_grids &&
-         (unsigned)(iz - c.z_off) < (unsigned)c.nz;
+// ---- where a node lives in a grid buffer --------------------------------------------------
+// dense   (c.compact == 0): the buffer holds planes [z_off, z_off + nz) of the G x G x G grid,
+//          plane-major (z slowest) -- the per-substep entry points and the Z-slab path, whose
+//          halo planes must sit at fixed addresses;
+// compact (c.compact != 0): the buffer holds ONLY the bounding box of the occupied nodes
+//          (`box`, on the device, x-range widened to 128-byte rows), z slowest inside the box:
+//          S saved grids of a rollout cost S x |box| x 16 B instead of S x G^3 x 16 B
+//          (SURVEY 8f.1).  A box larger than c.cap_nodes is an overflow: the map is empty, every
+//          kernel skips its work and box[6] is raised by box_clear (checked on the host).
+struct GridMap {
+  int x0, y0, z0, nx, ny, nz;
+};
+struct Box {
+  int lo[3], hi[3];
+};
+__device__ __forceinline__ Box load_box(const int32_t* __restrict__ b) {
+  Box r;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) { r.lo[a] = b[a]; r.hi[a] = b[3 + a]; }
+  return r;
 }
-__device__ __forceinline__ size_t node_index(const neuma_mpm_const& c, int ix, int iy, int iz) {
-  return ((size_t)(iz - c.z_off) * c.num_grids + iy) * c.num_grids + ix;
+__device__ __forceinline__ bool box_empty(const Box& b) {
+  return b.lo[0] > b.hi[0] || b.lo[1] > b.hi[1] || b.lo[2] > b.hi[2];
+}
+// the box as an iteration window: x-range widened to 8 nodes = 128-byte rows
+__device__ __forceinline__ GridMap box_window(const neuma_mpm_const& c, const Box& b) {
+  GridMap m;
+  if (box_empty(b)) { m.x0 = m.y0 = m.z0 = 0; m.nx = m.ny = m.nz = 0; return m; }
+  m.x0 = b.lo[0] & ~7;
+  const int x1 = c.compact ? (b.hi[0] | 7) : min(c.num_grids - 1, b.hi[0] | 7);
+  m.nx = x1 - m.x0 + 1;
+  m.y0 = b.lo[1]; m.ny = b.hi[1] - b.lo[1] + 1;
+  m.z0 = b.lo[2]; m.nz = b.hi[2] - b.lo[2] + 1;
+  return m;
+}
+__device__ __forceinline__ long long map_nodes(const GridMap& m) {
+  return (long long)m.nx * m.ny * m.nz;
+}
+__device__ __forceinline__ bool map_overflows(const neuma_mpm_const& c, const GridMap& m) {
+  return c.compact && map_nodes(m) > (long long)c.cap_nodes;
+}
+__device__ __forceinline__ GridMap grid_map(const neuma_mpm_const& c, const int32_t* __restrict__ box) {
+  if (!c.compact) return GridMap{0, 0, c.z_off, c.num_grids, c.num_grids, c.nz};
+  GridMap m = box_window(c, load_box(box));
+  if (map_overflows(c, m)) m.nx = m.ny = m.nz = 0;
+  return m;
+}
+__device__ __forceinline__ bool node_in_range(const GridMap& m, int ix, int iy, int iz) {
+  // The reference does not bounds-check (Warp release build): a particle at the upper clamp
+  // writes nodes G, G+1 ("latent OOB").  Here such node visits are dropped, in P2G,
+  // G2P and both adjoints alike (a compact box is already clipped to the domain).
+  return (unsigned)(ix - m.x0) < (unsigned)m.nx && (unsigned)(iy - m.y0) < (unsigned)m.ny &&
+         (unsigned)(iz - m.z0) < (unsigned)m.nz;
+}
+__device__ __forceinline__ size_t node_index(const GridMap& m, int ix, int iy, int iz) {
+  return ((size_t)(iz - m.z0) * m.ny + (iy - m.y0)) * m.nx + (ix - m.x0);
 }
 
-// grid_op on one node (mpm.py:373-429).  Returns v; `pass` gets 1/0 per
-// component: whether dL/dv flows back to (mv, m) (0 where the wall BC zeroed it
-// or the node is empty).  `vpre_nog` = mv / (m + eps) (needed by the adjoint).
+// ---- Z-slab overlap selection (neuma_mpm_const::sel_*): planes below sel_lo_end and from
+// sel_up_start on are shared with a neighbour rank.
+__device__ __forceinline__ bool plane_selected(const neuma_mpm_const& c, int iz) {
+  if (c.sel_mode == 0) return true;
+  const bool shared = iz < c.sel_lo_end || iz >= c.sel_up_start;
+  return (c.sel_mode == 1) == shared;
+}
+__device__ __forceinline__ bool particle_selected(const neuma_mpm_const& c, float z) {
+  if (c.sel_mode == 0) return true;
+  const int bz = base_node(z, c.inv_dx);   // the stencil touches planes bz .. bz + 2
+  const bool shared = bz < c.sel_lo_end || bz + 2 >= c.sel_up_start;
+  return (c.sel_mode == 1) == shared;
+}
+
+// grid_op on one node (mpm.py:373-429).  Returns v; `pass` gets 1/0 per component: whether
+// dL/dv flows back to (mv, m) (0 where the wall BC zeroed it or the node is empty).
+// `vpre_nog` = mv / (m + eps) (needed by the adjoint).
 __device__ __forceinline__ void node_velocity(const neuma_mpm_const& c, const float4 mvm, int ix,
                                               int iy, int iz, float v[3], float pass[3],
                                               float& inv_m, float vpre_nog[3]) {
@@ -88,9 +159,12 @@ __device__ __forceinline__ void node_velocity(const neuma_mpm_const& c, const fl
   }
 }
 
+// the rollout grids store a BC-zeroed velocity component as -0.0f (numerically 0 for G2P, and
+// exactly the "no gradient passes" mask the adjoint needs)
+constexpr uint32_t NEG_ZERO = 0x80000000u;
 
-// one particle's 27 node visits of p2g (mpm.py:321-371) into a packed (mv, m) grid
-__device__ __forceinline__ void p2g_particle(const neuma_mpm_const& c, int p,
+// ---- P2G: one particle's 27 node visits (mpm.py:321-371) into a packed (mv, m) grid --------
+__device__ __forceinline__ void p2g_particle(const neuma_mpm_const& c, const GridMap& gm, int p,
                                              const float* __restrict__ x,
                                              const float* __restrict__ v,
                                              const float* __restrict__ C,
@@ -110,7 +184,7 @@ __device__ __forceinline__ void p2g_particle(const neuma_mpm_const& c, int p,
 #pragma unroll
       for (int kk = 0; kk < 3; ++kk) {
         const int ix = s.b[0] + i, iy = s.b[1] + j, iz = s.b[2] + kk;
-        if (!node_in_range(c, ix, iy, iz)) continue;
+        if (!node_in_range(gm, ix, iy, iz)) continue;
         const float d0 = ((float)i - s.f[0]) * c.dx;
         const float d1 = ((float)j - s.f[1]) * c.dx;
         const float d2 = ((float)kk - s.f[2]) * c.dx;
@@ -118,10 +192,80 @@ __device__ __forceinline__ void p2g_particle(const neuma_mpm_const& c, int p,
         const float m0 = w * (pv[0] + (A[0] * d0 + A[1] * d1 + A[2] * d2));
         const float m1 = w * (pv[1] + (A[3] * d0 + A[4] * d1 + A[5] * d2));
         const float m2 = w * (pv[2] + (A[6] * d0 + A[7] * d1 + A[8] * d2));
-        red_add_f4(grid + node_index(c, ix, iy, iz), m0, m1, m2, w * p_mass);
+        red_add_f4(grid + node_index(gm, ix, iy, iz), m0, m1, m2, w * p_mass);
       }
 }
 
+// ---- G2P: one particle (mpm.py:432-498).  LAZY: the grid holds (mv, m) and grid_op is
+// evaluated per gathered node; otherwise it holds v.  Writes x', v', C', F'; returns x' in nx3.
+template <bool LAZY>
+__device__ __forceinline__ void g2p_particle(const neuma_mpm_const& c, const GridMap& gm, int p,
+                                             const float* __restrict__ x, const float* __restrict__ F,
+                                             const float* __restrict__ clip,
+                                             const float4* __restrict__ grid, float* __restrict__ x2,
+                                             float* __restrict__ v2, float* __restrict__ C2,
+                                             float* __restrict__ F2, float nx3[3]) {
+  const float px[3] = {x[3 * p], x[3 * p + 1], x[3 * p + 2]};
+  const Stencil s = make_stencil(px[0], px[1], px[2], c.inv_dx);
+  float nv[3] = {0.f, 0.f, 0.f};
+  float nC[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const float k4 = 4.0f * c.inv_dx * c.inv_dx;
+#pragma unroll
+  for (int kk = 0; kk < 3; ++kk)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const int ix = s.b[0] + i, iy = s.b[1] + j, iz = s.b[2] + kk;
+        if (!node_in_range(gm, ix, iy, iz)) continue;
+        const float4 q = grid[node_index(gm, ix, iy, iz)];
+        float gv[3];
+        if (LAZY) {
+          float pass[3], inv_m, vp[3];
+          node_velocity(c, q, ix, iy, iz, gv, pass, inv_m, vp);
+        } else {
+          gv[0] = q.x; gv[1] = q.y; gv[2] = q.z;
+        }
+        const float d[3] = {((float)i - s.f[0]) * c.dx, ((float)j - s.f[1]) * c.dx,
+                            ((float)kk - s.f[2]) * c.dx};
+        const float w = s.w[0][i] * s.w[1][j] * s.w[2][kk];
+        const float w4 = k4 * w;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          nv[a] += w * gv[a];
+#pragma unroll
+          for (int b = 0; b < 3; ++b) nC[3 * a + b] += w4 * (gv[a] * d[b]);
+        }
+      }
+  // F' = (I + dt C') F   (mpm.py:487)
+  float Fo[9], Fn[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) Fo[i] = F[9 * p + i];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+        acc += ((a == k ? 1.0f : 0.0f) + c.dt * nC[3 * a + k]) * Fo[3 * k + b];
+      Fn[3 * a + b] = acc;
+    }
+  const float bnd = clip[p] * c.dx;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    float nx = px[a] + c.dt * nv[a];
+    nx = fminf(fmaxf(nx, 0.0f + bnd), 1.0f - bnd);
+    nx3[a] = nx;
+    x2[3 * p + a] = nx;
+    v2[3 * p + a] = nv[a];
+  }
+#pragma unroll
+  for (int i = 0; i < 9; ++i) {
+    C2[9 * p + i] = nC[i];
+    F2[9 * p + i] = Fn[i];
+  }
+}
 
 // Upstream gradients of one particle's G2P outputs folded into the two
 // quantities the grid sees: gvt = dL/dv' (incl. the x' = clamp(x + dt v') path)
@@ -163,5 +307,174 @@ __device__ __forceinline__ G2PAdj g2p_adjoint_inputs(const neuma_mpm_const& c, i
   return r;
 }
 
+// ---- backward pass 1: scatter adj(G2P)'s dL/dv_node of one particle into gadj (xyz; w unused)
+__device__ __forceinline__ void g2p_adjoint_scatter(const neuma_mpm_const& c, const GridMap& gm, int p,
+                                                    const float* __restrict__ x, const G2PAdj& g,
+                                                    float4* __restrict__ gadj) {
+  const Stencil s = make_stencil(x[3 * p], x[3 * p + 1], x[3 * p + 2], c.inv_dx);
+  const float k4 = 4.0f * c.inv_dx * c.inv_dx;
+#pragma unroll
+  for (int kk = 0; kk < 3; ++kk)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const int ix = s.b[0] + i, iy = s.b[1] + j, iz = s.b[2] + kk;
+        if (!node_in_range(gm, ix, iy, iz)) continue;
+        const float d[3] = {((float)i - s.f[0]) * c.dx, ((float)j - s.f[1]) * c.dx,
+                            ((float)kk - s.f[2]) * c.dx};
+        const float w = s.w[0][i] * s.w[1][j] * s.w[2][kk];
+        float o[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+          o[a] = w * (g.gvt[a] + k4 * (g.gCt[3 * a] * d[0] + g.gCt[3 * a + 1] * d[1] +
+                                       g.gCt[3 * a + 2] * d[2]));
+        red_add_f4(gadj + node_index(gm, ix, iy, iz), o[0], o[1], o[2], 0.0f);
+      }
+}
+
+// ---- backward pass 3, one particle: gather its 27 nodes and accumulate adj(G2P) (the terms
+// that need v_node) and adj(P2G).
+//   LAZY  : `grid` holds (mv, m), `gadj` holds dL/dv_node; grid_op and its adjoint are evaluated
+//           per visit (per-substep entry points: no node pass);
+//   !LAZY : `grid` holds (v, m), `gadj` holds (dL/dmv, dL/dm) left by the node pass (rollout).
+// HAVE_C2: C2 is the forward's C'; otherwise it is recomputed from the gathered velocities.
+template <bool LAZY, bool HAVE_C2>
+__device__ __forceinline__ void bwd_gather_particle(
+    const neuma_mpm_const& c, const GridMap& gm, int p, const float* __restrict__ x,
+    const float* __restrict__ v, const float* __restrict__ C, const float* __restrict__ F,
+    const float* __restrict__ stress, const float* __restrict__ vol, const float* __restrict__ rho,
+    const float* __restrict__ clip, const float* __restrict__ v2, const float* __restrict__ C2,
+    const float* __restrict__ gx2, const float* __restrict__ gv2, const float* __restrict__ gC2,
+    const float* __restrict__ gF2, const float4* __restrict__ grid, const float4* __restrict__ gadj,
+    float* __restrict__ gx, float* __restrict__ gv, float* __restrict__ gC, float* __restrict__ gF,
+    float* __restrict__ gstress) {
+  const float p_vol = vol[p];
+  const float p_mass = p_vol * rho[p];
+  const Stencil s = make_stencil(x[3 * p], x[3 * p + 1], x[3 * p + 2], c.inv_dx);
+  const float ks = -c.dt * p_vol * 4.0f * c.inv_dx * c.inv_dx;
+  const float k4 = 4.0f * c.inv_dx * c.inv_dx;
+  float A[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) A[i] = ks * stress[9 * p + i] + p_mass * C[9 * p + i];
+  const float pv[3] = {p_mass * v[3 * p], p_mass * v[3 * p + 1], p_mass * v[3 * p + 2]};
+  const G2PAdj g = g2p_adjoint_inputs(c, p, x, F, clip, v2, gx2, gv2, gC2, gF2);
+  constexpr bool need_C = !HAVE_C2;
+
+  float acc_gmv[3] = {0.f, 0.f, 0.f};  // sum_n W g_mv
+  float gA[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float gd[3] = {0.f, 0.f, 0.f};       // sum_n dL/d dpos_n
+  float gw[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+  float nC[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // recomputed C'
+#pragma unroll
+  for (int kk = 0; kk < 3; ++kk)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const int ix = s.b[0] + i, iy = s.b[1] + j, iz = s.b[2] + kk;
+        if (!node_in_range(gm, ix, iy, iz)) continue;
+        const size_t ni = node_index(gm, ix, iy, iz);
+        const float4 q = grid[ni];
+        const float4 ga = gadj[ni];
+        float vn[3], gmv[3], gmn;
+        if (LAZY) {
+          float pass[3], inv_m, vp[3];
+          node_velocity(c, q, ix, iy, iz, vn, pass, inv_m, vp);
+          // adj(grid_op): v = mv/(m+eps) + g dt
+          const float gvn[3] = {ga.x * pass[0], ga.y * pass[1], ga.z * pass[2]};
+          gmv[0] = gvn[0] * inv_m; gmv[1] = gvn[1] * inv_m; gmv[2] = gvn[2] * inv_m;
+          gmn = -(vp[0] * gvn[0] + vp[1] * gvn[1] + vp[2] * gvn[2]) * inv_m;
+        } else {
+          vn[0] = q.x; vn[1] = q.y; vn[2] = q.z;
+          gmv[0] = ga.x; gmv[1] = ga.y; gmv[2] = ga.z;
+          gmn = ga.w;
+        }
+        const float d[3] = {((float)i - s.f[0]) * c.dx, ((float)j - s.f[1]) * c.dx,
+                            ((float)kk - s.f[2]) * c.dx};
+        const float w = s.w[0][i] * s.w[1][j] * s.w[2][kk];
+        // --- adj(G2P) terms that need v_node
+        float gCt_d[3], gCtT_v[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          gCt_d[a] = g.gCt[3 * a] * d[0] + g.gCt[3 * a + 1] * d[1] + g.gCt[3 * a + 2] * d[2];
+          gCtT_v[a] = g.gCt[a] * vn[0] + g.gCt[3 + a] * vn[1] + g.gCt[6 + a] * vn[2];
+        }
+        float gW = vn[0] * g.gvt[0] + vn[1] * g.gvt[1] + vn[2] * g.gvt[2] +
+                   k4 * (vn[0] * gCt_d[0] + vn[1] * gCt_d[1] + vn[2] * gCt_d[2]);
+        // --- adj(P2G)
+        float Ad[3], ATg[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          Ad[a] = A[3 * a] * d[0] + A[3 * a + 1] * d[1] + A[3 * a + 2] * d[2];
+          ATg[a] = A[a] * gmv[0] + A[3 + a] * gmv[1] + A[6 + a] * gmv[2];
+        }
+        gW += gmv[0] * (pv[0] + Ad[0]) + gmv[1] * (pv[1] + Ad[1]) + gmv[2] * (pv[2] + Ad[2]) +
+              gmn * p_mass;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          acc_gmv[a] += w * gmv[a];
+          gd[a] += w * (k4 * gCtT_v[a] + ATg[a]);
+#pragma unroll
+          for (int b = 0; b < 3; ++b) {
+            gA[3 * a + b] += w * (gmv[a] * d[b]);
+            if (need_C) nC[3 * a + b] += (k4 * w) * (vn[a] * d[b]);
+          }
+        }
+        gw[0][i] += gW * (s.w[1][j] * s.w[2][kk]);
+        gw[1][j] += gW * (s.w[0][i] * s.w[2][kk]);
+        gw[2][kk] += gW * (s.w[0][i] * s.w[1][j]);
+      }
+  // weights -> fx: dw0/df = -(1.5 - f), dw1/df = -2 (f - 1), dw2/df = f - 0.5
+  // dpos = (offset - fx) dx -> dL/dfx -= dx * gd ;  fx = x * inv_dx - base
+  if (gx) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const float f = s.f[a];
+      float gf = gw[a][0] * (-(1.5f - f)) + gw[a][1] * (-2.0f * (f - 1.0f)) + gw[a][2] * (f - 0.5f);
+      gf -= c.dx * gd[a];
+      gx[3 * p + a] = finite_or_zero(g.gxn[a] + c.inv_dx * gf);
+    }
+  }
+  if (gv) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) gv[3 * p + a] = finite_or_zero(p_mass * acc_gmv[a]);
+  }
+  if (gC) {
+#pragma unroll
+    for (int a = 0; a < 9; ++a) gC[9 * p + a] = finite_or_zero(p_mass * gA[a]);
+  }
+  if (gstress) {
+#pragma unroll
+    for (int a = 0; a < 9; ++a) gstress[9 * p + a] = finite_or_zero(ks * gA[a]);
+  }
+  if (gF) {
+    if (!need_C) {
+#pragma unroll
+      for (int a = 0; a < 9; ++a) nC[a] = C2[9 * p + a];
+    }
+    // gF = (I + dt C')^T gF'
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b) {
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+          acc += ((a == k ? 1.0f : 0.0f) + c.dt * nC[3 * k + a]) * gF2[9 * p + 3 * k + b];
+        gF[9 * p + 3 * a + b] = finite_or_zero(acc);
+      }
+  }
+}
+
+// disabled particles: the reference's kernels return early, no adjoint contribution
+__device__ __forceinline__ void zero_particle_grads(int p, float* gx, float* gv, float* gC, float* gF,
+                                                    float* gstress) {
+  if (gx) for (int a = 0; a < 3; ++a) gx[3 * p + a] = 0.f;
+  if (gv) for (int a = 0; a < 3; ++a) gv[3 * p + a] = 0.f;
+  if (gC) for (int a = 0; a < 9; ++a) gC[9 * p + a] = 0.f;
+  if (gF) for (int a = 0; a < 9; ++a) gF[9 * p + a] = 0.f;
+  if (gstress) for (int a = 0; a < 9; ++a) gstress[9 * p + a] = 0.f;
+}
 
 }  // namespace

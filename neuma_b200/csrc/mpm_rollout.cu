@@ -20,20 +20,9 @@
 // lanes then touch neighbouring nodes, so the 27 node visits of a warp coalesce in L1/L2.
 #include "mpm_common.cuh"
 #include <cub/device/device_radix_sort.cuh>
-#include <limits.h>
 #include <stdlib.h>
 
 namespace {
-
-struct Box {
-  int lo[3], hi[3];
-};
-__device__ __forceinline__ Box load_box(const int32_t* __restrict__ b) {
-  Box r;
-#pragma unroll
-  for (int a = 0; a < 3; ++a) { r.lo[a] = b[a]; r.hi[a] = b[3 + a]; }
-  return r;
-}
 
 __global__ void box_init_kernel(int32_t* box) {
   if (threadIdx.x < 3) box[threadIdx.x] = INT_MAX;
@@ -47,14 +36,21 @@ __device__ __forceinline__ void box_accumulate(const neuma_mpm_const& c, bool ac
                                                int* sbox /* shared int[6] */) {
   int lo[3] = {INT_MAX, INT_MAX, INT_MAX}, hi[3] = {INT_MIN, INT_MIN, INT_MIN};
   if (active) {
-    const float p[3] = {x0 * c.inv_dx, x1 * c.inv_dx, x2 * c.inv_dx};
+    const float p[3] = {x0, x1, x2};
     const int mn[3] = {0, 0, c.z_off}, mx[3] = {c.num_grids - 1, c.num_grids - 1, c.z_off + c.nz - 1};
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-      const int b = (int)(p[a] - 0.5f);
+      const int b = base_node(p[a], c.inv_dx);
       lo[a] = max(b, mn[a]);
       hi[a] = min(b + 2, mx[a]);
     }
+    // Z-slab ownership: a particle whose stencil needs a plane this rank does not
+    // hold would silently lose node visits -- count it in box[7]; the host raises
+    // (SlabRollout.check_drift).  The top of the DOMAIN is the reference's latent OOB, not drift.
+    const int bz = base_node(p[2], c.inv_dx);
+    const bool below = bz < c.z_off;
+    const bool above = bz + 2 > c.z_off + c.nz - 1 && c.z_off + c.nz < c.num_grids;
+    if (below || above) atomicAdd(&box[7], 1);
   }
   if (threadIdx.x < 6) sbox[threadIdx.x] = threadIdx.x < 3 ? INT_MAX : INT_MIN;
   __syncthreads();
@@ -83,49 +79,50 @@ box_reduce_kernel(neuma_mpm_const c, int n, const float* __restrict__ x,
   box_accumulate(c, active, px[0], px[1], px[2], box, sbox);
 }
 
-// iteration space of the node passes: the box, x-range widened to 128-byte rows
+// iteration space of the node passes: the box window (x-range widened to 128-byte rows)
 struct BoxIter {
-  int x0, nx, ny, y0, z0;
+  GridMap w;       // window iterated over
+  GridMap m;       // where the nodes live (== w in compact mode)
   long long total;
 };
-__device__ __forceinline__ BoxIter box_iter(const neuma_mpm_const& c, const Box& b) {
+__device__ __forceinline__ BoxIter box_iter(const neuma_mpm_const& c, const int32_t* __restrict__ box) {
   BoxIter it;
-  if (b.lo[0] > b.hi[0] || b.lo[1] > b.hi[1] || b.lo[2] > b.hi[2]) {
-    it.total = 0; it.x0 = it.nx = it.ny = it.y0 = it.z0 = 0;
-    return it;
+  it.w = box_window(c, load_box(box));
+  if (c.compact) {
+    if (map_overflows(c, it.w)) it.w.nx = it.w.ny = it.w.nz = 0;
+    it.m = it.w;
+  } else {
+    it.m = GridMap{0, 0, c.z_off, c.num_grids, c.num_grids, c.nz};
   }
-  it.x0 = b.lo[0] & ~7;
-  const int x1 = min(c.num_grids - 1, b.hi[0] | 7);
-  it.nx = x1 - it.x0 + 1;
-  it.y0 = b.lo[1];
-  it.ny = b.hi[1] - b.lo[1] + 1;
-  it.z0 = b.lo[2];
-  it.total = (long long)it.nx * it.ny * (b.hi[2] - b.lo[2] + 1);
+  it.total = map_nodes(it.w);
   return it;
 }
-__device__ __forceinline__ size_t box_node(const neuma_mpm_const& c, const BoxIter& it, long long i,
-                                           int& ix, int& iy, int& iz) {
-  const int row = (int)(i / it.nx);
-  ix = it.x0 + (int)(i - (long long)row * it.nx);
-  const int pl = row / it.ny;
-  iy = it.y0 + (row - pl * it.ny);
-  iz = it.z0 + pl;
-  return node_index(c, ix, iy, iz);
+__device__ __forceinline__ size_t box_node(const BoxIter& it, long long i, int& ix, int& iy, int& iz) {
+  const int row = (int)(i / it.w.nx);
+  ix = it.w.x0 + (int)(i - (long long)row * it.w.nx);
+  const int pl = row / it.w.ny;
+  iy = it.w.y0 + (row - pl * it.w.ny);
+  iz = it.w.z0 + pl;
+  return node_index(it.m, ix, iy, iz);
 }
 
-// zero the box region of up to two grids; optionally reset another box to "empty"
+// zero the box region of up to two grids; optionally reset another box to "empty".
+// Compact mode: raises box[6] when the box does not fit c.cap_nodes.
 __global__ void __launch_bounds__(256)
-box_clear_kernel(neuma_mpm_const c, const int32_t* __restrict__ box, float4* __restrict__ g0,
+box_clear_kernel(neuma_mpm_const c, int32_t* __restrict__ box, float4* __restrict__ g0,
                  float4* __restrict__ g1, int32_t* __restrict__ box_reset) {
   pdl_prologue();
   if (box_reset && blockIdx.x == 0 && threadIdx.x < 8)
     box_reset[threadIdx.x] = threadIdx.x < 3 ? INT_MAX : (threadIdx.x < 6 ? INT_MIN : 0);
-  const BoxIter it = box_iter(c, load_box(box));
+  if (c.compact && blockIdx.x == 0 && threadIdx.x == 0 &&
+      map_overflows(c, box_window(c, load_box(box))))
+    box[6] = 1;
+  const BoxIter it = box_iter(c, box);
   const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < it.total;
        i += (long long)gridDim.x * blockDim.x) {
     int ix, iy, iz;
-    const size_t ni = box_node(c, it, i, ix, iy, iz);
+    const size_t ni = box_node(it, i, ix, iy, iz);
     if (g0) g0[ni] = z;
     if (g1) g1[ni] = z;
   }
@@ -135,15 +132,15 @@ __global__ void __launch_bounds__(256)
 p2g_to_kernel(neuma_mpm_const c, int n, const float* __restrict__ x, const float* __restrict__ v,
               const float* __restrict__ C, const float* __restrict__ stress,
               const float* __restrict__ vol, const float* __restrict__ rho,
-              const int* __restrict__ enabled, float4* __restrict__ grid) {
+              const int* __restrict__ enabled, const int32_t* __restrict__ box,
+              float4* __restrict__ grid) {
   pdl_prologue();
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
-  if (enabled[p] == 0) return;
-  p2g_particle(c, p, x, v, C, stress, vol[p], rho[p], grid);
+  if (enabled[p] == 0 || !particle_selected(c, x[3 * p + 2])) return;
+  const GridMap gm = grid_map(c, box);
+  p2g_particle(c, gm, p, x, v, C, stress, vol[p], rho[p], grid);
 }
-
-constexpr uint32_t NEG_ZERO = 0x80000000u;
 
 // grid_op over the box, in place: (mv, m) -> (v, m); BC-zeroed components become -0.0f.
 // Optionally zeroes the same nodes of `adj` (the backward's scatter target).
@@ -151,19 +148,22 @@ __global__ void __launch_bounds__(256)
 grid_op_box_kernel(neuma_mpm_const c, const int32_t* __restrict__ box, float4* __restrict__ grid,
                    float4* __restrict__ adj) {
   pdl_prologue();
-  const BoxIter it = box_iter(c, load_box(box));
+  const BoxIter it = box_iter(c, box);
   const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < it.total;
        i += (long long)gridDim.x * blockDim.x) {
     int ix, iy, iz;
-    const size_t ni = box_node(c, it, i, ix, iy, iz);
+    const size_t ni = box_node(it, i, ix, iy, iz);
+    if (!plane_selected(c, iz)) continue;
     const float4 q = grid[ni];
     float v[3], pass[3], inv_m, vp[3];
     node_velocity(c, q, ix, iy, iz, v, pass, inv_m, vp);
-    if (q.w > 0.0f) {
 #pragma unroll
-      for (int a = 0; a < 3; ++a)
-        if (pass[a] == 0.0f) v[a] = __uint_as_float(NEG_ZERO);
+    for (int a = 0; a < 3; ++a) {
+      // canonical +0: a computed -0.0f (e.g. gravity passed as -0.0 on an empty node) must not
+      // be mistaken for the sentinel below
+      v[a] = v[a] + 0.0f;
+      if (q.w > 0.0f && pass[a] == 0.0f) v[a] = __uint_as_float(NEG_ZERO);
     }
     grid[ni] = make_float4(v[0], v[1], v[2], q.w);
     if (adj) adj[ni] = z;
@@ -176,67 +176,17 @@ template <bool WITH_BOX>
 __global__ void __launch_bounds__(256)
 g2p_from_kernel(neuma_mpm_const c, int n, const float* __restrict__ x, const float* __restrict__ F,
                 const float* __restrict__ clip, const int* __restrict__ enabled,
-                const float4* __restrict__ grid, float* __restrict__ x2, float* __restrict__ v2,
-                float* __restrict__ C2, float* __restrict__ F2, int32_t* __restrict__ box_next) {
+                const int32_t* __restrict__ box, const float4* __restrict__ grid,
+                float* __restrict__ x2, float* __restrict__ v2, float* __restrict__ C2,
+                float* __restrict__ F2, int32_t* __restrict__ box_next) {
   pdl_prologue();
   __shared__ int sbox[6];
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool active = p < n && enabled[p] != 0;
+  const bool active = p < n && enabled[p] != 0 && particle_selected(c, x[3 * p + 2]);
   float nx3[3] = {0.f, 0.f, 0.f};
   if (active) {
-    const float px[3] = {x[3 * p], x[3 * p + 1], x[3 * p + 2]};
-    const Stencil s = make_stencil(px[0], px[1], px[2], c.inv_dx);
-    float nv[3] = {0.f, 0.f, 0.f};
-    float nC[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    const float k4 = 4.0f * c.inv_dx * c.inv_dx;
-#pragma unroll
-    for (int kk = 0; kk < 3; ++kk)
-#pragma unroll
-      for (int j = 0; j < 3; ++j)
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          const int ix = s.b[0] + i, iy = s.b[1] + j, iz = s.b[2] + kk;
-          if (!node_in_range(c, ix, iy, iz)) continue;
-          const float4 q = grid[node_index(c, ix, iy, iz)];
-          const float gv[3] = {q.x, q.y, q.z};
-          const float d[3] = {((float)i - s.f[0]) * c.dx, ((float)j - s.f[1]) * c.dx,
-                              ((float)kk - s.f[2]) * c.dx};
-          const float w = s.w[0][i] * s.w[1][j] * s.w[2][kk];
-          const float w4 = k4 * w;
-#pragma unroll
-          for (int a = 0; a < 3; ++a) {
-            nv[a] += w * gv[a];
-#pragma unroll
-            for (int b = 0; b < 3; ++b) nC[3 * a + b] += w4 * (gv[a] * d[b]);
-          }
-        }
-    float Fo[9], Fn[9];
-#pragma unroll
-    for (int i = 0; i < 9; ++i) Fo[i] = F[9 * p + i];
-#pragma unroll
-    for (int a = 0; a < 3; ++a)
-#pragma unroll
-      for (int b = 0; b < 3; ++b) {
-        float acc = 0.f;
-#pragma unroll
-        for (int k = 0; k < 3; ++k)
-          acc += ((a == k ? 1.0f : 0.0f) + c.dt * nC[3 * a + k]) * Fo[3 * k + b];
-        Fn[3 * a + b] = acc;
-      }
-    const float bnd = clip[p] * c.dx;
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      float nx = px[a] + c.dt * nv[a];
-      nx = fminf(fmaxf(nx, 0.0f + bnd), 1.0f - bnd);
-      nx3[a] = nx;
-      x2[3 * p + a] = nx;
-      v2[3 * p + a] = nv[a];
-    }
-#pragma unroll
-    for (int i = 0; i < 9; ++i) {
-      C2[9 * p + i] = nC[i];
-      F2[9 * p + i] = Fn[i];
-    }
+    const GridMap gm = grid_map(c, box);
+    g2p_particle<false>(c, gm, p, x, F, clip, grid, x2, v2, C2, F2, nx3);
   }
   if (WITH_BOX) box_accumulate(c, active, nx3[0], nx3[1], nx3[2], box_next, sbox);
 }
@@ -248,32 +198,14 @@ bwd_scatter_adj_kernel(neuma_mpm_const c, int n, const float* __restrict__ x,
                        const int* __restrict__ enabled, const float* __restrict__ v2,
                        const float* __restrict__ gx2, const float* __restrict__ gv2,
                        const float* __restrict__ gC2, const float* __restrict__ gF2,
-                       float4* __restrict__ gadj) {
+                       const int32_t* __restrict__ box, float4* __restrict__ gadj) {
   pdl_prologue();
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
-  if (enabled[p] == 0) return;
+  if (enabled[p] == 0 || !particle_selected(c, x[3 * p + 2])) return;
+  const GridMap gm = grid_map(c, box);
   const G2PAdj g = g2p_adjoint_inputs(c, p, x, F, clip, v2, gx2, gv2, gC2, gF2);
-  const Stencil s = make_stencil(x[3 * p], x[3 * p + 1], x[3 * p + 2], c.inv_dx);
-  const float k4 = 4.0f * c.inv_dx * c.inv_dx;
-#pragma unroll
-  for (int kk = 0; kk < 3; ++kk)
-#pragma unroll
-    for (int j = 0; j < 3; ++j)
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        const int ix = s.b[0] + i, iy = s.b[1] + j, iz = s.b[2] + kk;
-        if (!node_in_range(c, ix, iy, iz)) continue;
-        const float d[3] = {((float)i - s.f[0]) * c.dx, ((float)j - s.f[1]) * c.dx,
-                            ((float)kk - s.f[2]) * c.dx};
-        const float w = s.w[0][i] * s.w[1][j] * s.w[2][kk];
-        float o[3];
-#pragma unroll
-        for (int a = 0; a < 3; ++a)
-          o[a] = w * (g.gvt[a] + k4 * (g.gCt[3 * a] * d[0] + g.gCt[3 * a + 1] * d[1] +
-                                       g.gCt[3 * a + 2] * d[2]));
-        red_add_f4(gadj + node_index(c, ix, iy, iz), o[0], o[1], o[2], 0.0f);
-      }
+  g2p_adjoint_scatter(c, gm, p, x, g, gadj);
 }
 
 // backward pass 2, per node of the box: adj(grid_op).  (v, m) and dL/dv -> (dL/dmv, dL/dm),
@@ -283,12 +215,13 @@ __global__ void __launch_bounds__(256)
 bwd_node_kernel(neuma_mpm_const c, const int32_t* __restrict__ box,
                 const float4* __restrict__ grid, float4* __restrict__ adj) {
   pdl_prologue();
-  const BoxIter it = box_iter(c, load_box(box));
+  const BoxIter it = box_iter(c, box);
   const float gdt[3] = {c.gravity[0] * c.dt, c.gravity[1] * c.dt, c.gravity[2] * c.dt};
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < it.total;
        i += (long long)gridDim.x * blockDim.x) {
     int ix, iy, iz;
-    const size_t ni = box_node(c, it, i, ix, iy, iz);
+    const size_t ni = box_node(it, i, ix, iy, iz);
+    if (!plane_selected(c, iz)) continue;
     const float4 q = grid[ni];
     const float4 ga = adj[ni];
     const bool has = q.w > 0.0f;
@@ -317,120 +250,20 @@ bwd_gather_v_kernel(neuma_mpm_const c, int n, const float* __restrict__ x,
                     const float* __restrict__ v2, const float* __restrict__ C2,
                     const float* __restrict__ gx2, const float* __restrict__ gv2,
                     const float* __restrict__ gC2, const float* __restrict__ gF2,
-                    const float4* __restrict__ grid, const float4* __restrict__ gadj,
-                    float* __restrict__ gx, float* __restrict__ gv, float* __restrict__ gC,
-                    float* __restrict__ gF, float* __restrict__ gstress) {
+                    const int32_t* __restrict__ box, const float4* __restrict__ grid,
+                    const float4* __restrict__ gadj, float* __restrict__ gx, float* __restrict__ gv,
+                    float* __restrict__ gC, float* __restrict__ gF, float* __restrict__ gstress) {
   pdl_prologue();
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
+  if (!particle_selected(c, x[3 * p + 2])) return;      // the other class's launch writes these rows
   if (enabled[p] == 0) {
-    if (gx) for (int a = 0; a < 3; ++a) gx[3 * p + a] = 0.f;
-    if (gv) for (int a = 0; a < 3; ++a) gv[3 * p + a] = 0.f;
-    if (gC) for (int a = 0; a < 9; ++a) gC[9 * p + a] = 0.f;
-    if (gF) for (int a = 0; a < 9; ++a) gF[9 * p + a] = 0.f;
-    if (gstress) for (int a = 0; a < 9; ++a) gstress[9 * p + a] = 0.f;
+    zero_particle_grads(p, gx, gv, gC, gF, gstress);
     return;
   }
-  const float p_vol = vol[p];
-  const float p_mass = p_vol * rho[p];
-  const Stencil s = make_stencil(x[3 * p], x[3 * p + 1], x[3 * p + 2], c.inv_dx);
-  const float ks = -c.dt * p_vol * 4.0f * c.inv_dx * c.inv_dx;
-  const float k4 = 4.0f * c.inv_dx * c.inv_dx;
-  float A[9];
-#pragma unroll
-  for (int i = 0; i < 9; ++i) A[i] = ks * stress[9 * p + i] + p_mass * C[9 * p + i];
-  const float pv[3] = {p_mass * v[3 * p], p_mass * v[3 * p + 1], p_mass * v[3 * p + 2]};
-  const G2PAdj g = g2p_adjoint_inputs(c, p, x, F, clip, v2, gx2, gv2, gC2, gF2);
-
-  float acc_gmv[3] = {0.f, 0.f, 0.f};
-  float gA[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  float gd[3] = {0.f, 0.f, 0.f};
-  float gw[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
-  float nC[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-  for (int kk = 0; kk < 3; ++kk)
-#pragma unroll
-    for (int j = 0; j < 3; ++j)
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        const int ix = s.b[0] + i, iy = s.b[1] + j, iz = s.b[2] + kk;
-        if (!node_in_range(c, ix, iy, iz)) continue;
-        const size_t ni = node_index(c, ix, iy, iz);
-        const float4 q = grid[ni];
-        const float4 ga = gadj[ni];
-        const float vn[3] = {q.x, q.y, q.z};
-        const float gmv[3] = {ga.x, ga.y, ga.z};
-        const float gm = ga.w;
-        const float d[3] = {((float)i - s.f[0]) * c.dx, ((float)j - s.f[1]) * c.dx,
-                            ((float)kk - s.f[2]) * c.dx};
-        const float w = s.w[0][i] * s.w[1][j] * s.w[2][kk];
-        float gCt_d[3], gCtT_v[3];
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-          gCt_d[a] = g.gCt[3 * a] * d[0] + g.gCt[3 * a + 1] * d[1] + g.gCt[3 * a + 2] * d[2];
-          gCtT_v[a] = g.gCt[a] * vn[0] + g.gCt[3 + a] * vn[1] + g.gCt[6 + a] * vn[2];
-        }
-        float gW = vn[0] * g.gvt[0] + vn[1] * g.gvt[1] + vn[2] * g.gvt[2] +
-                   k4 * (vn[0] * gCt_d[0] + vn[1] * gCt_d[1] + vn[2] * gCt_d[2]);
-        float Ad[3], ATg[3];
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-          Ad[a] = A[3 * a] * d[0] + A[3 * a + 1] * d[1] + A[3 * a + 2] * d[2];
-          ATg[a] = A[a] * gmv[0] + A[3 + a] * gmv[1] + A[6 + a] * gmv[2];
-        }
-        gW += gmv[0] * (pv[0] + Ad[0]) + gmv[1] * (pv[1] + Ad[1]) + gmv[2] * (pv[2] + Ad[2]) +
-              gm * p_mass;
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-          acc_gmv[a] += w * gmv[a];
-          gd[a] += w * (k4 * gCtT_v[a] + ATg[a]);
-#pragma unroll
-          for (int b = 0; b < 3; ++b) {
-            gA[3 * a + b] += w * (gmv[a] * d[b]);
-            if (!HAVE_C2) nC[3 * a + b] += (k4 * w) * (vn[a] * d[b]);
-          }
-        }
-        gw[0][i] += gW * (s.w[1][j] * s.w[2][kk]);
-        gw[1][j] += gW * (s.w[0][i] * s.w[2][kk]);
-        gw[2][kk] += gW * (s.w[0][i] * s.w[1][j]);
-      }
-  if (gx) {
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      const float f = s.f[a];
-      float gf = gw[a][0] * (-(1.5f - f)) + gw[a][1] * (-2.0f * (f - 1.0f)) + gw[a][2] * (f - 0.5f);
-      gf -= c.dx * gd[a];
-      gx[3 * p + a] = finite_or_zero(g.gxn[a] + c.inv_dx * gf);
-    }
-  }
-  if (gv) {
-#pragma unroll
-    for (int a = 0; a < 3; ++a) gv[3 * p + a] = finite_or_zero(p_mass * acc_gmv[a]);
-  }
-  if (gC) {
-#pragma unroll
-    for (int a = 0; a < 9; ++a) gC[9 * p + a] = finite_or_zero(p_mass * gA[a]);
-  }
-  if (gstress) {
-#pragma unroll
-    for (int a = 0; a < 9; ++a) gstress[9 * p + a] = finite_or_zero(ks * gA[a]);
-  }
-  if (gF) {
-    if (HAVE_C2) {
-#pragma unroll
-      for (int a = 0; a < 9; ++a) nC[a] = C2[9 * p + a];
-    }
-#pragma unroll
-    for (int a = 0; a < 3; ++a)
-#pragma unroll
-      for (int b = 0; b < 3; ++b) {
-        float acc = 0.f;
-#pragma unroll
-        for (int k = 0; k < 3; ++k)
-          acc += ((a == k ? 1.0f : 0.0f) + c.dt * nC[3 * k + a]) * gF2[9 * p + 3 * k + b];
-        gF[9 * p + 3 * a + b] = finite_or_zero(acc);
-      }
-  }
+  const GridMap gm = grid_map(c, box);
+  bwd_gather_particle<false, HAVE_C2>(c, gm, p, x, v, C, F, stress, vol, rho, clip, v2, C2, gx2, gv2, gC2,
+                                      gF2, grid, gadj, gx, gv, gC, gF, gstress);
 }
 
 // ------------------------------------------------------------------ cell order
@@ -450,7 +283,7 @@ cell_key_kernel(neuma_mpm_const c, int n, const float* __restrict__ x, uint32_t*
   uint32_t b[3];
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
-    const int t = (int)(x[3 * p + a] * c.inv_dx - 0.5f);
+    const int t = base_node(x[3 * p + a], c.inv_dx);
     b[a] = (uint32_t)min(max(t, 0), 1023);
   }
   // z is the slowest grid axis: give it the most significant interleaved bit
@@ -550,6 +383,120 @@ halo_add_ack_kernel(float4* __restrict__ dst, const float4* mailbox, size_t n,
   }
 }
 
+// ---- ONE kernel per summing halo exchange, both neighbours ----------------------
+// Per side: push my shared planes -- only the x-y window my particles occupy (`box`) -- into the
+// neighbour's mailbox over NVLink, publish the exchange number; wait for the neighbour's push,
+// add ITS window of the mailbox into my planes, acknowledge.  Mailboxes are double-buffered
+// (slot = exchange number & 1), so the push waits only for the acknowledgement of exchange
+// seq - 2.  Work is split by (plane, y) ROW over the warps, identically in both phases: a warp
+// only ever adds into rows it pushed itself, so no block has to wait for another block of this
+// grid (no grid barrier; the grid may be partially resident next to a concurrent P2G).
+// Counters are monotonic: cnt[0] = exchanges done, cnt[1] / cnt[2] = blocks that finished the
+// push / add phase since the beginning of time.
+__global__ void __launch_bounds__(256)
+halo_exchange_kernel(neuma_halo_side lo, neuma_halo_side hi, neuma_mpm_const c,
+                     const int32_t* __restrict__ box, int32_t* __restrict__ cnt) {
+  __shared__ int s_seq;
+  __shared__ int s_hdr[2][4];
+  const neuma_halo_side side[2] = {lo, hi};
+  const int G = c.num_grids;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * (blockDim.x >> 5) + warp, nw = gridDim.x * (blockDim.x >> 5);
+  if (threadIdx.x == 0) {
+    const int seq = *reinterpret_cast<volatile int*>(cnt) + 1;
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
+      if (side[s].planes)
+        while (ld_acquire_sys(side[s].my_ack_flag) < seq - 2) __nanosleep(32);
+    s_seq = seq;
+  }
+  __syncthreads();
+  const int seq = s_seq, slot = seq & 1;
+  // my x-y window: dense-grid rows [y0, y0 + ny), nodes [x0, x0 + nx) (x0, nx multiples of 8)
+  GridMap w = box_window(c, load_box(box));
+  if (c.compact) w.nx = w.ny = 0;   // the slab path keeps x, y dense (fixed halo addresses)
+  const size_t plane = (size_t)G * G;
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    if (!side[s].planes) continue;
+    const float4* __restrict__ src = reinterpret_cast<const float4*>(side[s].planes);
+    float4* __restrict__ dst = reinterpret_cast<float4*>(side[s].peer_mail) + (size_t)slot * side[s].npl * plane;
+    for (int row = gw; row < side[s].npl * w.ny; row += nw) {
+      const int pl = row / w.ny, y = w.y0 + (row - pl * w.ny);
+      const size_t o = (size_t)pl * plane + (size_t)y * G + w.x0;
+      for (int xx = lane; xx < w.nx; xx += 32) dst[o + xx] = src[o + xx];
+    }
+    if (blockIdx.x == 0 && threadIdx.x < 4) {
+      const int h[4] = {w.x0, w.nx, w.y0, w.ny};
+      side[s].peer_hdr[slot * 4 + threadIdx.x] = h[threadIdx.x];
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // the block that finishes the push phase last has seen every other block's fence: it publishes
+    if (atomicAdd(&cnt[1], 1) == seq * (int)gridDim.x - 1) {
+      __threadfence_system();
+#pragma unroll
+      for (int s = 0; s < 2; ++s)
+        if (side[s].planes) st_release_sys(side[s].peer_data_flag, seq);
+    }
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
+      if (side[s].planes) {
+        while (ld_acquire_sys(side[s].my_data_flag) < seq) __nanosleep(32);
+        for (int k = 0; k < 4; ++k)
+          s_hdr[s][k] = *reinterpret_cast<const volatile int*>(side[s].my_hdr + slot * 4 + k);
+      }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    if (!side[s].planes) continue;
+    const int x0 = s_hdr[s][0], nx = s_hdr[s][1], y0 = s_hdr[s][2], ny = s_hdr[s][3];
+    float4* __restrict__ dst = reinterpret_cast<float4*>(side[s].planes);
+    const float4* src = reinterpret_cast<const float4*>(side[s].my_mail) + (size_t)slot * side[s].npl * plane;
+    // (a) rows of MY window, dealt exactly as in the push phase: the warp that pushed a row is
+    //     the one that adds into it
+    for (int row = gw; row < side[s].npl * w.ny; row += nw) {
+      const int pl = row / w.ny, y = w.y0 + (row - pl * w.ny);
+      if (y < y0 || y >= y0 + ny) continue;
+      const size_t o = (size_t)pl * plane + (size_t)y * G + x0;
+      for (int xx = lane; xx < nx; xx += 32) {
+        float4 a = dst[o + xx];
+        const float4 b = __ldcv(src + o + xx);  // written by the peer GPU: never from a stale L1 line
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        dst[o + xx] = a;
+      }
+    }
+    // (b) rows of the SENDER's window outside mine: nobody pushed them, any warp may add
+    for (int row = gw; row < side[s].npl * ny; row += nw) {
+      const int pl = row / ny, y = y0 + (row - pl * ny);
+      if (y >= w.y0 && y < w.y0 + w.ny) continue;
+      const size_t o = (size_t)pl * plane + (size_t)y * G + x0;
+      for (int xx = lane; xx < nx; xx += 32) {
+        float4 a = dst[o + xx];
+        const float4 b = __ldcv(src + o + xx);
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        dst[o + xx] = a;
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(&cnt[2], 1) == seq * (int)gridDim.x - 1) {
+      cnt[0] = seq;
+      __threadfence_system();
+#pragma unroll
+      for (int s = 0; s < 2; ++s)
+        if (side[s].planes) st_release_sys(side[s].peer_ack_flag, seq);   // slot may be overwritten at seq + 2
+    }
+  }
+}
+
+constexpr int NEUMA_HALO_BLOCKS = 64;
+
 inline int node_pass_blocks(neuma_ctx* ctx) { return ctx->num_sms * 8; }
 
 // threads per block of the per-particle kernels (NEUMA_MPM_BLOCK overrides; tuned in profiles/)
@@ -567,6 +514,7 @@ int check_slab(neuma_ctx* ctx, const neuma_mpm_const* c) {
   if (c->num_grids <= 0 || c->nz <= 0 || c->z_off < 0 || c->z_off + c->nz > c->num_grids + 4)
     return neuma_fail_msg(ctx, "neuma_mpm: bad grid extents");
   if (c->bc != 0 && c->bc != 1) return neuma_fail_msg(ctx, "neuma_mpm: bc must be 0 or 1");
+  if (c->compact && c->cap_nodes <= 0) return neuma_fail_msg(ctx, "neuma_mpm: compact grid without cap_nodes");
   return 0;
 }
 
@@ -586,7 +534,7 @@ int neuma_mpm_box_from_x(neuma_ctx* ctx, const neuma_mpm_const* c, int n, const 
   return 0;
 }
 
-int neuma_mpm_box_clear(neuma_ctx* ctx, const neuma_mpm_const* c, const int32_t* box, float* grid0,
+int neuma_mpm_box_clear(neuma_ctx* ctx, const neuma_mpm_const* c, int32_t* box, float* grid0,
                         float* grid1, int32_t* box_reset, void* stream) {
   if (int r = check_slab(ctx, c)) return r;
   NEUMA_CUDA(ctx, neuma_launch(box_clear_kernel, dim3(node_pass_blocks(ctx)), dim3(256), 0, (cudaStream_t)stream,
@@ -597,12 +545,13 @@ int neuma_mpm_box_clear(neuma_ctx* ctx, const neuma_mpm_const* c, const int32_t*
 
 int neuma_mpm_p2g_to(neuma_ctx* ctx, const neuma_mpm_const* c, int n, const float* x, const float* v,
                      const float* C, const float* stress, const float* vol, const float* rho,
-                     const int32_t* enabled, float* grid, void* stream) {
+                     const int32_t* enabled, const int32_t* box, float* grid, void* stream) {
   if (int r = check_slab(ctx, c)) return r;
   if (n <= 0) return 0;
+  if (c->compact && !box) return neuma_fail_msg(ctx, "neuma_mpm_p2g_to: a compact grid needs its box");
   const int pb = pblock(256);
   NEUMA_CUDA(ctx, neuma_launch(p2g_to_kernel, dim3((n + pb - 1) / pb), dim3(pb), 0, (cudaStream_t)stream, *c, n, x,
-                               v, C, stress, vol, rho, enabled, (float4*)grid));
+                               v, C, stress, vol, rho, enabled, box, (float4*)grid));
   NEUMA_LAUNCH_CHECK(ctx, "p2g_to_kernel");
   return 0;
 }
@@ -618,15 +567,16 @@ int neuma_mpm_grid_op_box(neuma_ctx* ctx, const neuma_mpm_const* c, const int32_
 
 int neuma_mpm_g2p_from(neuma_ctx* ctx, const neuma_mpm_const* c, int n, const float* x,
                        const float* F, const float* clip_bound, const int32_t* enabled,
-                       const float* grid_v, float* x2, float* v2, float* C2, float* F2,
-                       int32_t* box_next, void* stream) {
+                       const int32_t* box, const float* grid_v, float* x2, float* v2, float* C2,
+                       float* F2, int32_t* box_next, void* stream) {
   if (int r = check_slab(ctx, c)) return r;
   if (n <= 0) return 0;
+  if (c->compact && !box) return neuma_fail_msg(ctx, "neuma_mpm_g2p_from: a compact grid needs its box");
   cudaStream_t st = (cudaStream_t)stream;
   const int pb = pblock(256);
   NEUMA_CUDA(ctx, neuma_launch(box_next ? g2p_from_kernel<true> : g2p_from_kernel<false>, dim3((n + pb - 1) / pb),
-                               dim3(pb), 0, st, *c, n, x, F, clip_bound, enabled, (const float4*)grid_v, x2, v2, C2,
-                               F2, box_next));
+                               dim3(pb), 0, st, *c, n, x, F, clip_bound, enabled, box, (const float4*)grid_v, x2, v2,
+                               C2, F2, box_next));
   NEUMA_LAUNCH_CHECK(ctx, "g2p_from_kernel");
   return 0;
 }
@@ -635,27 +585,28 @@ int neuma_mpm_rollout_fwd(neuma_ctx* ctx, const neuma_mpm_const* c, int n, const
                           const float* v, const float* C, const float* F, const float* stress,
                           const float* vol, const float* rho, const float* clip_bound,
                           const int32_t* enabled, float* x2, float* v2, float* C2, float* F2,
-                          float* grid, float* adj, const int32_t* box, int32_t* box_next,
+                          float* grid, float* adj, int32_t* box, int32_t* box_next,
                           void* stream) {
   if (!grid || !box) return neuma_fail_msg(ctx, "neuma_mpm_rollout_fwd: grid and box are required");
   if (int r = neuma_mpm_box_clear(ctx, c, box, grid, nullptr, box_next, stream)) return r;
-  if (int r = neuma_mpm_p2g_to(ctx, c, n, x, v, C, stress, vol, rho, enabled, grid, stream)) return r;
+  if (int r = neuma_mpm_p2g_to(ctx, c, n, x, v, C, stress, vol, rho, enabled, box, grid, stream)) return r;
   if (int r = neuma_mpm_grid_op_box(ctx, c, box, grid, adj, stream)) return r;
-  return neuma_mpm_g2p_from(ctx, c, n, x, F, clip_bound, enabled, grid, x2, v2, C2, F2, box_next,
+  return neuma_mpm_g2p_from(ctx, c, n, x, F, clip_bound, enabled, box, grid, x2, v2, C2, F2, box_next,
                             stream);
 }
 
 int neuma_mpm_bwd_scatter(neuma_ctx* ctx, const neuma_mpm_const* c, int n, const float* x,
                           const float* F, const float* clip_bound, const int32_t* enabled,
                           const float* v2, const float* gx2, const float* gv2, const float* gC2,
-                          const float* gF2, float* adj, void* stream) {
+                          const float* gF2, const int32_t* box, float* adj, void* stream) {
   if (int r = check_slab(ctx, c)) return r;
   if (n <= 0) return 0;
+  if (c->compact && !box) return neuma_fail_msg(ctx, "neuma_mpm_bwd_scatter: a compact grid needs its box");
   if (!v2 || !gx2 || !gv2 || !gC2 || !gF2 || !adj)
     return neuma_fail_msg(ctx, "neuma_mpm_bwd_scatter: NULL argument");
   const int pb = pblock(256);
   NEUMA_CUDA(ctx, neuma_launch(bwd_scatter_adj_kernel, dim3((n + pb - 1) / pb), dim3(pb), 0, (cudaStream_t)stream,
-                               *c, n, x, F, clip_bound, enabled, v2, gx2, gv2, gC2, gF2, (float4*)adj));
+                               *c, n, x, F, clip_bound, enabled, v2, gx2, gv2, gC2, gF2, box, (float4*)adj));
   NEUMA_LAUNCH_CHECK(ctx, "bwd_scatter_adj_kernel");
   return 0;
 }
@@ -678,7 +629,7 @@ int neuma_mpm_bwd_node_gather(neuma_ctx* ctx, const neuma_mpm_const* c, int n, c
   const int pb = pblock(128) > 128 ? 128 : pblock(128);
   NEUMA_CUDA(ctx, neuma_launch(C2 ? bwd_gather_v_kernel<true> : bwd_gather_v_kernel<false>, dim3((n + pb - 1) / pb),
                                dim3(pb), 0, st, *c, n, x, v, C, F, stress, vol, rho, clip_bound, enabled, v2, C2, gx2,
-                               gv2, gC2, gF2, (const float4*)grid_v, (const float4*)adj, gx, gv, gC, gF, gstress));
+                               gv2, gC2, gF2, box, (const float4*)grid_v, (const float4*)adj, gx, gv, gC, gF, gstress));
   NEUMA_LAUNCH_CHECK(ctx, "bwd_gather_v_kernel");
   return 0;
 }
@@ -690,7 +641,7 @@ int neuma_mpm_rollout_bwd(neuma_ctx* ctx, const neuma_mpm_const* c, int n, const
                           const float* gx2, const float* gv2, const float* gC2, const float* gF2,
                           const float* grid_v, float* adj, const int32_t* box, float* gx, float* gv,
                           float* gC, float* gF, float* gstress, void* stream) {
-  if (int r = neuma_mpm_bwd_scatter(ctx, c, n, x, F, clip_bound, enabled, v2, gx2, gv2, gC2, gF2, adj,
+  if (int r = neuma_mpm_bwd_scatter(ctx, c, n, x, F, clip_bound, enabled, v2, gx2, gv2, gC2, gF2, box, adj,
                                     stream))
     return r;
   return neuma_mpm_bwd_node_gather(ctx, c, n, x, v, C, F, stress, vol, rho, clip_bound, enabled, v2, C2,
@@ -731,6 +682,21 @@ int neuma_halo_add_ack(neuma_ctx* ctx, float* dst, const float* mailbox, size_t 
   halo_add_ack_kernel<<<(int)b, 256, 0, (cudaStream_t)stream>>>((float4*)dst, (const float4*)mailbox, nodes,
                                                                  my_data_flag, peer_ack_flag, my_seq, done);
   NEUMA_LAUNCH_CHECK(ctx, "halo_add_ack_kernel");
+  return 0;
+}
+
+int neuma_halo_exchange(neuma_ctx* ctx, const neuma_mpm_const* c, const neuma_halo_side* lo,
+                        const neuma_halo_side* hi, const int32_t* box, int32_t* cnt, void* stream) {
+  if (int r = check_slab(ctx, c)) return r;
+  if (c->compact) return neuma_fail_msg(ctx, "neuma_halo_exchange: the slab grids are dense in x, y");
+  if (!box || !cnt) return neuma_fail_msg(ctx, "neuma_halo_exchange: NULL argument");
+  neuma_halo_side none;
+  memset(&none, 0, sizeof(none));
+  const neuma_halo_side a = lo ? *lo : none, b = hi ? *hi : none;
+  if (!a.planes && !b.planes) return 0;
+  // a FIXED grid: the monotonic counters count blocks; all blocks co-resident with room to spare
+  halo_exchange_kernel<<<NEUMA_HALO_BLOCKS, 256, 0, (cudaStream_t)stream>>>(a, b, *c, box, cnt);
+  NEUMA_LAUNCH_CHECK(ctx, "halo_exchange_kernel");
   return 0;
 }
 

@@ -14,7 +14,7 @@ checkpoints load unchanged.  forward() is ONE fused CUDA kernel (SVD, invariants
 MLP, symmetrise, polar recombination); backward ONE more.
 
 The LoRA adaptor is folded into the weight on the host, W_eff = W + scaling * B A,
-as a differentiable torch expression evaluated once per parameter version, so
+as a differentiable torch expression evaluated on every forward, so
 autograd un-merges dL/dW_eff into dL/dA, dL/dB (and dL/dW if it is trainable).
 """
 from __future__ import annotations
@@ -132,7 +132,6 @@ class _InvariantFullMeta(nn.Module):
                                         _cfg(cfg, "nonlinearity")))
             width = next_width
         self.final_layer = MLPBlock(width, self.dim * self.dim, _cfg(cfg, "no_bias"), None, None)
-        self._weff_cache = None
 
     # ---- LoRA management (meta.py:185-194, loralib.py:13-81)
     def init_lora_layers(self, r: int, lora_alpha: int = 1):
@@ -143,7 +142,6 @@ class _InvariantFullMeta(nn.Module):
             lora = LinearLoRA(lin.in_features, lin.out_features, r=r, lora_alpha=lora_alpha)
             lora.weight.data = lin.weight.data
             block.fc = lora.to(lin.weight.device)
-        self._weff_cache = None
         print(f"Initialized LoRA layers in {type(self).__name__} with r={r} and alpha={lora_alpha}.")
 
     def freeze_all_except_lora(self):
@@ -155,14 +153,12 @@ class _InvariantFullMeta(nn.Module):
         sd = self.state_dict()
         return {k: sd[k] for k in sd if "lora_" in k}
 
-    # ---- merged weights, rebuilt only when a parameter changed (optimizer.step bumps _version)
+    # ---- merged weights: the differentiable expression W + scaling * B A is rebuilt on EVERY
+    # forward, as the reference does (loralib.py:216-224) -- three tiny matmuls.  (Round 1 cached
+    # it per parameter version, which broke two forward+backward rounds without an optimizer step
+    # and went stale under weight.data.copy_().)
     def effective_weights(self):
-        blocks = list(self.layers) + [self.final_layer]
-        key = tuple((p.data_ptr(), p._version, p.requires_grad) for p in self.parameters()) + \
-              (torch.is_grad_enabled(), tuple(getattr(b.fc, "merged", False) for b in blocks))
-        if self._weff_cache is None or self._weff_cache[0] != key:
-            self._weff_cache = (key, [b.effective_weight() for b in blocks])
-        return self._weff_cache[1]
+        return [b.effective_weight() for b in list(self.layers) + [self.final_layer]]
 
     def _kind(self) -> int:
         return self.KIND

@@ -13,7 +13,7 @@ from typing import Optional, Sequence, Tuple
 import numpy as np
 import torch
 
-from ._lib import Context, MPMConstC, RasterSettingsC, NeumaError, ptr
+from ._lib import Context, HaloSideC, MPMConstC, RasterSettingsC, NeumaError, ptr
 
 BC_CODES = {"noslip": 0, "freeslip": 1}
 
@@ -35,8 +35,9 @@ def _f32(t: torch.Tensor) -> torch.Tensor:
 
 
 def mpm_const(num_grids: int, dt: float, bound: int, gravity: Sequence[float], eps: float, bc: str,
-              z_off: int = 0, nz: Optional[int] = None) -> MPMConstC:
-    """MPMConstant (mpm.py:158-167, dx/inv_dx as mpm.py:516-517)."""
+              z_off: int = 0, nz: Optional[int] = None, cap_nodes: int = 0) -> MPMConstC:
+    """MPMConstant (mpm.py:158-167, dx/inv_dx as mpm.py:516-517).  cap_nodes > 0: the rollout grids
+    are COMPACT (they hold the node bounding box only, cap_nodes nodes each)."""
     if bc not in BC_CODES:
         raise ValueError("invalid boundary condition: {}".format(bc))  # mpm.py:550
     c = MPMConstC()
@@ -50,6 +51,9 @@ def mpm_const(num_grids: int, dt: float, bound: int, gravity: Sequence[float], e
     c.bc = BC_CODES[bc]
     c.z_off = int(z_off)
     c.nz = int(num_grids if nz is None else nz)
+    c.compact = 1 if cap_nodes > 0 else 0
+    c.cap_nodes = int(cap_nodes)
+    c.sel_mode, c.sel_lo_end, c.sel_up_start = 0, 0, 0
     return c
 
 
@@ -296,19 +300,19 @@ def mpm_box_clear(c: MPMConstC, box, grid0=None, grid1=None, box_reset=None) -> 
                    _stream(box))
 
 
-def mpm_p2g_to(c: MPMConstC, x, v, Cm, stress, vol, rho, enabled, grid) -> None:
+def mpm_p2g_to(c: MPMConstC, x, v, Cm, stress, vol, rho, enabled, grid, box=None) -> None:
     _ctx(x).call("neuma_mpm_p2g_to", C.byref(c), x.shape[0], ptr(x), ptr(v), ptr(Cm), ptr(stress),
-                 ptr(vol), ptr(rho), ptr(enabled), ptr(grid), _stream(x))
+                 ptr(vol), ptr(rho), ptr(enabled), ptr(box), ptr(grid), _stream(x))
 
 
 def mpm_grid_op_box(c: MPMConstC, box, grid, adj_to_clear=None) -> None:
     _ctx(grid).call("neuma_mpm_grid_op_box", C.byref(c), ptr(box), ptr(grid), ptr(adj_to_clear), _stream(grid))
 
 
-def mpm_g2p_from(c: MPMConstC, x, F, clip_bound, enabled, grid_v, out, box_next=None) -> None:
+def mpm_g2p_from(c: MPMConstC, x, F, clip_bound, enabled, grid_v, out, box_next=None, box=None) -> None:
     x2, v2, C2, F2 = out
     _ctx(x).call("neuma_mpm_g2p_from", C.byref(c), x.shape[0], ptr(x), ptr(F), ptr(clip_bound), ptr(enabled),
-                 ptr(grid_v), ptr(x2), ptr(v2), ptr(C2), ptr(F2), ptr(box_next), _stream(x))
+                 ptr(box), ptr(grid_v), ptr(x2), ptr(v2), ptr(C2), ptr(F2), ptr(box_next), _stream(x))
 
 
 def mpm_rollout_fwd(c: MPMConstC, x, v, Cm, F, stress, vol, rho, clip_bound, enabled, out, grid, adj, box,
@@ -402,9 +406,9 @@ def mpm_planes_add(dst: torch.Tensor, src: torch.Tensor) -> None:
     _ctx(dst).call("neuma_mpm_planes_add", ptr(dst), ptr(src), C.c_size_t(dst.numel() // 4), _stream(dst))
 
 
-def mpm_bwd_scatter(c: MPMConstC, x, F, clip_bound, enabled, v2, gx2, gv2, gC2, gF2, adj) -> None:
+def mpm_bwd_scatter(c: MPMConstC, x, F, clip_bound, enabled, v2, gx2, gv2, gC2, gF2, adj, box=None) -> None:
     _ctx(x).call("neuma_mpm_bwd_scatter", C.byref(c), x.shape[0], ptr(x), ptr(F), ptr(clip_bound), ptr(enabled),
-                 ptr(v2), ptr(gx2), ptr(gv2), ptr(gC2), ptr(gF2), ptr(adj), _stream(x))
+                 ptr(v2), ptr(gx2), ptr(gv2), ptr(gC2), ptr(gF2), ptr(box), ptr(adj), _stream(x))
 
 
 def mpm_bwd_node_gather(c: MPMConstC, x, v, Cm, F, stress, vol, rho, clip_bound, enabled, v2, C2, gx2, gv2, gC2,
@@ -459,3 +463,20 @@ def halo_push(src, peer_mailbox, peer_data_flag, my_ack_flag, my_seq, done) -> N
 def halo_add_ack(dst, mailbox, my_data_flag, peer_ack_flag, my_seq, done) -> None:
     _ctx(dst).call("neuma_halo_add_ack", ptr(dst), ptr(mailbox), C.c_size_t(dst.numel() // 4), ptr(my_data_flag),
                    ptr(peer_ack_flag), ptr(my_seq), ptr(done), _stream(dst))
+
+
+def halo_side(planes, peer_mail, peer_hdr, my_mail, my_hdr, peer_data_flag, my_data_flag, peer_ack_flag,
+              my_ack_flag, npl: int) -> HaloSideC:
+    h = HaloSideC()
+    for k, t in (("planes", planes), ("peer_mail", peer_mail), ("peer_hdr", peer_hdr), ("my_mail", my_mail),
+                 ("my_hdr", my_hdr), ("peer_data_flag", peer_data_flag), ("my_data_flag", my_data_flag),
+                 ("peer_ack_flag", peer_ack_flag), ("my_ack_flag", my_ack_flag)):
+        setattr(h, k, t.data_ptr())
+    h.npl = int(npl)
+    return h
+
+
+def halo_exchange(c: MPMConstC, lo: Optional[HaloSideC], hi: Optional[HaloSideC], box, cnt) -> None:
+    """ONE kernel: push my window of the shared planes to both neighbours, add theirs (neuma_halo_exchange)."""
+    _ctx(box).call("neuma_halo_exchange", C.byref(c), C.byref(lo) if lo is not None else None,
+                   C.byref(hi) if hi is not None else None, ptr(box), ptr(cnt), _stream(box))

@@ -14,10 +14,13 @@ the same kernels with the Python/autograd overhead removed:
     CUDA graph (static buffers) and replayed;
   * the MPM substeps run the rollout path of the library (csrc/mpm_rollout.cu): particles
     are put in cell (Morton) order at load_state(), every substep keeps its own packed grid
-    (S x G^3 x 16 B, plus as much again for the adjoint scatter target) so the backward
-    reads the forward's grid instead of re-running P2G, and clears / node passes touch only
-    the device-side bounding box of the occupied nodes.  Everything this class returns or
-    accepts is in the CALLER's particle order;
+    so the backward reads the forward's grid instead of re-running P2G.  The saved grids are
+    COMPACT: a slot holds only the bounding box of the occupied nodes (device-side box, updated
+    by G2P for the next substep), `cap_nodes` float4 nodes for the grid and as many for the
+    adjoint scatter target -- at 100 k / 128^3 that is 32 B x ~0.2 M nodes = 6 MB per substep
+    instead of 67 MB dense (the reference pins 52.8 MB of particle state per substep,
+    modules/nclaw/sim/interface.py:108-123).  Everything this class returns or accepts is in
+    the CALLER's particle order;
   * LoRA is handled by the caller: the engine takes merged weights and returns
     dL/dW_eff (see neuma_b200.material for the un-merge).
 """
@@ -28,14 +31,19 @@ from typing import List, Optional, Sequence
 import torch
 
 from . import ops
-from ._lib import RasterSettingsC
+from ._lib import RasterSettingsC, NeumaError
 
 
 class FusedFrame:
     def __init__(self, n: int, cconst, statics, We: Sequence[torch.Tensor], Wp: Sequence[torch.Tensor],
                  alpha: float, substeps: int, device, bind=None, gaussians=None,
                  settings: Optional[RasterSettingsC] = None, center=None, size=None,
-                 elastic_kind: int = ops.KIND_ELASTIC, use_graphs: bool = True, sort: bool = True):
+                 elastic_kind: int = ops.KIND_ELASTIC, use_graphs: bool = True, sort: bool = True,
+                 compact: bool = True, grid_margin: int = 6, cap_nodes: Optional[int] = None):
+        """compact: saved grids hold the node bounding box only; their capacity is fixed at the first
+        load_state() from that state's box widened by `grid_margin` nodes on every side (room for
+        the cloud to move / deform over the frames this engine will see), or given as cap_nodes.
+        A later box that does not fit is reported by check() -- nothing is written out of bounds."""
         self.n, self.S, self.dev = int(n), int(substeps), device
         self.c = cconst
         self._statics_in = tuple(t.contiguous() for t in statics)
@@ -80,10 +88,44 @@ class FusedFrame:
         self._g_fwd = self._g_bwd = None
         self._ctx = ops._ctx(self.x)
         # per-substep packed grids ((mv, m) -> (v, m) in place), adjoint scatter targets, boxes
-        nodes = cconst.nz * cconst.num_grids * cconst.num_grids
-        self.grid = torch.empty(S, nodes, 4, **f)
-        self.adj = torch.empty(S, nodes, 4, **f)
+        self.compact, self.grid_margin = bool(compact), int(grid_margin)
         self.box = torch.zeros(S + 1, 8, device=device, dtype=torch.int32)
+        self.grid = self.adj = None
+        if not self.compact:
+            self._alloc_grids(cconst.nz * cconst.num_grids * cconst.num_grids)
+        elif cap_nodes is not None:
+            self._alloc_grids(int(cap_nodes))
+
+    def _alloc_grids(self, nodes: int) -> None:
+        f = dict(device=self.dev, dtype=torch.float32)
+        if self.compact:
+            self.c = self.c.variant(compact=1, cap_nodes=int(nodes))
+        self.cap_nodes = int(nodes)
+        self.grid = torch.empty(self.S, nodes, 4, **f)
+        # ONE adjoint scatter target, cleared (over the substep's box) inside the backward itself
+        self.adj = torch.empty(nodes, 4, **f)
+
+    def _cap_from_box(self, box_host) -> int:
+        lo, hi = box_host[:3], box_host[3:6]
+        if any(h < l for l, h in zip(lo, hi)):
+            return 4096
+        m, G = self.grid_margin, self.c.num_grids
+        ext = [min(h + m, G - 1) - max(l - m, 0) + 1 for l, h in zip(lo, hi)]
+        ext[0] = min(G + 7, ((ext[0] + 7) // 8 + 1) * 8)      # x rows are widened to multiples of 8
+        return int(ext[0] * ext[1] * ext[2])
+
+    def memory_bytes_per_substep(self) -> dict:
+        """What one substep of the rollout keeps resident for the backward."""
+        particle = 4 * (3 + 3 + 9 + 9 + 9 + 9) * self.n          # x, v, C, F, stress, F_trial
+        grid = 0 if self.grid is None else 16 * self.cap_nodes
+        return {"particle_state": particle, "grids": grid, "per_particle": (particle + grid) / max(self.n, 1)}
+
+    def check(self) -> None:
+        """Raises if a substep's node box did not fit the compact grid slots (that substep was
+        skipped on the device).  Synchronises."""
+        if self.compact and self.grid is not None and bool(self.box[:, 6].any().item()):
+            raise NeumaError("FusedFrame: the particles' node box outgrew the compact grid slots "
+                                 f"(cap_nodes={self.cap_nodes}); build the engine with a larger grid_margin / cap_nodes")
 
     # ------------------------------------------------------------------ sim
     def _sim_forward(self) -> None:
@@ -98,26 +140,34 @@ class FusedFrame:
             ops.constitutive_fwd_staged(self.kind_e, self.F[s], self.We_st, 0.0, self.stress[s])
             main.wait_stream(self._side)
             ops.mpm_p2g_to(c, self.x[s], self.v[s], self.C[s], self.stress[s], self.vol, self.rho, self.enabled,
-                           self.grid[s])
-            ops.mpm_grid_op_box(c, self.box[s], self.grid[s], self.adj[s])
+                           self.grid[s], box=self.box[s])
+            ops.mpm_grid_op_box(c, self.box[s], self.grid[s], None)
             ops.mpm_g2p_from(c, self.x[s], self.F[s], self.clip, self.enabled, self.grid[s],
-                             (self.x[s + 1], self.v[s + 1], self.C[s + 1], self.Ftrial[s]), self.box[s + 1])
+                             (self.x[s + 1], self.v[s + 1], self.C[s + 1], self.Ftrial[s]), self.box[s + 1],
+                             box=self.box[s])
             ops.constitutive_fwd_staged(ops.KIND_PLASTIC, self.Ftrial[s], self.Wp_st, self.alpha, self.F[s + 1])
 
     def _sim_backward(self) -> None:
         """Consumes self.g[0] = dL/d(state[S]); leaves dL/d(state[0]) in self.g[0]
         and accumulates dL/dW_eff into gWe / gWp."""
         c = self.c
+        main = torch.cuda.current_stream(self.dev)
         cur, nxt = 0, 1
         for s in reversed(range(self.S)):
             gx2, gv2, gC2, gF_next = self.g[cur]
+            # the adjoint scatter target is cleared over this substep's box on a side branch, next to
+            # the plasticity backward (it was last read by the gather of substep s + 1)
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                ops.mpm_box_clear(c, self.box[s], self.adj, None, None)
             # plasticity: F[s+1] = P(Ftrial[s])
             ops.constitutive_bwd_partials(ops.KIND_PLASTIC, self.Ftrial[s], self.Wp_st, self.alpha, gF_next,
                                           self.gFtrial, self.gWp_part)
+            main.wait_stream(self._side)
             gx, gv, gC, gF = self.g[nxt]
             ops.mpm_rollout_bwd(c, self.x[s], self.v[s], self.C[s], self.F[s], self.stress[s], self.vol,
                                 self.rho, self.clip, self.enabled, self.v[s + 1], self.C[s + 1],
-                                gx2, gv2, gC2, self.gFtrial, self.grid[s], self.adj[s], self.box[s],
+                                gx2, gv2, gC2, self.gFtrial, self.grid[s], self.adj, self.box[s],
                                 gx, gv, gC, gF, self.gstress)
             # elasticity: stress[s] = E(F[s]);  dL/dF[s] += E'(F[s])^T gstress
             ops.constitutive_bwd_partials(self.kind_e, self.F[s], self.We_st, 0.0, self.gstress, gF,
@@ -130,8 +180,7 @@ class FusedFrame:
                 a.copy_(b)
 
     def _capture(self, fn, pre=None):
-        """`pre` re-establishes what `fn` consumes (the backward eats the zeroed adjoint grids the
-        forward leaves behind: ONE backward per forward)."""
+        """`pre` re-establishes what `fn` consumes."""
         if pre is not None:
             pre()
         fn()                                  # warm-up: grows the library workspaces outside capture
@@ -168,6 +217,8 @@ class FusedFrame:
             self.C[0].copy_(C)
             self.F[0].copy_(F)
         ops.mpm_box_from_x(self.c, self.x[0], self.enabled, self.box[0])
+        if self.grid is None:                       # first state: size the compact grid slots (one host read)
+            self._alloc_grids(self._cap_from_box(self.box[0].cpu().tolist()))
 
     def _to_caller(self, t: torch.Tensor) -> torch.Tensor:
         return ops.gather_rows(t, self.inv) if self.sort else t
@@ -193,8 +244,8 @@ class FusedFrame:
         return tuple(self._to_caller(t[S]) for t in (self.x, self.v, self.C, self.F))
 
     def sim_backward(self, gx, gv, gC, gF):
-        """Reverse pass of the LAST sim_forward(): call it once per forward (it consumes the zeroed
-        adjoint grids the forward's node pass prepared).  Gradients in / out in the caller's order."""
+        """Reverse pass of the LAST sim_forward() (may be called again: the adjoint scatter target is
+        cleared inside the backward).  Gradients in / out in the caller's order."""
         for dst, src in zip(self.g[0], (gx, gv, gC, gF)):
             if src is None:
                 dst.zero_()
@@ -210,7 +261,7 @@ class FusedFrame:
             if self._g_bwd is None:
                 keep = [t.clone() for t in self.g[0]]
                 keep_w = [t.clone() for t in self.gWe + self.gWp]
-                self._g_bwd = self._capture(self._sim_backward, pre=self._sim_forward)
+                self._g_bwd = self._capture(self._sim_backward)
                 for dst, src in zip(self.g[0], keep):
                     dst.copy_(src)
                 for dst, src in zip(self.gWe + self.gWp, keep_w):

@@ -194,25 +194,86 @@ class PeerHalo:
                              self.cnt[2 + u: 3 + u], self.cnt[6 + u: 7 + u])
 
 
+class FusedHalo:
+    """The summing halo exchange as ONE kernel per exchange for both neighbours
+    (csrc/mpm_rollout.cu::halo_exchange_kernel, neuma_halo_exchange): pushes only the x-y window
+    this rank's particles occupy, double-buffered mailboxes in torch symmetric memory
+    (peer-mapped over NVLink / NVSwitch), monotonic DATA / ACK flags -- pointers only, so the
+    whole rollout including its exchanges replays from a CUDA graph, and the kernel can run on a
+    side stream next to the interior P2G / G2P (SlabRollout overlap)."""
+
+    def __init__(self, G: int, k: int, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import ops
+        self.ops = ops
+        self.group = dist.group.WORLD if group is None else group
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self.npl, self.G = 2 + 2 * k, int(G)
+        # [from lower | from upper][slot][planes][y][x][4]
+        self.mshape = (2, 2, self.npl, self.G, self.G, 4)
+        self.mail = symm_mem.empty(self.mshape, dtype=torch.float32, device=device)
+        self.mhdl = symm_mem.rendezvous(self.mail, self.group)
+        # ints: [0:2] data flag from lower / upper, [2:4] ack flag from lower / upper,
+        #       [8:16] window header from lower (2 slots x 4), [16:24] from upper
+        self.ints = symm_mem.empty((32,), dtype=torch.int32, device=device)
+        self.ihdl = symm_mem.rendezvous(self.ints, self.group)
+        self.ints.zero_()
+        self.cnt = torch.zeros(4, dtype=torch.int32, device=device)
+        torch.cuda.synchronize(device)
+        self.mhdl.barrier(0)                                   # every rank's flags are zero before anyone pushes
+        nbs = [nb for nb in (self.rank - 1, self.rank + 1) if 0 <= nb < self.world]
+        self.peer_mail = {nb: self.mhdl.get_buffer(nb, self.mshape, torch.float32, 0) for nb in nbs}
+        self.peer_ints = {nb: self.ihdl.get_buffer(nb, (32,), torch.int32, 0) for nb in nbs}
+
+    def _side(self, planes: torch.Tensor, plan: "SlabPlan", up: bool):
+        ov = plan.overlap(self.rank, up)
+        if ov is None:
+            return None
+        z_off = plan.local_planes(self.rank)[0]
+        nb = self.rank + 1 if up else self.rank - 1
+        u = 1 if up else 0                 # my slot for data FROM this neighbour
+        o = 1 - u                          # seen from that neighbour I am its other side
+        pi, mi = self.peer_ints[nb], self.ints
+        view = planes[ov[0] - z_off: ov[0] - z_off + ov[1]]
+        return self.ops.halo_side(view, self.peer_mail[nb][o], pi[8 + 8 * o: 16 + 8 * o], self.mail[u],
+                                  mi[8 + 8 * u: 16 + 8 * u], pi[o: o + 1], mi[u: u + 1], pi[2 + o: 3 + o],
+                                  mi[2 + u: 3 + u], ov[1])
+
+    def exchange(self, planes: torch.Tensor, plan: "SlabPlan", c, box: torch.Tensor) -> None:
+        lo, hi = self._side(planes, plan, False), self._side(planes, plan, True)
+        self.ops.halo_exchange(c, lo, hi, box, self.cnt)
+
+
 class SlabRollout:
     """S-substep differentiable rollout (elasticity -> MPM -> plasticity) of this rank's slab.
 
     Same kernels and per-substep saved grids as neuma_b200.pipeline.FusedFrame, plus the halo
-    exchange: halo="peer" (default) pushes the shared planes through NVLink peer memory
-    (PeerHalo) and replays forward / backward as CUDA graphs; halo="nccl" uses send/recv pairs
-    with eager launches."""
+    exchange:
+      halo="fused" (default)  ONE own kernel per exchange (FusedHalo), windowed to the occupied x-y
+                              range; with overlap=True it runs on a side stream while the
+                              particles that do not touch a shared plane go through P2G, grid_op and
+                              G2P (forward) / the adjoint scatter, node pass and gather (backward):
+                              boundary particles first -> exchange || interior -> boundary rest;
+      halo="peer"             round 1: push + add/ack kernel pair per neighbour (PeerHalo);
+      halo="nccl"             send/recv pairs, eager launches.
+    The classes are decided per particle at run time from its current position (exact under
+    drift), csrc/mpm_common.cuh::particle_selected."""
 
     def __init__(self, G: int, dt: float, We, Wp, alpha: float, substeps: int, device, group=None,
                  bound: int = 1, gravity=(0.0, -9.8, 0.0), eps: float = 6e-7, bc: str = "noslip",
-                 halo_k: int = 1, elastic_kind: int = 0, halo: str = "peer", use_graphs: Optional[bool] = None):
+                 halo_k: int = 1, elastic_kind: int = 0, halo: str = "fused", use_graphs: Optional[bool] = None,
+                 overlap: bool = True, standalone: bool = False):
         from . import ops
         self.ops = ops
         self.G, self.dt, self.S, self.dev, self.group = int(G), float(dt), int(substeps), device, group
         self.cargs = (int(bound), tuple(gravity), float(eps), bc)
         self.k = int(halo_k)
         self.alpha, self.kind_e = float(alpha), elastic_kind
-        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        # standalone: this process runs the whole cloud alone even if a process group exists
+        # (bench.py times the 1-GPU frame on rank 0 beside the sharded one)
+        self.world = dist.get_world_size(group) if (dist.is_initialized() and not standalone) else 1
+        self.rank = dist.get_rank(group) if (dist.is_initialized() and not standalone) else 0
+        self.skip_exchange = False          # timing experiments only: results are wrong without the exchange
         self.We = [w.detach().to(device).contiguous() for w in We]
         self.Wp = [w.detach().to(device).contiguous() for w in Wp]
         self.We_st = ops.constitutive_stage(*self.We)
@@ -224,14 +285,18 @@ class SlabRollout:
         self.plan: Optional[SlabPlan] = None
         self.n = 0
         self._scratch: dict = {}
-        if halo not in ("peer", "nccl"):
-            raise ValueError("halo must be 'peer' or 'nccl'")
+        if halo not in ("fused", "peer", "nccl"):
+            raise ValueError("halo must be 'fused', 'peer' or 'nccl'")
+        self.halo = halo
         self._peer = PeerHalo(G, self.k, device, group) if (halo == "peer" and self.world > 1) else None
+        self._fused = FusedHalo(G, self.k, device, group) if (halo == "fused" and self.world > 1) else None
+        self.overlap = bool(overlap) and self._fused is not None
         # graphs need capturable communication: peer memory yes, NCCL send/recv no
-        self.use_graphs = (halo == "peer" or self.world == 1) if use_graphs is None else bool(use_graphs)
-        if self.use_graphs and self._peer is None and self.world > 1:
-            raise ValueError("CUDA graphs need halo='peer' (NCCL send/recv is not capturable here)")
+        self.use_graphs = (halo != "nccl" or self.world == 1) if use_graphs is None else bool(use_graphs)
+        if self.use_graphs and halo == "nccl" and self.world > 1:
+            raise ValueError("CUDA graphs need halo='fused' or 'peer' (NCCL send/recv is not capturable here)")
         self._graphs: dict = {}
+        self._side = torch.cuda.Stream(device)
 
     # ------------------------------------------------------------------ distribution
     def distribute(self, x, v, C, F, vol, rho, clip, enabled) -> None:
@@ -244,6 +309,12 @@ class SlabRollout:
         mine = (self.plan.owner_of(base) == self.rank).nonzero(as_tuple=True)[0]
         z_off, nz = self.plan.local_planes(self.rank)
         self.c = ops.mpm_const(G, self.dt, self.cargs[0], self.cargs[1], self.cargs[2], self.cargs[3], z_off, nz)
+        # planes below lo_end / from up_start on are shared with the lower / upper neighbour
+        ov_lo, ov_up = self.plan.overlap(self.rank, False), self.plan.overlap(self.rank, True)
+        lo_end = ov_lo[0] + ov_lo[1] if ov_lo is not None else -(1 << 30)
+        up_start = ov_up[0] if ov_up is not None else (1 << 30)
+        self.c_bnd = self.c.variant(sel_mode=1, sel_lo_end=lo_end, sel_up_start=up_start)
+        self.c_int = self.c.variant(sel_mode=2, sel_lo_end=lo_end, sel_up_start=up_start)
         loc = [t[mine.to(t.device)].to(dev).contiguous() for t in (x, v, C, F, vol, rho, clip, enabled)]
         perm = ops.mpm_cell_order(self.c, loc[0]) if loc[0].shape[0] else torch.zeros(0, dtype=torch.int32, device=dev)
         loc = [ops.gather_rows(t, perm) if t.shape[0] else t for t in loc]
@@ -257,7 +328,7 @@ class SlabRollout:
         self.x[0], self.v[0], self.C[0], self.F[0] = loc[:4]
         self.vol, self.rho, self.clip, self.enabled = loc[4:]
         self.grid = torch.zeros(S, nz, G, G, 4, **f)
-        self.adj = torch.zeros(S, nz, G, G, 4, **f)
+        self.adj = torch.zeros(nz, G, G, 4, **f)           # ONE adjoint scatter target, cleared in the backward
         self.box = torch.zeros(S + 1, 8, device=dev, dtype=torch.int32)
         self.g = [[torch.zeros(n, 3, **f), torch.zeros(n, 3, **f), torch.zeros(n, 3, 3, **f),
                    torch.zeros(n, 3, 3, **f)] for _ in range(2)]
@@ -275,10 +346,12 @@ class SlabRollout:
                 out.append(planes[ov[0] - z_off: ov[0] - z_off + ov[1]])
         return out
 
-    def _exchange(self, planes: torch.Tensor) -> None:
-        if self.world == 1:
+    def _exchange(self, planes: torch.Tensor, box: torch.Tensor) -> None:
+        if self.world == 1 or self.skip_exchange:
             return
-        if self._peer is not None:
+        if self._fused is not None:
+            self._fused.exchange(planes, self.plan, self.c, box)
+        elif self._peer is not None:
             self._peer.exchange(planes, self.plan, self.ops.mpm_planes_add)
         else:
             exchange_sum(planes, self.plan, self.rank, self.group, add=self.ops.mpm_planes_add, scratch=self._scratch)
@@ -295,8 +368,7 @@ class SlabRollout:
                 keep = [t.clone() for t in self.g[0]]
             body()                                   # warm-up on the current stream: workspaces, scratch
             torch.cuda.synchronize(self.dev)
-            if key == "bwd":                         # the warm-up consumed the adjoint grids / upstream grads
-                self._forward_body()
+            if key == "bwd":                         # the warm-up consumed the upstream grads
                 for dst, src in zip(self.g[0], keep):
                     dst.copy_(src)
                 for t in (self.gWe_part, self.gWp_part):
@@ -314,19 +386,40 @@ class SlabRollout:
         S = self.S
         return self.x[S], self.v[S], self.C[S], self.F[S]
 
+    def _mpm_fwd(self, c, s: int, grid_op: bool = True) -> None:
+        ops = self.ops
+        if grid_op:
+            ops.mpm_grid_op_box(c, self.box[s], self.grid[s], None)
+        ops.mpm_g2p_from(c, self.x[s], self.F[s], self.clip, self.enabled, self.grid[s],
+                         (self.x[s + 1], self.v[s + 1], self.C[s + 1], self.Ftrial[s]), self.box[s + 1])
+
+    def _p2g(self, c, s: int) -> None:
+        self.ops.mpm_p2g_to(c, self.x[s], self.v[s], self.C[s], self.stress[s], self.vol, self.rho, self.enabled,
+                            self.grid[s])
+
     def _forward_body(self) -> None:
         ops, c = self.ops, self.c
+        main = torch.cuda.current_stream(self.dev)
+        windowed = self._fused is not None
         for s in range(self.S):
             ops.constitutive_fwd_staged(self.kind_e, self.F[s], self.We_st, 0.0, self.stress[s])
             ops.mpm_box_clear(c, self.box[s], self.grid[s], None, self.box[s + 1])
-            for vw in self._overlap_views(self.grid[s]):       # shared planes must be valid everywhere
-                vw.zero_()
-            ops.mpm_p2g_to(c, self.x[s], self.v[s], self.C[s], self.stress[s], self.vol, self.rho, self.enabled,
-                           self.grid[s])
-            self._exchange(self.grid[s])                        # the ONE exchange of the substep
-            ops.mpm_grid_op_box(c, self.box[s], self.grid[s], self.adj[s])
-            ops.mpm_g2p_from(c, self.x[s], self.F[s], self.clip, self.enabled, self.grid[s],
-                             (self.x[s + 1], self.v[s + 1], self.C[s + 1], self.Ftrial[s]), self.box[s + 1])
+            if self.world > 1 and not windowed:
+                for vw in self._overlap_views(self.grid[s]):       # whole shared planes are added: must be valid
+                    vw.zero_()
+            if self.overlap:
+                self._p2g(self.c_bnd, s)                            # particles touching a shared plane first
+                self._side.wait_stream(main)
+                with torch.cuda.stream(self._side):
+                    self._exchange(self.grid[s], self.box[s])       # the ONE exchange of the substep ...
+                self._p2g(self.c_int, s)                            # ... under the interior particles' work
+                self._mpm_fwd(self.c_int, s)
+                main.wait_stream(self._side)
+                self._mpm_fwd(self.c_bnd, s)
+            else:
+                self._p2g(c, s)
+                self._exchange(self.grid[s], self.box[s])           # the ONE exchange of the substep
+                self._mpm_fwd(c, s)
             ops.constitutive_fwd_staged(ops.KIND_PLASTIC, self.Ftrial[s], self.Wp_st, self.alpha, self.F[s + 1])
 
     def backward(self, gx, gv, gC, gF):
@@ -350,26 +443,60 @@ class SlabRollout:
 
     def _backward_body(self) -> None:
         ops, c = self.ops, self.c
+        main = torch.cuda.current_stream(self.dev)
+        windowed = self._fused is not None
         cur, nxt = 0, 1
         for s in reversed(range(self.S)):
             gx2, gv2, gC2, gF_next = self.g[cur]
+            # clear the adjoint scatter target over this substep's box next to the plasticity backward
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                ops.mpm_box_clear(c, self.box[s], self.adj, None, None)
+                if self.world > 1 and not windowed:
+                    for vw in self._overlap_views(self.adj):
+                        vw.zero_()
             ops.constitutive_bwd_partials(ops.KIND_PLASTIC, self.Ftrial[s], self.Wp_st, self.alpha, gF_next,
                                           self.gFtrial, self.gWp_part)
+            main.wait_stream(self._side)
             gxo, gvo, gCo, gFo = self.g[nxt]
-            for vw in self._overlap_views(self.adj[s]):
-                vw.zero_()
-            ops.mpm_bwd_scatter(c, self.x[s], self.F[s], self.clip, self.enabled, self.v[s + 1], gx2, gv2, gC2,
-                                self.gFtrial, self.adj[s])
-            self._exchange(self.adj[s])                         # the ONE exchange of the backward substep
-            ops.mpm_bwd_node_gather(c, self.x[s], self.v[s], self.C[s], self.F[s], self.stress[s], self.vol,
-                                    self.rho, self.clip, self.enabled, self.v[s + 1], self.C[s + 1], gx2, gv2, gC2,
-                                    self.gFtrial, self.grid[s], self.adj[s], self.box[s], gxo, gvo, gCo, gFo,
-                                    self.gstress)
+
+            def scatter(cc):
+                ops.mpm_bwd_scatter(cc, self.x[s], self.F[s], self.clip, self.enabled, self.v[s + 1], gx2, gv2, gC2,
+                                    self.gFtrial, self.adj)
+
+            def node_gather(cc):
+                ops.mpm_bwd_node_gather(cc, self.x[s], self.v[s], self.C[s], self.F[s], self.stress[s], self.vol,
+                                        self.rho, self.clip, self.enabled, self.v[s + 1], self.C[s + 1], gx2, gv2,
+                                        gC2, self.gFtrial, self.grid[s], self.adj, self.box[s], gxo, gvo, gCo, gFo,
+                                        self.gstress)
+            if self.overlap:
+                scatter(self.c_bnd)
+                self._side.wait_stream(main)
+                with torch.cuda.stream(self._side):
+                    self._exchange(self.adj, self.box[s])           # the ONE exchange of the backward substep
+                scatter(self.c_int)
+                node_gather(self.c_int)
+                main.wait_stream(self._side)
+                node_gather(self.c_bnd)
+            else:
+                scatter(c)
+                self._exchange(self.adj, self.box[s])
+                node_gather(c)
             ops.constitutive_bwd_partials(self.kind_e, self.F[s], self.We_st, 0.0, self.gstress, gFo,
                                           self.gWe_part, accumulate_gF=True)
             cur, nxt = nxt, cur
 
     # ------------------------------------------------------------------ ownership
+    def check_drift(self) -> None:
+        """Raises if, during the last forward(), a particle's stencil needed a grid plane this rank
+        does not hold (it moved more than the halo allowance k within the frame): its node visits
+        were dropped on the device, so state and gradients of that frame are wrong.  The count is
+        reduced on the device by G2P next to the node box (box[:, 7]).  Synchronises."""
+        lost = int(self.box[:, 7].sum().item()) if self.n else 0
+        if lost:
+            raise RuntimeError(f"SlabRollout rank {self.rank}: {lost} particle-substeps left the slab's planes "
+                               f"(halo_k={self.k}); re-run with a larger halo_k or repartition more often")
+
     def drift_ok(self) -> bool:
         """True while every local particle still sits inside the planes this rank holds."""
         if self.n == 0:
@@ -403,7 +530,8 @@ class SlabRollout:
 
     def repartition(self, n_global: int) -> None:
         """Frame boundary: particles change owner (migration) and the slabs are re-balanced.
-        state[S] becomes the new state[0]."""
+        state[S] becomes the new state[0].  Raises if the finished frame violated the drift bound."""
+        self.check_drift()
         S = self.S
         full = [self.gather_global(t, n_global) for t in
                 (self.x[S], self.v[S], self.C[S], self.F[S], self.vol, self.rho, self.clip, self.enabled)]

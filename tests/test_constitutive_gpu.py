@@ -152,3 +152,27 @@ def test_staged_and_partials_paths_match_atomics_path(cuda_dev, n):
     for a, b in zip(gW, gW_ref):
         assert rel_err(a, 2 * b) < 1e-4
     assert float(part.abs().max()) == 0.0                  # slots are zeroed by the reduce
+
+
+def test_lora_two_rounds_without_optimizer_step(cuda_dev):
+    """two forward+backward rounds with LoRA and no optimizer.step() in between (gradient
+    accumulation, a repeated loss evaluation) must work, and weight.data.copy_() must be seen --
+    the reference rebuilds the LoRA product on every forward (loralib.py:216-224)."""
+    from neuma_b200.material import InvariantFullMetaElasticity
+    torch.manual_seed(5)
+    cfg = dict(layer_widths=[64, 64], norm=None, nonlinearity="gelu", no_bias=True, normalize_input=True)
+    m = InvariantFullMetaElasticity(cfg).to(cuda_dev)
+    m.init_lora_layers(r=16, lora_alpha=16)
+    m.freeze_all_except_lora()
+    for blk in list(m.layers) + [m.final_layer]:
+        torch.nn.init.normal_(blk.fc.lora_B, std=0.05)
+    F = (torch.eye(3) + 0.05 * torch.randn(300, 3, 3)).to(cuda_dev)
+    m(F).square().sum().backward()
+    g1 = [p.grad.clone() for p in m.parameters() if p.requires_grad]
+    m(F).square().sum().backward()                                   # accumulates: no "backward twice" error
+    for a, p in zip(g1, [p for p in m.parameters() if p.requires_grad]):
+        assert rel_err(p.grad, 2 * a) < 1e-5
+    y0 = m(F).detach().clone()
+    with torch.no_grad():
+        m.layers[0].fc.weight.data.copy_(0.5 * m.layers[0].fc.weight.data)   # does not bump _version
+    assert (m(F).detach() - y0).abs().max() > 1e-6

@@ -15,10 +15,10 @@ def _dev(d, dev):
     return {k: t.to(dev) for k, t in d.items()}
 
 
-def _consts(G, dt, bc, eps=6e-7, gravity=(0.0, -9.8, 0.0), bound=1):
+def _consts(G, dt, bc, eps=6e-7, gravity=(0.0, -9.8, 0.0), bound=1, cap_nodes=0):
     from neuma_b200 import ops
     return (O.MPMConst(num_grids=G, dt=dt, bound=bound, gravity=gravity, eps=eps, bc=bc),
-            ops.mpm_const(G, dt, bound, gravity, eps, bc))
+            ops.mpm_const(G, dt, bound, gravity, eps, bc, cap_nodes=cap_nodes))
 
 
 def _buffers(G, dev, slots=1):
@@ -28,22 +28,25 @@ def _buffers(G, dev, slots=1):
     return grid, adj, box
 
 
+@pytest.mark.parametrize("compact", [False, True])
 @pytest.mark.parametrize("n,G,bc,lo,hi", [(5000, 32, "noslip", 0.3, 0.7), (20000, 64, "freeslip", 0.3, 0.7),
                                           (3000, 16, "noslip", 0.02, 0.98), (3000, 16, "freeslip", 0.02, 0.98),
                                           (333, 16, "noslip", 0.4, 0.45)])
-def test_rollout_fwd_bwd_vs_oracle(cuda_dev, n, G, bc, lo, hi):
-    """clouds touching the walls exercise the BC -0.0f marker and the box clamping"""
+def test_rollout_fwd_bwd_vs_oracle(cuda_dev, n, G, bc, lo, hi, compact):
+    """clouds touching the walls exercise the BC -0.0f marker and the box clamping; compact = the
+    saved grid holds the node bounding box only (cap_nodes nodes), as FusedFrame allocates it"""
     from neuma_b200 import ops
-    co, cc = _consts(G, 1e-3, bc)
+    co, cc = _consts(G, 1e-3, bc, cap_nodes=(G + 8) * G * G if compact else 0)
     d = make_cloud(n, G, seed=5 + n, lo=lo, hi=hi, disabled_frac=0.05)
     # keep the reference's latent out-of-range write out of the test (SURVEY 7)
     d["x"].clamp_(max=1 - 1.6 / G)
     g = _dev(d, cuda_dev)
-    grid, adj, box = _buffers(G, cuda_dev)
+    grid, adj, box = _buffers(G + 3 if compact else G, cuda_dev)
     ops.mpm_box_from_x(cc, g["x"], g["enabled"], box[0])
     out = tuple(torch.empty_like(g[k]) for k in ("x", "v", "C", "F"))
     ops.mpm_rollout_fwd(cc, g["x"], g["v"], g["C"], g["F"], g["stress"], g["vol"], g["rho"], g["clip"],
                         g["enabled"], out, grid[0], adj[0], box[0], box[1])
+    assert int(box[0, 6]) == 0 and int(box[1, 7]) == 0               # no overflow, no slab drift
     d64 = {k: (t.double() if t.is_floating_point() else t) for k, t in d.items()}
     o = O.substep_fwd(co, d64["x"], d64["v"], d64["C"], d64["F"], d64["stress"], d64["vol"],
                       d64["rho"], d64["clip"], d["enabled"])
@@ -145,3 +148,47 @@ def test_empty_box(cuda_dev):
     torch.cuda.synchronize()
     assert torch.all(out[0] == 7.0)                                     # disabled particles are not written
     assert torch.isnan(grid).all()                                      # nothing was touched
+
+
+def test_compact_overflow_is_flagged_not_written(cuda_dev):
+    """a node box larger than cap_nodes: the substep is skipped on the device, box[6] raised, nothing
+    is written outside the slot"""
+    from neuma_b200 import ops
+    co, cc = _consts(32, 1e-3, "noslip", cap_nodes=1000)
+    d = make_cloud(2000, 32, seed=2)
+    g = _dev(d, cuda_dev)
+    grid = torch.full((1000 + 64, 4), 5.0, device=cuda_dev)
+    box = torch.zeros(2, 8, dtype=torch.int32, device=cuda_dev)
+    ops.mpm_box_from_x(cc, g["x"], g["enabled"], box[0])
+    out = tuple(torch.full_like(g[k], 7.0) for k in ("x", "v", "C", "F"))
+    ops.mpm_rollout_fwd(cc, g["x"], g["v"], g["C"], g["F"], g["stress"], g["vol"], g["rho"], g["clip"],
+                        g["enabled"], out, grid[:1000], None, box[0], box[1])
+    torch.cuda.synchronize()
+    assert int(box[0, 6]) == 1
+    assert torch.all(grid == 5.0)
+
+
+def test_negative_zero_gravity_is_not_the_bc_sentinel(cuda_dev):
+    """gravity = (-0.0, g, 0) must not make empty-node velocities look BC-zeroed"""
+    from neuma_b200 import ops
+    grav = (-0.0, -9.8, 0.0)
+    co, cc = _consts(32, 1e-3, "noslip", gravity=grav)
+    d = make_cloud(3000, 32, seed=8)
+    g = _dev(d, cuda_dev)
+    grid, adj, box = _buffers(32, cuda_dev)
+    ops.mpm_box_from_x(cc, g["x"], g["enabled"], box[0])
+    out = tuple(torch.empty_like(g[k]) for k in ("x", "v", "C", "F"))
+    ops.mpm_rollout_fwd(cc, g["x"], g["v"], g["C"], g["F"], g["stress"], g["vol"], g["rho"], g["clip"],
+                        g["enabled"], out, grid[0], adj[0], box[0], box[1])
+    gen = torch.Generator().manual_seed(1)
+    gouts = [torch.randn(3000, 3, generator=gen), torch.randn(3000, 3, generator=gen),
+             torch.randn(3000, 3, 3, generator=gen), torch.randn(3000, 3, 3, generator=gen)]
+    d64 = {k: (t.double() if t.is_floating_point() else t) for k, t in d.items()}
+    og = O.substep_bwd(co, d["x"], d["v"], d["C"], d["F"], d["stress"], d64["vol"], d64["rho"], d64["clip"],
+                       d["enabled"], *gouts)
+    grads = [torch.empty_like(g[k]) for k in ("x", "v", "C", "F", "stress")]
+    ops.mpm_rollout_bwd(cc, g["x"], g["v"], g["C"], g["F"], g["stress"], g["vol"], g["rho"], g["clip"],
+                        g["enabled"], out[1], out[2], *[t.to(cuda_dev) for t in gouts], grid[0], adj[0], box[0],
+                        *grads)
+    for a, b in zip(grads, og):
+        assert rel_err(a, b) < 5e-4

@@ -48,7 +48,7 @@ def _reference(dev, n, G, S, dt):
     return out, g0, [t.clone() for t in eng.gWe + eng.gWp]
 
 
-def _slab_run(rank, world, port, n, G, S, dt, q, halo="peer"):
+def _slab_run(rank, world, port, n, G, S, dt, q, halo="fused", overlap=True, vscale=1.0):
     from neuma_b200.slab import SlabRollout
     if world > 1:
         os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -59,9 +59,20 @@ def _slab_run(rank, world, port, n, G, S, dt, q, halo="peer"):
     try:
         W, alpha = _weights()
         d, g = _problem(n, G)
-        sim = SlabRollout(G, dt, W["elastic"], W["plastic"], alpha, S, dev, halo=halo)
+        d["v"] = d["v"] * vscale
+        sim = SlabRollout(G, dt, W["elastic"], W["plastic"], alpha, S, dev, halo=halo, overlap=overlap)
         sim.distribute(d["x"], d["v"], d["C"], d["F"], d["vol"], d["rho"], d["clip"], d["enabled"])
         out = sim.forward()
+        if vscale > 1.0:               # drift test: the device-side counter must catch the lost stencils
+            try:
+                sim.check_drift()
+                caught = False
+            except RuntimeError:
+                caught = True
+            if q is not None:
+                q.put(("drift", rank, caught))
+            return None, None, caught
+        sim.check_drift()
         assert sim.drift_ok()
         ids = sim.ids
         g0 = sim.backward(*[t.to(dev)[ids] for t in g])
@@ -109,10 +120,12 @@ def test_slab_world1_matches_fused_frame(cuda_dev):
     _check(res, gW, ref)
 
 
-@pytest.mark.parametrize("world,halo", [(2, "peer"), (2, "nccl"), (4, "peer")])
-def test_slab_multi_gpu_matches_single(cuda_dev, world, halo):
-    """halo="peer": NVLink peer-memory pushes + flag kernels, whole rollout replayed as CUDA graphs;
-    halo="nccl": send/recv pairs, eager launches"""
+@pytest.mark.parametrize("world,halo,overlap", [(2, "fused", True), (2, "fused", False), (2, "peer", False),
+                                                 (2, "nccl", False), (4, "fused", True)])
+def test_slab_multi_gpu_matches_single(cuda_dev, world, halo, overlap):
+    """halo="fused": one windowed exchange kernel per substep on a side stream under the interior
+    particles' work (overlap) or in line; halo="peer": round-1 push / add kernel pairs; halo="nccl":
+    send/recv pairs, eager launches.  All against the single-GPU engine in global particle order."""
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     n, G, S, dt = 40000, 64, 3, 2.5e-4
@@ -120,7 +133,8 @@ def test_slab_multi_gpu_matches_single(cuda_dev, world, halo):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_slab_run, args=(r, world, port, n, G, S, dt, q, halo)) for r in range(world)]
+    procs = [ctx.Process(target=_slab_run, args=(r, world, port, n, G, S, dt, q, halo, overlap))
+             for r in range(world)]
     for p in procs:
         p.start()
     got = [q.get(timeout=300) for _ in range(world)]
@@ -131,3 +145,49 @@ def test_slab_multi_gpu_matches_single(cuda_dev, world, halo):
     total = main[2] + sum(g_ for g_ in got if not isinstance(g_, tuple))
     assert total == n
     _check(main[0], main[1], ref)
+
+
+def test_slab_drift_beyond_halo_is_detected(cuda_dev):
+    """ADVICE r1: a particle that leaves the planes its rank holds within a frame loses node visits;
+    the device-side counter (box[:, 7], reduced by G2P) must make check_drift() raise."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    n, G, S, dt = 20000, 64, 6, 2.5e-4
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    # |v| ~ 60: 6 substeps x 2.5e-4 x 60 x 64 cells = 5.8 planes > k + 2
+    procs = [ctx.Process(target=_slab_run, args=(r, 2, port, n, G, S, dt, q, "fused", True, 200.0)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=300) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=120)
+    assert any(g_[2] for g_ in got)
+
+
+def test_slab_world1_matches_oracle(cuda_dev):
+    """the slab engine against the CPU oracle itself (not only against FusedFrame)"""
+    from oracle import constitutive_oracle as CO, mpm_oracle as MO
+    n, G, S, dt = 6000, 32, 2, 5e-4
+    W, alpha = _weights()
+    d, g = _problem(n, G)
+    res, gW, counts = _slab_run(0, 1, 0, n, G, S, dt, None)
+    co = MO.MPMConst(num_grids=G, dt=dt, bound=1, eps=6e-7, bc="noslip")
+    x, v, C, F = [d[k].double().requires_grad_(True) for k in ("x", "v", "C", "F")]
+    We = [w.double().requires_grad_(True) for w in W["elastic"]]
+    Wp = [w.double().requires_grad_(True) for w in W["plastic"]]
+    s_ = (x, v, C, F)
+    for _ in range(S):
+        stress = CO.elasticity(s_[3], We)
+        x2, v2, C2, F2 = MO.substep_fwd(co, s_[0], s_[1], s_[2], s_[3], stress, d["vol"].double(), d["rho"].double(),
+                                        d["clip"].double(), d["enabled"])
+        s_ = (x2, v2, C2, CO.plasticity(F2, Wp, alpha))
+    loss = sum((a * b.double()).sum() for a, b in zip(s_, g))
+    og = torch.autograd.grad(loss, [x, v, C, F] + We + Wp)
+    for a, b, name in zip(res[:4], s_, "xvCF"):
+        assert rel_err(a, b) < 1e-4, name
+    for a, b, name in zip(res[4:], og[:4], ["gx", "gv", "gC", "gF"]):
+        assert rel_err(a, b) < 1e-3, name
+    for a, b in zip(gW, og[4:]):
+        assert rel_err(a, b) < 2e-3

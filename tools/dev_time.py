@@ -55,9 +55,9 @@ for n, G in [(100_000, 128), (200_000, 128), (1_000_000, 256), (50_000, 64)]:
         box = torch.zeros(2, 8, dtype=torch.int32, device=dev)
         ops.mpm_box_from_x(cc, dd["x"], dd["enabled"], box[0])
         res["r_clear_us" + tag] = timeit(lambda: ops.mpm_box_clear(cc, box[0], grid, None, box[1]))
-        res["r_p2g_us" + tag] = timeit(lambda: ops.mpm_p2g_to(cc, dd["x"], dd["v"], dd["C"], dd["stress"], dd["vol"], dd["rho"], dd["enabled"], grid))
+        res["r_p2g_us" + tag] = timeit(lambda: ops.mpm_p2g_to(cc, dd["x"], dd["v"], dd["C"], dd["stress"], dd["vol"], dd["rho"], dd["enabled"], grid, box=box[0]))
         res["r_gridop_us" + tag] = timeit(lambda: ops.mpm_grid_op_box(cc, box[0], grid, adj))
-        res["r_g2p_us" + tag] = timeit(lambda: ops.mpm_g2p_from(cc, dd["x"], dd["F"], dd["clip"], dd["enabled"], grid, out, box[1]))
+        res["r_g2p_us" + tag] = timeit(lambda: ops.mpm_g2p_from(cc, dd["x"], dd["F"], dd["clip"], dd["enabled"], grid, out, box[1], box=box[0]))
         rf = lambda: ops.mpm_rollout_fwd(cc, dd["x"], dd["v"], dd["C"], dd["F"], dd["stress"], dd["vol"], dd["rho"], dd["clip"], dd["enabled"], out, grid, adj, box[0], box[1])
         res["r_fwd_us" + tag] = timeit(rf)
         g5 = [torch.empty_like(dd[k]) for k in ("x", "v", "C", "F", "stress")]
