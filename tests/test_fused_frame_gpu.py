@@ -70,7 +70,7 @@ def test_set_weights_restages(cuda_dev):
     eng.set_weights(We=W["elastic"])
     c = eng.sim_forward()
     for x, y in zip(a, c):
-        assert rel_err(x, y) < 1e-5
+        assert rel_err(x, y) < 5e-5          # two runs of fp32 atomics (different order), per-element metric
 
 
 def test_two_chained_frames_against_oracle(cuda_dev):

