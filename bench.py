@@ -479,16 +479,18 @@ def slab_measure(dev, world: int, rank: int, substeps: int, steps: int, warmup: 
                 "exchanges_per_frame": 2 * substeps,
                 "halo_bytes_dense_per_frame": sum(o[1] for o in ov) * spec["G"] ** 2 * 16 * 2 * 2 * substeps})
     if variants:
-        # where the exchange time goes: the same frame without the overlap, and without any exchange
-        # (wrong results, valid timing)
-        if sim.overlap:
-            sim.overlap, sim._graphs = False, {}
-            out["ms_per_frame_no_overlap"] = time_ms(sim, g, True)
-        sim.skip_exchange, sim._graphs = True, {}
+        # where the exchange time goes: the same frame with the other overlap modes, and without
+        # any exchange (wrong results, valid timing)
+        by_mode = {sim.overlap: ms}
+        for mode in ("none", "scatter", "full"):
+            if mode not in by_mode and sim._fused is not None:
+                sim.overlap, sim._graphs = mode, {}
+                by_mode[mode] = time_ms(sim, g, True)
+        out["ms_per_frame_by_overlap"] = by_mode
+        sim.overlap, sim.skip_exchange, sim._graphs = "none", True, {}
         ms0 = time_ms(sim, g, True)
         out["ms_per_frame_no_exchange"] = ms0
-        ref = out.get("ms_per_frame_no_overlap", ms)
-        out["halo_us_per_exchange"] = (ref - ms0) * 1000.0 / (2 * substeps)
+        out["halo_us_per_exchange"] = (by_mode.get("none", ms) - ms0) * 1000.0 / (2 * substeps)
         out["halo_exposed_us_per_exchange"] = (ms - ms0) * 1000.0 / (2 * substeps)
     return out
 

@@ -69,9 +69,9 @@ typedef struct {
 
 /* One side (lower or upper z-neighbour) of the Z-slab halo exchange.  All pointers
  * are DEVICE pointers; peer_* point into the NEIGHBOUR's memory (NVLink peer mapping).  A
- * mailbox holds 2 slots x npl x G x G float4 nodes, a header 2 slots x 4 int32 (the sender's
- * x0, nx, y0, ny window); flags are single int32, zero-initialised once.  planes == NULL: no
- * neighbour on this side. */
+ * mailbox holds 2 slots x npl x G x G float4 nodes, a header 2 slots x 8 int32 (the sender's
+ * window x0, nx, y0, ny, first plane, planes); flags are single int32, zero-initialised once.
+ * planes == NULL: no neighbour on this side. */
 typedef struct {
   float* planes;               /* my shared planes inside the grid being exchanged */
   float* peer_mail;            /* neighbour's mailbox for what I send */
@@ -83,7 +83,7 @@ typedef struct {
   int32_t* peer_ack_flag;
   const int32_t* my_ack_flag;
   int32_t npl;                 /* number of shared planes */
-  int32_t pad;
+  int32_t z0;                  /* global index of the first shared plane */
 } neuma_halo_side;
 
 /* GaussianRasterizationSettings, modules/d3gs/gaussian_renderer/__init__.py:103-116.

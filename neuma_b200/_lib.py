@@ -38,7 +38,7 @@ class HaloSideC(C.Structure):
         ("planes", C.c_void_p), ("peer_mail", C.c_void_p), ("peer_hdr", C.c_void_p),
         ("my_mail", C.c_void_p), ("my_hdr", C.c_void_p), ("peer_data_flag", C.c_void_p),
         ("my_data_flag", C.c_void_p), ("peer_ack_flag", C.c_void_p), ("my_ack_flag", C.c_void_p),
-        ("npl", C.c_int32), ("pad", C.c_int32),
+        ("npl", C.c_int32), ("z0", C.c_int32),
     ]
 
 

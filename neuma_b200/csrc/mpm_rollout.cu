@@ -384,9 +384,10 @@ halo_add_ack_kernel(float4* __restrict__ dst, const float4* mailbox, size_t n,
 }
 
 // ---- ONE kernel per summing halo exchange, both neighbours ----------------------
-// Per side: push my shared planes -- only the x-y window my particles occupy (`box`) -- into the
-// neighbour's mailbox over NVLink, publish the exchange number; wait for the neighbour's push,
-// add ITS window of the mailbox into my planes, acknowledge.  Mailboxes are double-buffered
+// Per side: push my shared planes -- only the window (x, y and z range) my particles occupy
+// (`box`: what box_clear zeroed and P2G wrote) -- into the neighbour's mailbox over NVLink,
+// publish the exchange number; wait for the neighbour's push, add the part of ITS window that
+// overlaps mine into my planes, acknowledge.  Mailboxes are double-buffered
 // (slot = exchange number & 1), so the push waits only for the acknowledgement of exchange
 // seq - 2.  Work is split by (plane, y) ROW over the warps, identically in both phases: a warp
 // only ever adds into rows it pushed itself, so no block has to wait for another block of this
@@ -397,7 +398,7 @@ __global__ void __launch_bounds__(256)
 halo_exchange_kernel(neuma_halo_side lo, neuma_halo_side hi, neuma_mpm_const c,
                      const int32_t* __restrict__ box, int32_t* __restrict__ cnt) {
   __shared__ int s_seq;
-  __shared__ int s_hdr[2][4];
+  __shared__ int s_hdr[2][6];
   const neuma_halo_side side[2] = {lo, hi};
   const int G = c.num_grids;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -412,23 +413,33 @@ halo_exchange_kernel(neuma_halo_side lo, neuma_halo_side hi, neuma_mpm_const c,
   }
   __syncthreads();
   const int seq = s_seq, slot = seq & 1;
-  // my x-y window: dense-grid rows [y0, y0 + ny), nodes [x0, x0 + nx) (x0, nx multiples of 8)
+  // my window: dense-grid rows [y0, y0 + ny), nodes [x0, x0 + nx) (x0, nx multiples of 8), planes
+  // [z0, z0 + nz) -- the region box_clear zeroed and P2G wrote; everything else in my grid slot is
+  // stale and must neither be sent nor read
   GridMap w = box_window(c, load_box(box));
-  if (c.compact) w.nx = w.ny = 0;   // the slab path keeps x, y dense (fixed halo addresses)
+  if (c.compact) w.nx = w.ny = w.nz = 0;   // the slab path keeps x, y dense (fixed halo addresses)
   const size_t plane = (size_t)G * G;
+  // per side: my planes inside the shared region [zs, zs + npl), as offsets into it
+  int mp0[2], mpn[2];
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    const int lo_pl = max(w.z0, side[s].z0), hi_pl = min(w.z0 + w.nz, side[s].z0 + side[s].npl);
+    mp0[s] = lo_pl - side[s].z0;
+    mpn[s] = (side[s].planes && hi_pl > lo_pl && w.nx > 0 && w.ny > 0) ? hi_pl - lo_pl : 0;
+  }
 #pragma unroll
   for (int s = 0; s < 2; ++s) {
     if (!side[s].planes) continue;
     const float4* __restrict__ src = reinterpret_cast<const float4*>(side[s].planes);
     float4* __restrict__ dst = reinterpret_cast<float4*>(side[s].peer_mail) + (size_t)slot * side[s].npl * plane;
-    for (int row = gw; row < side[s].npl * w.ny; row += nw) {
-      const int pl = row / w.ny, y = w.y0 + (row - pl * w.ny);
+    for (int row = gw; row < mpn[s] * w.ny; row += nw) {
+      const int pl = mp0[s] + row / w.ny, y = w.y0 + row % w.ny;
       const size_t o = (size_t)pl * plane + (size_t)y * G + w.x0;
       for (int xx = lane; xx < w.nx; xx += 32) dst[o + xx] = src[o + xx];
     }
-    if (blockIdx.x == 0 && threadIdx.x < 4) {
-      const int h[4] = {w.x0, w.nx, w.y0, w.ny};
-      side[s].peer_hdr[slot * 4 + threadIdx.x] = h[threadIdx.x];
+    if (blockIdx.x == 0 && threadIdx.x < 6) {
+      const int h[6] = {w.x0, w.nx, w.y0, w.ny, mp0[s], mpn[s]};
+      side[s].peer_hdr[slot * 8 + threadIdx.x] = h[threadIdx.x];
     }
   }
   __threadfence_system();
@@ -445,8 +456,8 @@ halo_exchange_kernel(neuma_halo_side lo, neuma_halo_side hi, neuma_mpm_const c,
     for (int s = 0; s < 2; ++s)
       if (side[s].planes) {
         while (ld_acquire_sys(side[s].my_data_flag) < seq) __nanosleep(32);
-        for (int k = 0; k < 4; ++k)
-          s_hdr[s][k] = *reinterpret_cast<const volatile int*>(side[s].my_hdr + slot * 4 + k);
+        for (int k = 0; k < 6; ++k)
+          s_hdr[s][k] = *reinterpret_cast<const volatile int*>(side[s].my_hdr + slot * 8 + k);
       }
   }
   __syncthreads();
@@ -454,33 +465,27 @@ halo_exchange_kernel(neuma_halo_side lo, neuma_halo_side hi, neuma_mpm_const c,
   for (int s = 0; s < 2; ++s) {
     if (!side[s].planes) continue;
     const int x0 = s_hdr[s][0], nx = s_hdr[s][1], y0 = s_hdr[s][2], ny = s_hdr[s][3];
+    const int sp0 = s_hdr[s][4], spn = s_hdr[s][5];          // the sender's planes inside the shared region
+    if (nx <= 0 || ny <= 0 || spn <= 0) continue;
     float4* __restrict__ dst = reinterpret_cast<float4*>(side[s].planes);
     const float4* src = reinterpret_cast<const float4*>(side[s].my_mail) + (size_t)slot * side[s].npl * plane;
     // (a) rows of MY window, dealt exactly as in the push phase: the warp that pushed a row is
     //     the one that adds into it
-    for (int row = gw; row < side[s].npl * w.ny; row += nw) {
-      const int pl = row / w.ny, y = w.y0 + (row - pl * w.ny);
-      if (y < y0 || y >= y0 + ny) continue;
-      const size_t o = (size_t)pl * plane + (size_t)y * G + x0;
-      for (int xx = lane; xx < nx; xx += 32) {
+    for (int row = gw; row < mpn[s] * w.ny; row += nw) {
+      const int pl = mp0[s] + row / w.ny, y = w.y0 + row % w.ny;
+      if (y < y0 || y >= y0 + ny || pl < sp0 || pl >= sp0 + spn) continue;
+      // nodes outside MY window are never read by my kernels (they lie outside my node box)
+      const int xa = max(x0, w.x0), xb = min(x0 + nx, w.x0 + w.nx);
+      const size_t o = (size_t)pl * plane + (size_t)y * G + xa;
+      for (int xx = lane; xx < xb - xa; xx += 32) {
         float4 a = dst[o + xx];
         const float4 b = __ldcv(src + o + xx);  // written by the peer GPU: never from a stale L1 line
         a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
         dst[o + xx] = a;
       }
     }
-    // (b) rows of the SENDER's window outside mine: nobody pushed them, any warp may add
-    for (int row = gw; row < side[s].npl * ny; row += nw) {
-      const int pl = row / ny, y = y0 + (row - pl * ny);
-      if (y >= w.y0 && y < w.y0 + w.ny) continue;
-      const size_t o = (size_t)pl * plane + (size_t)y * G + x0;
-      for (int xx = lane; xx < nx; xx += 32) {
-        float4 a = dst[o + xx];
-        const float4 b = __ldcv(src + o + xx);
-        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
-        dst[o + xx] = a;
-      }
-    }
+    // (b) rows of the SENDER's window outside mine: nobody pushed them and my kernels never read them
+    //     (they lie outside my node box) -- nothing to do.
   }
   __syncthreads();
   if (threadIdx.x == 0) {

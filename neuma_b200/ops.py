@@ -466,13 +466,13 @@ def halo_add_ack(dst, mailbox, my_data_flag, peer_ack_flag, my_seq, done) -> Non
 
 
 def halo_side(planes, peer_mail, peer_hdr, my_mail, my_hdr, peer_data_flag, my_data_flag, peer_ack_flag,
-              my_ack_flag, npl: int) -> HaloSideC:
+              my_ack_flag, npl: int, z0: int) -> HaloSideC:
     h = HaloSideC()
     for k, t in (("planes", planes), ("peer_mail", peer_mail), ("peer_hdr", peer_hdr), ("my_mail", my_mail),
                  ("my_hdr", my_hdr), ("peer_data_flag", peer_data_flag), ("my_data_flag", my_data_flag),
                  ("peer_ack_flag", peer_ack_flag), ("my_ack_flag", my_ack_flag)):
         setattr(h, k, t.data_ptr())
-    h.npl = int(npl)
+    h.npl, h.z0 = int(npl), int(z0)
     return h
 
 

@@ -214,8 +214,8 @@ class FusedHalo:
         self.mail = symm_mem.empty(self.mshape, dtype=torch.float32, device=device)
         self.mhdl = symm_mem.rendezvous(self.mail, self.group)
         # ints: [0:2] data flag from lower / upper, [2:4] ack flag from lower / upper,
-        #       [8:16] window header from lower (2 slots x 4), [16:24] from upper
-        self.ints = symm_mem.empty((32,), dtype=torch.int32, device=device)
+        #       [8:24] window header from lower (2 slots x 8), [24:40] from upper
+        self.ints = symm_mem.empty((48,), dtype=torch.int32, device=device)
         self.ihdl = symm_mem.rendezvous(self.ints, self.group)
         self.ints.zero_()
         self.cnt = torch.zeros(4, dtype=torch.int32, device=device)
@@ -223,7 +223,7 @@ class FusedHalo:
         self.mhdl.barrier(0)                                   # every rank's flags are zero before anyone pushes
         nbs = [nb for nb in (self.rank - 1, self.rank + 1) if 0 <= nb < self.world]
         self.peer_mail = {nb: self.mhdl.get_buffer(nb, self.mshape, torch.float32, 0) for nb in nbs}
-        self.peer_ints = {nb: self.ihdl.get_buffer(nb, (32,), torch.int32, 0) for nb in nbs}
+        self.peer_ints = {nb: self.ihdl.get_buffer(nb, (48,), torch.int32, 0) for nb in nbs}
 
     def _side(self, planes: torch.Tensor, plan: "SlabPlan", up: bool):
         ov = plan.overlap(self.rank, up)
@@ -235,9 +235,9 @@ class FusedHalo:
         o = 1 - u                          # seen from that neighbour I am its other side
         pi, mi = self.peer_ints[nb], self.ints
         view = planes[ov[0] - z_off: ov[0] - z_off + ov[1]]
-        return self.ops.halo_side(view, self.peer_mail[nb][o], pi[8 + 8 * o: 16 + 8 * o], self.mail[u],
-                                  mi[8 + 8 * u: 16 + 8 * u], pi[o: o + 1], mi[u: u + 1], pi[2 + o: 3 + o],
-                                  mi[2 + u: 3 + u], ov[1])
+        return self.ops.halo_side(view, self.peer_mail[nb][o], pi[8 + 16 * o: 24 + 16 * o], self.mail[u],
+                                  mi[8 + 16 * u: 24 + 16 * u], pi[o: o + 1], mi[u: u + 1], pi[2 + o: 3 + o],
+                                  mi[2 + u: 3 + u], ov[1], ov[0])
 
     def exchange(self, planes: torch.Tensor, plan: "SlabPlan", c, box: torch.Tensor) -> None:
         lo, hi = self._side(planes, plan, False), self._side(planes, plan, True)
@@ -253,7 +253,8 @@ class SlabRollout:
                               range; with overlap=True it runs on a side stream while the
                               particles that do not touch a shared plane go through P2G, grid_op and
                               G2P (forward) / the adjoint scatter, node pass and gather (backward):
-                              boundary particles first -> exchange || interior -> boundary rest;
+                              boundary particles first -> exchange || interior -> boundary rest
+                              (overlap="full"), or only the scatter pass is split (overlap="scatter");
       halo="peer"             round 1: push + add/ack kernel pair per neighbour (PeerHalo);
       halo="nccl"             send/recv pairs, eager launches.
     The classes are decided per particle at run time from its current position (exact under
@@ -262,7 +263,7 @@ class SlabRollout:
     def __init__(self, G: int, dt: float, We, Wp, alpha: float, substeps: int, device, group=None,
                  bound: int = 1, gravity=(0.0, -9.8, 0.0), eps: float = 6e-7, bc: str = "noslip",
                  halo_k: int = 1, elastic_kind: int = 0, halo: str = "fused", use_graphs: Optional[bool] = None,
-                 overlap: bool = True, standalone: bool = False):
+                 overlap="scatter", standalone: bool = False):
         from . import ops
         self.ops = ops
         self.G, self.dt, self.S, self.dev, self.group = int(G), float(dt), int(substeps), device, group
@@ -290,7 +291,17 @@ class SlabRollout:
         self.halo = halo
         self._peer = PeerHalo(G, self.k, device, group) if (halo == "peer" and self.world > 1) else None
         self._fused = FusedHalo(G, self.k, device, group) if (halo == "fused" and self.world > 1) else None
-        self.overlap = bool(overlap) and self._fused is not None
+        # overlap of the exchange with particle work (fused halo only):
+        #   "scatter": the scatter pass (P2G / adjoint scatter) runs boundary class first, the exchange
+        #              goes to a side stream under the interior class's scatter, one join before the
+        #              node pass (ONE extra launch per exchange);
+        #   "full":    the interior class also runs its node pass and gather (G2P / adjoint gather)
+        #              under the exchange (four extra launches per exchange);
+        #   "none" / False: everything in line.
+        overlap = {True: "scatter", False: "none", None: "none"}.get(overlap, overlap)
+        if overlap not in ("none", "scatter", "full"):
+            raise ValueError("overlap must be 'none', 'scatter' or 'full'")
+        self.overlap = overlap if self._fused is not None else "none"
         # graphs need capturable communication: peer memory yes, NCCL send/recv no
         self.use_graphs = (halo != "nccl" or self.world == 1) if use_graphs is None else bool(use_graphs)
         if self.use_graphs and halo == "nccl" and self.world > 1:
@@ -407,15 +418,19 @@ class SlabRollout:
             if self.world > 1 and not windowed:
                 for vw in self._overlap_views(self.grid[s]):       # whole shared planes are added: must be valid
                     vw.zero_()
-            if self.overlap:
+            if self.overlap != "none":
                 self._p2g(self.c_bnd, s)                            # particles touching a shared plane first
                 self._side.wait_stream(main)
                 with torch.cuda.stream(self._side):
                     self._exchange(self.grid[s], self.box[s])       # the ONE exchange of the substep ...
                 self._p2g(self.c_int, s)                            # ... under the interior particles' work
-                self._mpm_fwd(self.c_int, s)
-                main.wait_stream(self._side)
-                self._mpm_fwd(self.c_bnd, s)
+                if self.overlap == "full":
+                    self._mpm_fwd(self.c_int, s)
+                    main.wait_stream(self._side)
+                    self._mpm_fwd(self.c_bnd, s)
+                else:
+                    main.wait_stream(self._side)
+                    self._mpm_fwd(c, s)
             else:
                 self._p2g(c, s)
                 self._exchange(self.grid[s], self.box[s])           # the ONE exchange of the substep
@@ -469,15 +484,19 @@ class SlabRollout:
                                         self.rho, self.clip, self.enabled, self.v[s + 1], self.C[s + 1], gx2, gv2,
                                         gC2, self.gFtrial, self.grid[s], self.adj, self.box[s], gxo, gvo, gCo, gFo,
                                         self.gstress)
-            if self.overlap:
+            if self.overlap != "none":
                 scatter(self.c_bnd)
                 self._side.wait_stream(main)
                 with torch.cuda.stream(self._side):
                     self._exchange(self.adj, self.box[s])           # the ONE exchange of the backward substep
                 scatter(self.c_int)
-                node_gather(self.c_int)
-                main.wait_stream(self._side)
-                node_gather(self.c_bnd)
+                if self.overlap == "full":
+                    node_gather(self.c_int)
+                    main.wait_stream(self._side)
+                    node_gather(self.c_bnd)
+                else:
+                    main.wait_stream(self._side)
+                    node_gather(c)
             else:
                 scatter(c)
                 self._exchange(self.adj, self.box[s])
