@@ -163,7 +163,8 @@ def run_gpu(args):
     pre.load_state(d["x"], d["v"], d["C"], d["F"])
     x0, v0, C0, F0 = [t.clone() for t in pre.sim_forward()]
     del pre
-    eng = FusedFrame(n, cc, statics, We, Wp, wl["w"]["alpha"], S, dev, bind=bind, gaussians=gs, settings=settings)
+    eng = FusedFrame(n, cc, statics, We, Wp, wl["w"]["alpha"], S, dev, bind=bind, gaussians=gs, settings=settings,
+                     fuse=not args.no_fuse)
     eng.load_state(x0, v0, C0, F0)
     k_prev = g["xyz"].to(dev)
     de_x_prev = d["x"].clone()
@@ -172,7 +173,7 @@ def run_gpu(args):
 
     # launches per frame: count one eager (un-graphed) frame with the library's own counter
     eager = FusedFrame(n, cc, statics, We, Wp, wl["w"]["alpha"], S, dev, bind=bind, gaussians=gs,
-                       settings=settings, use_graphs=False)
+                       settings=settings, use_graphs=False, fuse=not args.no_fuse)
     eager.load_state(x0, v0, C0, F0)
     l0 = ctx.launches
     eager.frame_fwd_bwd(gt, de_x_prev, k_prev)
@@ -482,7 +483,7 @@ def slab_measure(dev, world: int, rank: int, substeps: int, steps: int, warmup: 
         # where the exchange time goes: the same frame with the other overlap modes, and without
         # any exchange (wrong results, valid timing)
         by_mode = {sim.overlap: ms}
-        for mode in ("none", "scatter", "full"):
+        for mode in ("none", "split"):
             if mode not in by_mode and sim._fused is not None:
                 sim.overlap, sim._graphs = mode, {}
                 by_mode[mode] = time_ms(sim, g, True)
@@ -609,6 +610,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default=WORKLOAD, choices=["bouncyball-50k-64", "jellyduck-100k-128", "claycat-200k-128"],
                     help="parity-test configs of BASELINE.json for the record; the headline is jellyduck-100k-128")
+    ap.add_argument("--no-fuse", action="store_true",
+                    help="A/B: P2G / adjoint scatter as their own kernels instead of inside the constitutive epilogues")
     ap.add_argument("--no-slab", action="store_true", help="skip the Z-slab (config 5) section of the line")
     ap.add_argument("--slab-steps", type=int, default=5, help="timed frames of the Z-slab section")
     ap.add_argument("--halo", default="fused", choices=["fused", "peer", "nccl"],

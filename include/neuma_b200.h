@@ -48,7 +48,9 @@ typedef struct neuma_ctx neuma_ctx;
  *   sel_mode / sel_lo_end / sel_up_start : Z-slab overlap.  Planes below sel_lo_end
  *       and from sel_up_start on are SHARED with a neighbour rank.  sel_mode 1 restricts a
  *       particle kernel to the particles whose stencil touches a shared plane and a node pass
- *       to the shared planes; sel_mode 2 to the complement; 0 = everything. */
+ *       to the shared planes; sel_mode 2 to the complement; 0 = everything; sel_mode 3 = everything,
+ *       but the launch covers particles the caller classified as interior: one that touches a
+ *       shared plane is counted in box[7] (scatter kernels only). */
 typedef struct {
   int32_t num_grids;
   float dt;
@@ -313,6 +315,25 @@ int neuma_constitutive_bwd_partials(neuma_ctx* ctx, int kind, int n, int hidden,
                                     int accumulate_gF, float* gWpart, void* stream);
 int neuma_constitutive_reduce_partials(neuma_ctx* ctx, int hidden, float* gWpart, float* gW0,
                                        float* gW1, float* gW2, void* stream);
+
+/* MPM work fused into the constitutive kernels' epilogues (what FusedFrame / SlabRollout run):
+ *   neuma_constitutive_fwd_p2g     elasticity (kind 0 or 2) + p2g (mpm.py:321-371) of every enabled
+ *                                  particle into `grid` -- finetune.py:362-363 as ONE kernel; the
+ *                                  stress is still written (the backward reads it);
+ *   neuma_constitutive_bwd_scatter plasticity backward + the adjoint scatter of g2p into `adj`
+ *                                  (= neuma_constitutive_bwd_partials(kind 1) followed by
+ *                                  neuma_mpm_bwd_scatter with gF2 = the gFtrial just computed).
+ * c / box / grid / adj as in the rollout entry points (c->sel_mode applies to the MPM part). */
+int neuma_constitutive_fwd_p2g(neuma_ctx* ctx, int kind, int n, int hidden, const float* F, const void* staged,
+                               float* stress, const neuma_mpm_const* c, const float* x, const float* v,
+                               const float* C, const float* vol, const float* rho, const int32_t* enabled,
+                               const int32_t* box, float* grid, void* stream);
+int neuma_constitutive_bwd_scatter(neuma_ctx* ctx, int n, int hidden, const float* Ftrial, const void* staged,
+                                   float alpha, const float* gout, float* gFtrial, float* gWpart,
+                                   const neuma_mpm_const* c, const float* x, const float* F,
+                                   const float* clip_bound, const int32_t* enabled, const float* v2,
+                                   const float* gx2, const float* gv2, const float* gC2, const int32_t* box,
+                                   float* adj, void* stream);
 
 /* ---- particle -> Gaussian binding: modules/tune/utils.py:424-472 ------- */
 /* out[K,ncol] = B in[Np,ncol] (transpose=0) or out[Np,ncol] = B^T in[K,ncol]

@@ -101,6 +101,8 @@ SIGNATURES = {
     "neuma_constitutive_bwd_staged": [_P, _I, _I, _I, _P, _P, _F, _P, _P, _P, _P, _P, _P],
     "neuma_constitutive_partials_floats": [_P],
     "neuma_constitutive_bwd_partials": [_P, _I, _I, _I, _P, _P, _F, _P, _P, _I, _P, _P],
+    "neuma_constitutive_fwd_p2g": [_P, _I, _I, _I, _P, _P, _P, _CP] + [_P] * 9,
+    "neuma_constitutive_bwd_scatter": [_P, _I, _I, _P, _P, _F, _P, _P, _P, _CP] + [_P] * 11,
     "neuma_constitutive_reduce_partials": [_P, _I, _P, _P, _P, _P, _P],
     "neuma_bind_spmm": [_P, _I, _I, _P, _P, _P, _I, _P, _P, _I, _P],
     "neuma_particles_to_gaussians": [_P, _I] + [_P] * 15,

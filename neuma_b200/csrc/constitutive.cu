@@ -45,6 +45,7 @@
 // which is the exact sum of the dU and dV terms of the textbook SVD adjoint but has
 // no 1/(sigma_i^2 - sigma_j^2) pole at F ~ I (SURVEY 7 "SVD-gradient degeneracy").
 #include "common.cuh"
+#include "mpm_common.cuh"
 #include "svd3.cuh"
 #include "umma.cuh"
 
@@ -420,10 +421,30 @@ __device__ __forceinline__ uint32_t block_setup(Bars* bars, uint32_t* tmem_slot,
   return *tmem_slot;
 }
 
+// ---- MPM work fused into the epilogues (the particle row is already in this thread's hands) -----
+// forward, elasticity: P2G of the particle right after its stress is known -- the fire-and-forget
+// vector reductions of one pipeline's tile overlap the SVD / GELU work of the other pipelines
+// (a stand-alone P2G kernel is bound by the LSU / L2 atomic rate with idle ALUs, this kernel by
+// the ALUs with an idle LSU); grid == NULL: not fused.
+struct FusedP2G {
+  neuma_mpm_const c;
+  const float *x, *v, *C, *vol, *rho;
+  const int32_t *enabled, *box;
+  float4* grid;
+};
+// backward, plasticity: the adjoint scatter of G2P (mpm_rollout.cu::bwd_scatter_adj_kernel) right
+// after dL/dF_trial is known; adj == NULL: not fused.
+struct FusedScatter {
+  neuma_mpm_const c;
+  const float *x, *F, *clip, *v2, *gx2, *gv2, *gC2;
+  const int32_t *enabled, *box;
+  float4* adj;
+};
+
 // ------------------------------------------------------------------ forward
 __global__ void __launch_bounds__(FWD_THREADS, 1)
 constitutive_fwd_kernel(int kind, int n, const float* __restrict__ F, const uint8_t* __restrict__ staged,
-                        float alpha, float* __restrict__ out) {
+                        float alpha, float* __restrict__ out, const FusedP2G fp) {
   constexpr int NS = NS_FWD, NPIPE = NPIPE_FWD;
   using W = WImg<NS>;
   using P = PipeFwd<NS>;
@@ -516,6 +537,10 @@ constitutive_fwd_kernel(int kind, int n, const float* __restrict__ F, const uint
           O = mat3_mul_nt(Pm, k.F);  // cauchy = P F^T
         }
         mat3_store(out + (size_t)pi * 9, O);
+        if (fp.grid && fp.enabled[pi] != 0 && particle_selected(fp.c, fp.x[3 * pi + 2])) {
+          check_interior_class(fp.c, fp.x[3 * pi + 2], fp.box);
+          p2g_particle(fp.c, grid_map(fp.c, fp.box), pi, fp.x, fp.v, fp.C, O.m, fp.vol[pi], fp.rho[pi], fp.grid);
+        }
       }
     }
   }
@@ -530,7 +555,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
 constitutive_bwd_kernel(int kind, int n, const float* __restrict__ F, const uint8_t* __restrict__ staged,
                         float alpha, const float* __restrict__ gout, float* __restrict__ gF,
                         float* __restrict__ gW0, float* __restrict__ gW1, float* __restrict__ gW2,
-                        float* __restrict__ gWpart, int accumulate_gF) {
+                        float* __restrict__ gWpart, int accumulate_gF, const FusedScatter fs) {
   constexpr int NS = NS_BWD, NPIPE = NPIPE_BWD;
   using W = WImg<NS>;
   using P = PipeBwd<NS>;
@@ -779,6 +804,11 @@ constitutive_bwd_kernel(int kind, int n, const float* __restrict__ F, const uint
           for (int i = 0; i < 9; ++i) gFt.m[i] += prev.m[i];
         }
         mat3_store(gF + (size_t)pi * 9, gFt);
+        if (fs.adj && fs.enabled[pi] != 0 && particle_selected(fs.c, fs.x[3 * pi + 2])) {
+          check_interior_class(fs.c, fs.x[3 * pi + 2], fs.box);
+          const G2PAdj g = g2p_adjoint_inputs(fs.c, pi, fs.x, fs.F, fs.clip, fs.v2, fs.gx2, fs.gv2, fs.gC2, gFt.m);
+          g2p_adjoint_scatter(fs.c, grid_map(fs.c, fs.box), pi, fs.x, g, fs.adj);
+        }
       }
       PHASE(13);
     }
@@ -1037,8 +1067,31 @@ int neuma_constitutive_fwd_staged(neuma_ctx* ctx, int kind, int n, int hidden, c
   if (int r = set_attrs(ctx)) return r;
   const int tiles = (n + TP - 1) / TP;
   const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
+  FusedP2G none;
+  memset(&none, 0, sizeof(none));
   NEUMA_CUDA(ctx, neuma_launch(constitutive_fwd_kernel, dim3(grid), dim3(FWD_THREADS), FWD_SMEM, (cudaStream_t)stream,
-                               kind, n, F, (const uint8_t*)staged, alpha, out));
+                               kind, n, F, (const uint8_t*)staged, alpha, out, none));
+  NEUMA_LAUNCH_CHECK(ctx, "constitutive_fwd_kernel");
+  return 0;
+}
+
+int neuma_constitutive_fwd_p2g(neuma_ctx* ctx, int kind, int n, int hidden, const float* F, const void* staged,
+                               float* stress, const neuma_mpm_const* c, const float* x, const float* v,
+                               const float* C, const float* vol, const float* rho, const int32_t* enabled,
+                               const int32_t* box, float* grid, void* stream) {
+  if (int r = check_args(ctx, kind, hidden)) return r;
+  if (kind == 1) return neuma_fail_msg(ctx, "neuma_constitutive_fwd_p2g: elasticity kinds only (0, 2)");
+  if (!c || !x || !v || !C || !vol || !rho || !enabled || !grid || !stress)
+    return neuma_fail_msg(ctx, "neuma_constitutive_fwd_p2g: NULL argument");
+  if ((c->compact || c->sel_mode == 3) && !box)
+    return neuma_fail_msg(ctx, "neuma_constitutive_fwd_p2g: a compact grid / sel_mode 3 needs the box");
+  if (n <= 0) return 0;
+  if (int r = set_attrs(ctx)) return r;
+  const int tiles = (n + TP - 1) / TP;
+  const int grid_dim = tiles < ctx->num_sms ? tiles : ctx->num_sms;
+  FusedP2G fp{*c, x, v, C, vol, rho, enabled, box, (float4*)grid};
+  NEUMA_CUDA(ctx, neuma_launch(constitutive_fwd_kernel, dim3(grid_dim), dim3(FWD_THREADS), FWD_SMEM,
+                               (cudaStream_t)stream, kind, n, F, (const uint8_t*)staged, 0.0f, stress, fp));
   NEUMA_LAUNCH_CHECK(ctx, "constitutive_fwd_kernel");
   return 0;
 }
@@ -1055,12 +1108,14 @@ int neuma_constitutive_bwd_staged(neuma_ctx* ctx, int kind, int n, int hidden, c
   const int tiles = (n + TP - 1) / TP;
   const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
   cudaStream_t st = (cudaStream_t)stream;
+  FusedScatter none;
+  memset(&none, 0, sizeof(none));
   if (wgrad)
     constitutive_bwd_kernel<true><<<grid, BWD_THREADS, BWD_SMEM, st>>>(
-        kind, n, F, (const uint8_t*)staged, alpha, gout, gF, gW0, gW1, gW2, nullptr, 0);
+        kind, n, F, (const uint8_t*)staged, alpha, gout, gF, gW0, gW1, gW2, nullptr, 0, none);
   else
     constitutive_bwd_kernel<false><<<grid, BWD_THREADS, BWD_SMEM, st>>>(
-        kind, n, F, (const uint8_t*)staged, alpha, gout, gF, gW0, gW1, gW2, nullptr, 0);
+        kind, n, F, (const uint8_t*)staged, alpha, gout, gF, gW0, gW1, gW2, nullptr, 0, none);
   NEUMA_LAUNCH_CHECK(ctx, "constitutive_bwd_kernel");
   return 0;
 }
@@ -1076,9 +1131,34 @@ int neuma_constitutive_bwd_partials(neuma_ctx* ctx, int kind, int n, int hidden,
   if (int r = set_attrs(ctx)) return r;
   const int tiles = (n + TP - 1) / TP;
   const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
+  FusedScatter none;
+  memset(&none, 0, sizeof(none));
   NEUMA_CUDA(ctx, neuma_launch(constitutive_bwd_kernel<true>, dim3(grid), dim3(BWD_THREADS), BWD_SMEM,
                                (cudaStream_t)stream, kind, n, F, (const uint8_t*)staged, alpha, gout, gF,
-                               (float*)nullptr, (float*)nullptr, (float*)nullptr, gWpart, accumulate_gF));
+                               (float*)nullptr, (float*)nullptr, (float*)nullptr, gWpart, accumulate_gF, none));
+  NEUMA_LAUNCH_CHECK(ctx, "constitutive_bwd_kernel");
+  return 0;
+}
+
+int neuma_constitutive_bwd_scatter(neuma_ctx* ctx, int n, int hidden, const float* Ftrial, const void* staged,
+                                   float alpha, const float* gout, float* gFtrial, float* gWpart,
+                                   const neuma_mpm_const* c, const float* x, const float* F,
+                                   const float* clip_bound, const int32_t* enabled, const float* v2,
+                                   const float* gx2, const float* gv2, const float* gC2, const int32_t* box,
+                                   float* adj, void* stream) {
+  if (int r = check_args(ctx, 1, hidden)) return r;
+  if (!gWpart || !c || !x || !F || !clip_bound || !enabled || !v2 || !gx2 || !gv2 || !gC2 || !adj || !gFtrial)
+    return neuma_fail_msg(ctx, "neuma_constitutive_bwd_scatter: NULL argument");
+  if ((c->compact || c->sel_mode == 3) && !box)
+    return neuma_fail_msg(ctx, "neuma_constitutive_bwd_scatter: a compact grid / sel_mode 3 needs the box");
+  if (n <= 0) return 0;
+  if (int r = set_attrs(ctx)) return r;
+  const int tiles = (n + TP - 1) / TP;
+  const int grid_dim = tiles < ctx->num_sms ? tiles : ctx->num_sms;
+  FusedScatter fs{*c, x, F, clip_bound, v2, gx2, gv2, gC2, enabled, box, (float4*)adj};
+  NEUMA_CUDA(ctx, neuma_launch(constitutive_bwd_kernel<true>, dim3(grid_dim), dim3(BWD_THREADS), BWD_SMEM,
+                               (cudaStream_t)stream, 1, n, Ftrial, (const uint8_t*)staged, alpha, gout, gFtrial,
+                               (float*)nullptr, (float*)nullptr, (float*)nullptr, gWpart, 0, fs));
   NEUMA_LAUNCH_CHECK(ctx, "constitutive_bwd_kernel");
   return 0;
 }

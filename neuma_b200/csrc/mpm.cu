@@ -38,7 +38,7 @@ p2g_kernel(neuma_mpm_const c, int n, const float* __restrict__ x, const float* _
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
   if (enabled[p] == 0) return;
-  p2g_particle(c, dense_map(c), p, x, v, C, stress, vol[p], rho[p], grid);
+  p2g_particle(c, dense_map(c), p, x, v, C, stress + 9 * (size_t)p, vol[p], rho[p], grid);
 }
 
 // ------------------------------------------------------------------ grid_op (dense)
@@ -87,8 +87,8 @@ bwd_scatter_kernel(neuma_mpm_const c, int n, const float* __restrict__ x,
   if (p >= n) return;
   if (enabled[p] == 0) return;
   const GridMap gm = dense_map(c);
-  p2g_particle(c, gm, p, x, v, C, stress, vol[p], rho[p], grid);
-  const G2PAdj g = g2p_adjoint_inputs(c, p, x, F, clip, v2, gx2, gv2, gC2, gF2);
+  p2g_particle(c, gm, p, x, v, C, stress + 9 * (size_t)p, vol[p], rho[p], grid);
+  const G2PAdj g = g2p_adjoint_inputs(c, p, x, F, clip, v2, gx2, gv2, gC2, gF2 + 9 * (size_t)p);
   g2p_adjoint_scatter(c, gm, p, x, g, gadj);
 }
 

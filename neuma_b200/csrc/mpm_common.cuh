@@ -105,10 +105,18 @@ __device__ __forceinline__ bool plane_selected(const neuma_mpm_const& c, int iz)
   return (c.sel_mode == 1) == shared;
 }
 __device__ __forceinline__ bool particle_selected(const neuma_mpm_const& c, float z) {
-  if (c.sel_mode == 0) return true;
+  if (c.sel_mode == 0 || c.sel_mode == 3) return true;
   const int bz = base_node(z, c.inv_dx);   // the stencil touches planes bz .. bz + 2
   const bool shared = bz < c.sel_lo_end || bz + 2 >= c.sel_up_start;
   return (c.sel_mode == 1) == shared;
+}
+// sel_mode 3: the caller launched this kernel over particles it CLASSIFIED as interior (its scatter
+// runs next to the halo exchange of the boundary class).  One that touches a shared plane after all
+// would be missed by the neighbour: count it in box[7] so that the host raises (SlabRollout.check_drift).
+__device__ __forceinline__ void check_interior_class(const neuma_mpm_const& c, float z, const int32_t* box) {
+  if (c.sel_mode != 3) return;
+  const int bz = base_node(z, c.inv_dx);
+  if (bz < c.sel_lo_end || bz + 2 >= c.sel_up_start) atomicAdd(const_cast<int32_t*>(box) + 7, 1);
 }
 
 // grid_op on one node (mpm.py:373-429).  Returns v; `pass` gets 1/0 per component: whether
@@ -164,18 +172,20 @@ __device__ __forceinline__ void node_velocity(const neuma_mpm_const& c, const fl
 constexpr uint32_t NEG_ZERO = 0x80000000u;
 
 // ---- P2G: one particle's 27 node visits (mpm.py:321-371) into a packed (mv, m) grid --------
+// `stress9`: the particle's 9 stress values (a row of the stress array, or registers of the kernel
+// that just computed them -- constitutive.cu fuses this into the elasticity kernel's epilogue)
 __device__ __forceinline__ void p2g_particle(const neuma_mpm_const& c, const GridMap& gm, int p,
                                              const float* __restrict__ x,
                                              const float* __restrict__ v,
                                              const float* __restrict__ C,
-                                             const float* __restrict__ stress, float p_vol,
+                                             const float* stress9, float p_vol,
                                              float p_rho, float4* __restrict__ grid) {
   const float p_mass = p_vol * p_rho;
   const Stencil s = make_stencil(x[3 * p], x[3 * p + 1], x[3 * p + 2], c.inv_dx);
   const float k = -c.dt * p_vol * 4.0f * c.inv_dx * c.inv_dx;
   float A[9];
 #pragma unroll
-  for (int i = 0; i < 9; ++i) A[i] = k * stress[9 * p + i] + p_mass * C[9 * p + i];
+  for (int i = 0; i < 9; ++i) A[i] = k * stress9[i] + p_mass * C[9 * p + i];
   const float pv[3] = {p_mass * v[3 * p], p_mass * v[3 * p + 1], p_mass * v[3 * p + 2]};
 #pragma unroll
   for (int i = 0; i < 3; ++i)
@@ -283,7 +293,7 @@ __device__ __forceinline__ G2PAdj g2p_adjoint_inputs(const neuma_mpm_const& c, i
                                                      const float* __restrict__ gx2,
                                                      const float* __restrict__ gv2,
                                                      const float* __restrict__ gC2,
-                                                     const float* __restrict__ gF2) {
+                                                     const float* gF2row /* dL/dF' of THIS particle */) {
   G2PAdj r;
   const float bnd = clip[p] * c.dx;
   const float lo = 0.0f + bnd, hi = 1.0f - bnd;
@@ -301,7 +311,7 @@ __device__ __forceinline__ G2PAdj g2p_adjoint_inputs(const neuma_mpm_const& c, i
     for (int b = 0; b < 3; ++b) {
       float acc = 0.f;
 #pragma unroll
-      for (int k = 0; k < 3; ++k) acc += gF2[9 * p + 3 * a + k] * F[9 * p + 3 * b + k];
+      for (int k = 0; k < 3; ++k) acc += gF2row[3 * a + k] * F[9 * p + 3 * b + k];
       r.gCt[3 * a + b] = gC2[9 * p + 3 * a + b] + c.dt * acc;
     }
   return r;
@@ -358,7 +368,7 @@ __device__ __forceinline__ void bwd_gather_particle(
 #pragma unroll
   for (int i = 0; i < 9; ++i) A[i] = ks * stress[9 * p + i] + p_mass * C[9 * p + i];
   const float pv[3] = {p_mass * v[3 * p], p_mass * v[3 * p + 1], p_mass * v[3 * p + 2]};
-  const G2PAdj g = g2p_adjoint_inputs(c, p, x, F, clip, v2, gx2, gv2, gC2, gF2);
+  const G2PAdj g = g2p_adjoint_inputs(c, p, x, F, clip, v2, gx2, gv2, gC2, gF2 + 9 * (size_t)p);
   constexpr bool need_C = !HAVE_C2;
 
   float acc_gmv[3] = {0.f, 0.f, 0.f};  // sum_n W g_mv

@@ -138,8 +138,9 @@ p2g_to_kernel(neuma_mpm_const c, int n, const float* __restrict__ x, const float
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
   if (enabled[p] == 0 || !particle_selected(c, x[3 * p + 2])) return;
+  check_interior_class(c, x[3 * p + 2], box);
   const GridMap gm = grid_map(c, box);
-  p2g_particle(c, gm, p, x, v, C, stress, vol[p], rho[p], grid);
+  p2g_particle(c, gm, p, x, v, C, stress + 9 * (size_t)p, vol[p], rho[p], grid);
 }
 
 // grid_op over the box, in place: (mv, m) -> (v, m); BC-zeroed components become -0.0f.
@@ -203,8 +204,9 @@ bwd_scatter_adj_kernel(neuma_mpm_const c, int n, const float* __restrict__ x,
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
   if (enabled[p] == 0 || !particle_selected(c, x[3 * p + 2])) return;
+  check_interior_class(c, x[3 * p + 2], box);
   const GridMap gm = grid_map(c, box);
-  const G2PAdj g = g2p_adjoint_inputs(c, p, x, F, clip, v2, gx2, gv2, gC2, gF2);
+  const G2PAdj g = g2p_adjoint_inputs(c, p, x, F, clip, v2, gx2, gv2, gC2, gF2 + 9 * (size_t)p);
   g2p_adjoint_scatter(c, gm, p, x, g, gadj);
 }
 
@@ -553,7 +555,8 @@ int neuma_mpm_p2g_to(neuma_ctx* ctx, const neuma_mpm_const* c, int n, const floa
                      const int32_t* enabled, const int32_t* box, float* grid, void* stream) {
   if (int r = check_slab(ctx, c)) return r;
   if (n <= 0) return 0;
-  if (c->compact && !box) return neuma_fail_msg(ctx, "neuma_mpm_p2g_to: a compact grid needs its box");
+  if ((c->compact || c->sel_mode == 3) && !box)
+    return neuma_fail_msg(ctx, "neuma_mpm_p2g_to: a compact grid / sel_mode 3 needs the box");
   const int pb = pblock(256);
   NEUMA_CUDA(ctx, neuma_launch(p2g_to_kernel, dim3((n + pb - 1) / pb), dim3(pb), 0, (cudaStream_t)stream, *c, n, x,
                                v, C, stress, vol, rho, enabled, box, (float4*)grid));
@@ -606,7 +609,8 @@ int neuma_mpm_bwd_scatter(neuma_ctx* ctx, const neuma_mpm_const* c, int n, const
                           const float* gF2, const int32_t* box, float* adj, void* stream) {
   if (int r = check_slab(ctx, c)) return r;
   if (n <= 0) return 0;
-  if (c->compact && !box) return neuma_fail_msg(ctx, "neuma_mpm_bwd_scatter: a compact grid needs its box");
+  if ((c->compact || c->sel_mode == 3) && !box)
+    return neuma_fail_msg(ctx, "neuma_mpm_bwd_scatter: a compact grid / sel_mode 3 needs the box");
   if (!v2 || !gx2 || !gv2 || !gC2 || !gF2 || !adj)
     return neuma_fail_msg(ctx, "neuma_mpm_bwd_scatter: NULL argument");
   const int pb = pblock(256);

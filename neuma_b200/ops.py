@@ -393,6 +393,23 @@ def constitutive_bwd_partials(kind: int, F, staged, alpha: float, gout, gF, gWpa
                  C.c_float(alpha), ptr(gout), ptr(gF), int(accumulate_gF), ptr(gWpart), _stream(F))
 
 
+def constitutive_fwd_p2g(kind: int, F, staged, stress, c: MPMConstC, x, v, Cm, vol, rho, enabled, grid, box=None,
+                         hidden: int = 64) -> None:
+    """elasticity + P2G in one kernel (neuma_constitutive_fwd_p2g)."""
+    _ctx(F).call("neuma_constitutive_fwd_p2g", int(kind), F.shape[0], hidden, ptr(F), ptr(staged), ptr(stress),
+                 C.byref(c), ptr(x), ptr(v), ptr(Cm), ptr(vol), ptr(rho), ptr(enabled), ptr(box), ptr(grid),
+                 _stream(F))
+
+
+def constitutive_bwd_scatter(Ftrial, staged, alpha: float, gout, gFtrial, gWpart, c: MPMConstC, x, F, clip_bound,
+                             enabled, v2, gx2, gv2, gC2, adj, box=None, hidden: int = 64) -> None:
+    """plasticity backward + adjoint scatter of G2P in one kernel (neuma_constitutive_bwd_scatter)."""
+    _ctx(F).call("neuma_constitutive_bwd_scatter", Ftrial.shape[0], hidden, ptr(Ftrial), ptr(staged),
+                 C.c_float(alpha), ptr(gout), ptr(gFtrial), ptr(gWpart), C.byref(c), ptr(x), ptr(F),
+                 ptr(clip_bound), ptr(enabled), ptr(v2), ptr(gx2), ptr(gv2), ptr(gC2), ptr(box), ptr(adj),
+                 _stream(F))
+
+
 def constitutive_reduce_partials(gWpart, gW0, gW1, gW2, hidden: int = 64) -> None:
     """gW* += sum of the slots; the slots are zeroed."""
     _ctx(gWpart).call("neuma_constitutive_reduce_partials", hidden, ptr(gWpart), ptr(gW0), ptr(gW1), ptr(gW2),

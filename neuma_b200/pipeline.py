@@ -39,7 +39,7 @@ class FusedFrame:
                  alpha: float, substeps: int, device, bind=None, gaussians=None,
                  settings: Optional[RasterSettingsC] = None, center=None, size=None,
                  elastic_kind: int = ops.KIND_ELASTIC, use_graphs: bool = True, sort: bool = True,
-                 compact: bool = True, grid_margin: int = 6, cap_nodes: Optional[int] = None):
+                 compact: bool = True, grid_margin: int = 6, cap_nodes: Optional[int] = None, fuse: bool = True):
         """compact: saved grids hold the node bounding box only; their capacity is fixed at the first
         load_state() from that state's box widened by `grid_margin` nodes on every side (room for
         the cloud to move / deform over the frames this engine will see), or given as cap_nodes.
@@ -50,6 +50,7 @@ class FusedFrame:
         # statics in the engine's (cell-sorted) particle order; refreshed by load_state()
         self.vol, self.rho, self.clip, self.enabled = [t.clone() for t in self._statics_in]
         self.sort = bool(sort)
+        self.fuse = bool(fuse)       # P2G / adjoint scatter inside the constitutive kernels' epilogues
         self.perm = torch.arange(n, device=device, dtype=torch.int32)   # sorted slot -> caller index
         self.inv = self.perm.clone()                                    # caller index -> sorted slot
         self.We = [w.detach().clone().contiguous() for w in We]     # engine-owned static buffers (set_weights)
@@ -131,21 +132,30 @@ class FusedFrame:
     def _sim_forward(self) -> None:
         c = self.c
         main = torch.cuda.current_stream(self.dev)
+        ops.mpm_box_clear(c, self.box[0], self.grid[0], None, self.box[1])
         for s in range(self.S):
-            # the box clear of this substep's grid slot runs on a side branch next to the elasticity
-            # kernel (both only need the previous substep's G2P): one kernel boundary less on the path
-            self._side.wait_stream(main)
-            with torch.cuda.stream(self._side):
-                ops.mpm_box_clear(c, self.box[s], self.grid[s], None, self.box[s + 1])
-            ops.constitutive_fwd_staged(self.kind_e, self.F[s], self.We_st, 0.0, self.stress[s])
-            main.wait_stream(self._side)
-            ops.mpm_p2g_to(c, self.x[s], self.v[s], self.C[s], self.stress[s], self.vol, self.rho, self.enabled,
-                           self.grid[s], box=self.box[s])
+            if self.fuse:
+                # elasticity + P2G in ONE kernel: the particle is scattered by the thread that just
+                # computed its stress (csrc/constitutive.cu, FusedP2G)
+                ops.constitutive_fwd_p2g(self.kind_e, self.F[s], self.We_st, self.stress[s], c, self.x[s], self.v[s],
+                                         self.C[s], self.vol, self.rho, self.enabled, self.grid[s], box=self.box[s])
+            else:
+                ops.constitutive_fwd_staged(self.kind_e, self.F[s], self.We_st, 0.0, self.stress[s])
+                ops.mpm_p2g_to(c, self.x[s], self.v[s], self.C[s], self.stress[s], self.vol, self.rho, self.enabled,
+                               self.grid[s], box=self.box[s])
             ops.mpm_grid_op_box(c, self.box[s], self.grid[s], None)
             ops.mpm_g2p_from(c, self.x[s], self.F[s], self.clip, self.enabled, self.grid[s],
                              (self.x[s + 1], self.v[s + 1], self.C[s + 1], self.Ftrial[s]), self.box[s + 1],
                              box=self.box[s])
+            if s + 1 < self.S:
+                # the box clear of the NEXT substep's grid slot runs on a side branch next to the
+                # plasticity kernel (both only need this substep's G2P)
+                self._side.wait_stream(main)
+                with torch.cuda.stream(self._side):
+                    ops.mpm_box_clear(c, self.box[s + 1], self.grid[s + 1], None, self.box[s + 2])
             ops.constitutive_fwd_staged(ops.KIND_PLASTIC, self.Ftrial[s], self.Wp_st, self.alpha, self.F[s + 1])
+            if s + 1 < self.S:
+                main.wait_stream(self._side)
 
     def _sim_backward(self) -> None:
         """Consumes self.g[0] = dL/d(state[S]); leaves dL/d(state[0]) in self.g[0]
@@ -153,25 +163,35 @@ class FusedFrame:
         c = self.c
         main = torch.cuda.current_stream(self.dev)
         cur, nxt = 0, 1
+        # the ONE adjoint scatter target is cleared over a substep's box inside the backward itself
+        ops.mpm_box_clear(c, self.box[self.S - 1], self.adj, None, None)
         for s in reversed(range(self.S)):
             gx2, gv2, gC2, gF_next = self.g[cur]
-            # the adjoint scatter target is cleared over this substep's box on a side branch, next to
-            # the plasticity backward (it was last read by the gather of substep s + 1)
-            self._side.wait_stream(main)
-            with torch.cuda.stream(self._side):
-                ops.mpm_box_clear(c, self.box[s], self.adj, None, None)
-            # plasticity: F[s+1] = P(Ftrial[s])
-            ops.constitutive_bwd_partials(ops.KIND_PLASTIC, self.Ftrial[s], self.Wp_st, self.alpha, gF_next,
-                                          self.gFtrial, self.gWp_part)
-            main.wait_stream(self._side)
             gx, gv, gC, gF = self.g[nxt]
-            ops.mpm_rollout_bwd(c, self.x[s], self.v[s], self.C[s], self.F[s], self.stress[s], self.vol,
-                                self.rho, self.clip, self.enabled, self.v[s + 1], self.C[s + 1],
-                                gx2, gv2, gC2, self.gFtrial, self.grid[s], self.adj, self.box[s],
-                                gx, gv, gC, gF, self.gstress)
+            # plasticity: F[s+1] = P(Ftrial[s]); then adj(G2P) scatters dL/dv_node into adj
+            if self.fuse:
+                ops.constitutive_bwd_scatter(self.Ftrial[s], self.Wp_st, self.alpha, gF_next, self.gFtrial,
+                                             self.gWp_part, c, self.x[s], self.F[s], self.clip, self.enabled,
+                                             self.v[s + 1], gx2, gv2, gC2, self.adj, box=self.box[s])
+            else:
+                ops.constitutive_bwd_partials(ops.KIND_PLASTIC, self.Ftrial[s], self.Wp_st, self.alpha, gF_next,
+                                              self.gFtrial, self.gWp_part)
+                ops.mpm_bwd_scatter(c, self.x[s], self.F[s], self.clip, self.enabled, self.v[s + 1], gx2, gv2, gC2,
+                                    self.gFtrial, self.adj, box=self.box[s])
+            ops.mpm_bwd_node_gather(c, self.x[s], self.v[s], self.C[s], self.F[s], self.stress[s], self.vol,
+                                    self.rho, self.clip, self.enabled, self.v[s + 1], self.C[s + 1], gx2, gv2, gC2,
+                                    self.gFtrial, self.grid[s], self.adj, self.box[s], gx, gv, gC, gF, self.gstress)
+            if s > 0:
+                # adj was last read by the gather above: clear it for substep s - 1 next to the
+                # elasticity backward
+                self._side.wait_stream(main)
+                with torch.cuda.stream(self._side):
+                    ops.mpm_box_clear(c, self.box[s - 1], self.adj, None, None)
             # elasticity: stress[s] = E(F[s]);  dL/dF[s] += E'(F[s])^T gstress
             ops.constitutive_bwd_partials(self.kind_e, self.F[s], self.We_st, 0.0, self.gstress, gF,
                                           self.gWe_part, accumulate_gF=True)
+            if s > 0:
+                main.wait_stream(self._side)
             cur, nxt = nxt, cur
         ops.constitutive_reduce_partials(self.gWe_part, *self.gWe)
         ops.constitutive_reduce_partials(self.gWp_part, *self.gWp)

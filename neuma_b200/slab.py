@@ -263,7 +263,7 @@ class SlabRollout:
     def __init__(self, G: int, dt: float, We, Wp, alpha: float, substeps: int, device, group=None,
                  bound: int = 1, gravity=(0.0, -9.8, 0.0), eps: float = 6e-7, bc: str = "noslip",
                  halo_k: int = 1, elastic_kind: int = 0, halo: str = "fused", use_graphs: Optional[bool] = None,
-                 overlap="scatter", standalone: bool = False):
+                 overlap="split", standalone: bool = False, fuse: bool = True):
         from . import ops
         self.ops = ops
         self.G, self.dt, self.S, self.dev, self.group = int(G), float(dt), int(substeps), device, group
@@ -298,10 +298,16 @@ class SlabRollout:
         #   "full":    the interior class also runs its node pass and gather (G2P / adjoint gather)
         #              under the exchange (four extra launches per exchange);
         #   "none" / False: everything in line.
-        overlap = {True: "scatter", False: "none", None: "none"}.get(overlap, overlap)
-        if overlap not in ("none", "scatter", "full"):
-            raise ValueError("overlap must be 'none', 'scatter' or 'full'")
+        #   "split":   the particles are kept boundary class first (static classes with a margin of k
+        #              planes, decided at distribute()); elasticity + P2G of the boundary range, then
+        #              the exchange on a side stream under elasticity + P2G of the interior range
+        #              (backward: plasticity backward + adjoint scatter likewise).  An interior-range
+        #              particle that touches a shared plane after all is counted on the device.
+        overlap = {True: "split", False: "none", None: "none"}.get(overlap, overlap)
+        if overlap not in ("none", "scatter", "full", "split"):
+            raise ValueError("overlap must be 'none', 'split', 'scatter' or 'full'")
         self.overlap = overlap if self._fused is not None else "none"
+        self.fuse = bool(fuse)      # P2G / adjoint scatter inside the constitutive kernels' epilogues
         # graphs need capturable communication: peer memory yes, NCCL send/recv no
         self.use_graphs = (halo != "nccl" or self.world == 1) if use_graphs is None else bool(use_graphs)
         if self.use_graphs and halo == "nccl" and self.world > 1:
@@ -326,8 +332,16 @@ class SlabRollout:
         up_start = ov_up[0] if ov_up is not None else (1 << 30)
         self.c_bnd = self.c.variant(sel_mode=1, sel_lo_end=lo_end, sel_up_start=up_start)
         self.c_int = self.c.variant(sel_mode=2, sel_lo_end=lo_end, sel_up_start=up_start)
+        self.c_chk = self.c.variant(sel_mode=3, sel_lo_end=lo_end, sel_up_start=up_start)
         loc = [t[mine.to(t.device)].to(dev).contiguous() for t in (x, v, C, F, vol, rho, clip, enabled)]
         perm = ops.mpm_cell_order(self.c, loc[0]) if loc[0].shape[0] else torch.zeros(0, dtype=torch.int32, device=dev)
+        # boundary class first (cell order inside each class): particles whose stencil can reach a
+        # shared plane within the frame -- the exact criterion widened by the drift allowance k
+        bz = SlabPlan.base_plane(loc[0][:, 2], G)[perm.long()]
+        bnd = (bz < lo_end + self.k) | (bz + 2 >= up_start - self.k)
+        order = torch.cat([bnd.nonzero(as_tuple=True)[0], (~bnd).nonzero(as_tuple=True)[0]])
+        perm = perm[order].contiguous()
+        self.nb = int(bnd.sum().item())
         loc = [ops.gather_rows(t, perm) if t.shape[0] else t for t in loc]
         self.ids = mine.to(dev)[perm.long()]
         n = self.n = int(loc[0].shape[0])
@@ -406,19 +420,38 @@ class SlabRollout:
 
     def _p2g(self, c, s: int) -> None:
         self.ops.mpm_p2g_to(c, self.x[s], self.v[s], self.C[s], self.stress[s], self.vol, self.rho, self.enabled,
-                            self.grid[s])
+                            self.grid[s], box=self.box[s])
+
+    def _elastic_p2g(self, c, s: int, lo: int, hi: int) -> None:
+        """elasticity (+ P2G, fused or as a second kernel) of the particle range [lo, hi)"""
+        ops = self.ops
+        if hi <= lo:
+            return
+        sl = slice(lo, hi)
+        if self.fuse:
+            ops.constitutive_fwd_p2g(self.kind_e, self.F[s][sl], self.We_st, self.stress[s][sl], c, self.x[s][sl],
+                                     self.v[s][sl], self.C[s][sl], self.vol[sl], self.rho[sl], self.enabled[sl],
+                                     self.grid[s], box=self.box[s])
+        else:
+            ops.constitutive_fwd_staged(self.kind_e, self.F[s][sl], self.We_st, 0.0, self.stress[s][sl])
+            ops.mpm_p2g_to(c, self.x[s][sl], self.v[s][sl], self.C[s][sl], self.stress[s][sl], self.vol[sl],
+                           self.rho[sl], self.enabled[sl], self.grid[s], box=self.box[s])
 
     def _forward_body(self) -> None:
         ops, c = self.ops, self.c
         main = torch.cuda.current_stream(self.dev)
         windowed = self._fused is not None
-        for s in range(self.S):
-            ops.constitutive_fwd_staged(self.kind_e, self.F[s], self.We_st, 0.0, self.stress[s])
+        legacy = self.overlap in ("scatter", "full")
+
+        def clear(s):
             ops.mpm_box_clear(c, self.box[s], self.grid[s], None, self.box[s + 1])
             if self.world > 1 and not windowed:
                 for vw in self._overlap_views(self.grid[s]):       # whole shared planes are added: must be valid
                     vw.zero_()
-            if self.overlap != "none":
+        clear(0)
+        for s in range(self.S):
+            if legacy:
+                ops.constitutive_fwd_staged(self.kind_e, self.F[s], self.We_st, 0.0, self.stress[s])
                 self._p2g(self.c_bnd, s)                            # particles touching a shared plane first
                 self._side.wait_stream(main)
                 with torch.cuda.stream(self._side):
@@ -431,11 +464,25 @@ class SlabRollout:
                 else:
                     main.wait_stream(self._side)
                     self._mpm_fwd(c, s)
+            elif self.overlap == "split":
+                self._elastic_p2g(c, s, 0, self.nb)                 # boundary range: elasticity + P2G
+                self._side.wait_stream(main)
+                with torch.cuda.stream(self._side):
+                    self._exchange(self.grid[s], self.box[s])       # the ONE exchange of the substep ...
+                self._elastic_p2g(self.c_chk, s, self.nb, self.n)   # ... under the interior range's kernel
+                main.wait_stream(self._side)
+                self._mpm_fwd(c, s)
             else:
-                self._p2g(c, s)
+                self._elastic_p2g(c, s, 0, self.n)
                 self._exchange(self.grid[s], self.box[s])           # the ONE exchange of the substep
                 self._mpm_fwd(c, s)
+            if s + 1 < self.S:        # next substep's grid clear on a side branch next to the plasticity kernel
+                self._side.wait_stream(main)
+                with torch.cuda.stream(self._side):
+                    clear(s + 1)
             ops.constitutive_fwd_staged(ops.KIND_PLASTIC, self.Ftrial[s], self.Wp_st, self.alpha, self.F[s + 1])
+            if s + 1 < self.S:
+                main.wait_stream(self._side)
 
     def backward(self, gx, gv, gC, gF):
         """dL/d(local state[S]) -> dL/d(local state[0]); gWe / gWp hold the ALL-REDUCED weight gradients."""
@@ -456,35 +503,52 @@ class SlabRollout:
                 o += t.numel()
         return self.g[self.S % 2]
 
+    def _plastic_bwd_scatter(self, c, s: int, lo: int, hi: int, gx2, gv2, gC2, gF_next) -> None:
+        """plasticity backward (+ adjoint scatter of G2P, fused or as a second kernel) of [lo, hi)"""
+        ops = self.ops
+        if hi <= lo:
+            return
+        sl = slice(lo, hi)
+        if self.fuse:
+            ops.constitutive_bwd_scatter(self.Ftrial[s][sl], self.Wp_st, self.alpha, gF_next[sl], self.gFtrial[sl],
+                                         self.gWp_part, c, self.x[s][sl], self.F[s][sl], self.clip[sl],
+                                         self.enabled[sl], self.v[s + 1][sl], gx2[sl], gv2[sl], gC2[sl], self.adj,
+                                         box=self.box[s])
+        else:
+            ops.constitutive_bwd_partials(ops.KIND_PLASTIC, self.Ftrial[s][sl], self.Wp_st, self.alpha, gF_next[sl],
+                                          self.gFtrial[sl], self.gWp_part)
+            ops.mpm_bwd_scatter(c, self.x[s][sl], self.F[s][sl], self.clip[sl], self.enabled[sl], self.v[s + 1][sl],
+                                gx2[sl], gv2[sl], gC2[sl], self.gFtrial[sl], self.adj, box=self.box[s])
+
     def _backward_body(self) -> None:
         ops, c = self.ops, self.c
         main = torch.cuda.current_stream(self.dev)
         windowed = self._fused is not None
+        legacy = self.overlap in ("scatter", "full")
         cur, nxt = 0, 1
+
+        def clear(s):      # the ONE adjoint scatter target, cleared over a substep's box inside the backward
+            ops.mpm_box_clear(c, self.box[s], self.adj, None, None)
+            if self.world > 1 and not windowed:
+                for vw in self._overlap_views(self.adj):
+                    vw.zero_()
+        clear(self.S - 1)
         for s in reversed(range(self.S)):
             gx2, gv2, gC2, gF_next = self.g[cur]
-            # clear the adjoint scatter target over this substep's box next to the plasticity backward
-            self._side.wait_stream(main)
-            with torch.cuda.stream(self._side):
-                ops.mpm_box_clear(c, self.box[s], self.adj, None, None)
-                if self.world > 1 and not windowed:
-                    for vw in self._overlap_views(self.adj):
-                        vw.zero_()
-            ops.constitutive_bwd_partials(ops.KIND_PLASTIC, self.Ftrial[s], self.Wp_st, self.alpha, gF_next,
-                                          self.gFtrial, self.gWp_part)
-            main.wait_stream(self._side)
             gxo, gvo, gCo, gFo = self.g[nxt]
 
             def scatter(cc):
                 ops.mpm_bwd_scatter(cc, self.x[s], self.F[s], self.clip, self.enabled, self.v[s + 1], gx2, gv2, gC2,
-                                    self.gFtrial, self.adj)
+                                    self.gFtrial, self.adj, box=self.box[s])
 
             def node_gather(cc):
                 ops.mpm_bwd_node_gather(cc, self.x[s], self.v[s], self.C[s], self.F[s], self.stress[s], self.vol,
                                         self.rho, self.clip, self.enabled, self.v[s + 1], self.C[s + 1], gx2, gv2,
                                         gC2, self.gFtrial, self.grid[s], self.adj, self.box[s], gxo, gvo, gCo, gFo,
                                         self.gstress)
-            if self.overlap != "none":
+            if legacy:
+                ops.constitutive_bwd_partials(ops.KIND_PLASTIC, self.Ftrial[s], self.Wp_st, self.alpha, gF_next,
+                                              self.gFtrial, self.gWp_part)
                 scatter(self.c_bnd)
                 self._side.wait_stream(main)
                 with torch.cuda.stream(self._side):
@@ -497,12 +561,26 @@ class SlabRollout:
                 else:
                     main.wait_stream(self._side)
                     node_gather(c)
+            elif self.overlap == "split":
+                self._plastic_bwd_scatter(c, s, 0, self.nb, gx2, gv2, gC2, gF_next)
+                self._side.wait_stream(main)
+                with torch.cuda.stream(self._side):
+                    self._exchange(self.adj, self.box[s])           # the ONE exchange of the backward substep
+                self._plastic_bwd_scatter(self.c_chk, s, self.nb, self.n, gx2, gv2, gC2, gF_next)
+                main.wait_stream(self._side)
+                node_gather(c)
             else:
-                scatter(c)
+                self._plastic_bwd_scatter(c, s, 0, self.n, gx2, gv2, gC2, gF_next)
                 self._exchange(self.adj, self.box[s])
                 node_gather(c)
+            if s > 0:          # adj was last read by the gather: clear it for substep s - 1 next to the elasticity bwd
+                self._side.wait_stream(main)
+                with torch.cuda.stream(self._side):
+                    clear(s - 1)
             ops.constitutive_bwd_partials(self.kind_e, self.F[s], self.We_st, 0.0, self.gstress, gFo,
                                           self.gWe_part, accumulate_gF=True)
+            if s > 0:
+                main.wait_stream(self._side)
             cur, nxt = nxt, cur
 
     # ------------------------------------------------------------------ ownership

@@ -48,7 +48,7 @@ def _reference(dev, n, G, S, dt):
     return out, g0, [t.clone() for t in eng.gWe + eng.gWp]
 
 
-def _slab_run(rank, world, port, n, G, S, dt, q, halo="fused", overlap="scatter", vscale=1.0):
+def _slab_run(rank, world, port, n, G, S, dt, q, halo="fused", overlap="split", vscale=1.0):
     from neuma_b200.slab import SlabRollout
     if world > 1:
         os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -120,8 +120,9 @@ def test_slab_world1_matches_fused_frame(cuda_dev):
     _check(res, gW, ref)
 
 
-@pytest.mark.parametrize("world,halo,overlap", [(2, "fused", "scatter"), (2, "fused", "full"), (2, "fused", "none"),
-                                                 (2, "peer", "none"), (2, "nccl", "none"), (4, "fused", "scatter")])
+@pytest.mark.parametrize("world,halo,overlap", [(2, "fused", "split"), (2, "fused", "scatter"), (2, "fused", "full"),
+                                                 (2, "fused", "none"), (2, "peer", "none"), (2, "nccl", "none"),
+                                                 (4, "fused", "split")])
 def test_slab_multi_gpu_matches_single(cuda_dev, world, halo, overlap):
     """halo="fused": one windowed exchange kernel per substep on a side stream under the interior
     particles' work (overlap) or in line; halo="peer": round-1 push / add kernel pairs; halo="nccl":
@@ -157,7 +158,7 @@ def test_slab_drift_beyond_halo_is_detected(cuda_dev):
     q = ctx.Queue()
     port = _free_port()
     # |v| ~ 60: 6 substeps x 2.5e-4 x 60 x 64 cells = 5.8 planes > k + 2
-    procs = [ctx.Process(target=_slab_run, args=(r, 2, port, n, G, S, dt, q, "fused", "scatter", 200.0)) for r in range(2)]
+    procs = [ctx.Process(target=_slab_run, args=(r, 2, port, n, G, S, dt, q, "fused", "split", 200.0)) for r in range(2)]
     for p in procs:
         p.start()
     got = [q.get(timeout=300) for _ in range(2)]
