@@ -48,6 +48,7 @@
 #include "mpm_common.cuh"
 #include "svd3.cuh"
 #include "umma.cuh"
+#include <stdlib.h>
 
 // Developer instrumentation (tools/phase_timing.py builds a copy with -DNEUMA_PHASE_TIMING):
 // thread 0 of CTA 0 accumulates clock64() deltas per phase of its pipeline.
@@ -145,7 +146,18 @@ struct PipeBwd {
 };
 constexpr uint32_t FWD_SMEM = WImg<NS_FWD>::BYTES + NPIPE_FWD * PipeFwd<NS_FWD>::BYTES;  // 221184
 constexpr uint32_t BWD_SMEM = WImg<NS_BWD>::BYTES + NPIPE_BWD * PipeBwd<NS_BWD>::BYTES;  // 188416
-constexpr int FWD_THREADS = NPIPE_FWD * TP + 32, BWD_THREADS = NPIPE_BWD * TP + 32;
+// RT = threads per particle row (1 or 2).  With RT = 2 a pipeline has 8 warps: warps 0-3 ("owners")
+// hold the particle rows -- SVD, invariants, output head -- and the columns [0, 32) of the GELU /
+// gradient phases, warps 4-7 ("helpers") the columns [32, 64) of the same rows (a warp reaches the
+// TMEM lanes 32 (warp % 4) ..., so warp w and w + 4 share a lane quarter).  Twice the warps per SM
+// for the phases that dominate (GELU + split + store: 60 % of a tile), same shared memory.
+template <int RT> constexpr int fwd_threads() { return NPIPE_FWD * TP * RT + 32; }
+template <int RT> constexpr int bwd_threads() { return NPIPE_BWD * TP * RT + 32; }
+// backward, RT = 2: F, U, V, sigma of the row parked in shared memory between the phases
+// ([element][row]: conflict-free), so that 544 threads fit the register file
+constexpr int STASH_FLOATS = 30;
+constexpr uint32_t STASH_BYTES = STASH_FLOATS * TP * 4;
+template <int RT> constexpr uint32_t bwd_smem() { return BWD_SMEM + (RT == 2 ? NPIPE_BWD * STASH_BYTES : 0u); }
 
 // ---- TMEM columns (fp32, lane = particle row unless noted)
 constexpr uint32_t FWD_PIPE_COLS = 64, FWD_TMEM_COLS = 256;
@@ -301,14 +313,15 @@ __device__ __forceinline__ bool mbar_test(uint32_t mbar, uint32_t parity) {
 }
 struct PipeSync {
   uint32_t done, wfull, wdone;  // shared-memory addresses of the pipeline's mbarriers
-  uint32_t bar_id;              // named barrier of the pipeline (1 + p), 128 threads
+  uint32_t bar_id;              // named barrier of the pipeline (1 + p)
   uint32_t ph_done, ph_wdone;
+  uint32_t nthreads;            // threads of the pipeline (128 RT)
   // my smem operand writes / TMEM accesses of this phase are finished; returns once every
   // thread of the pipeline got here
   __device__ __forceinline__ void publish() const {
     umma::fence_async_smem();
     umma::fence_before_sync();
-    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(TP) : "memory");
+    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nthreads) : "memory");
   }
   // non-blocking hand-over to a dedicated issuing warp polling wfull
   __device__ __forceinline__ void publish_async() const {
@@ -330,10 +343,12 @@ struct PipeSync {
 
 // GELU phase of one particle row: read the 64 accumulator columns, write gelu() as the next
 // GEMM's A operand and, in the backward, put gelu'() back into the same TMEM columns.
-template <int NS, bool KEEP_GRAD>
-__device__ __forceinline__ void gelu_phase(uint32_t t_acc, uint8_t* img, int r) {
+// RT threads share a row: this one owns the columns [half * 64 / RT, (half + 1) * 64 / RT).
+template <int NS, bool KEEP_GRAD, int RT>
+__device__ __forceinline__ void gelu_phase(uint32_t t_acc, uint8_t* img, int r, int half) {
 #pragma unroll 1
-  for (int q = 0; q < 4; ++q) {
+  for (int q0 = 0; q0 < 4 / RT; ++q0) {
+    const int q = half * (4 / RT) + q0;
     float h[16], a[16];
     umma::tmem_ld16(t_acc + 16 * q, h);
     umma::tmem_wait_ld();
@@ -352,12 +367,13 @@ __device__ __forceinline__ void gelu_phase(uint32_t t_acc, uint8_t* img, int r) 
 }
 // dL/dh = dL/da * gelu'(h): both in TMEM; the result becomes an A operand tile at `img`
 // once the weight-gradient GEMM that still reads the tile's previous content is done.
-template <int NS>
-__device__ __forceinline__ void grad_phase(uint32_t t_acc, uint32_t t_dgelu, uint8_t* img, int r,
+template <int NS, int RT>
+__device__ __forceinline__ void grad_phase(uint32_t t_acc, uint32_t t_dgelu, uint8_t* img, int r, int half,
                                            PipeSync& ps, bool wait_w) {
   if (wait_w) ps.wait_wdone();
 #pragma unroll 1
-  for (int q = 0; q < 4; ++q) {
+  for (int q0 = 0; q0 < 4 / RT; ++q0) {
+    const int q = half * (4 / RT) + q0;
     float g[16], d[16];
     umma::tmem_ld16(t_acc + 16 * q, g);
     umma::tmem_ld16(t_dgelu + 16 * q, d);
@@ -386,7 +402,7 @@ struct Bars {
 template <int NPIPE>
 __device__ __forceinline__ uint32_t block_setup(Bars* bars, uint32_t* tmem_slot, uint8_t* sm_w,
                                                 const uint8_t* __restrict__ staged, uint32_t w_bytes,
-                                                uint32_t tmem_cols) {
+                                                uint32_t tmem_cols, uint32_t pipe_threads) {
   const int warp = threadIdx.x >> 5;
   pdl_launch_dependents();
   if (threadIdx.x == 0) {
@@ -394,7 +410,7 @@ __device__ __forceinline__ uint32_t block_setup(Bars* bars, uint32_t* tmem_slot,
 #pragma unroll
     for (int p = 0; p < NPIPE; ++p) {
       umma::mbar_init(umma::smem_u32(&bars->done[p]), 1);
-      umma::mbar_init(umma::smem_u32(&bars->wfull[p]), TP);
+      umma::mbar_init(umma::smem_u32(&bars->wfull[p]), pipe_threads);
       umma::mbar_init(umma::smem_u32(&bars->wdone[p]), 1);
     }
     umma::fence_mbar_init();
@@ -442,23 +458,25 @@ struct FusedScatter {
 };
 
 // ------------------------------------------------------------------ forward
-__global__ void __launch_bounds__(FWD_THREADS, 1)
+template <int RT>
+__global__ void __launch_bounds__(fwd_threads<RT>(), 1)
 constitutive_fwd_kernel(int kind, int n, const float* __restrict__ F, const uint8_t* __restrict__ staged,
                         float alpha, float* __restrict__ out, const FusedP2G fp) {
-  constexpr int NS = NS_FWD, NPIPE = NPIPE_FWD;
+  constexpr int NS = NS_FWD, NPIPE = NPIPE_FWD, PW = 4 * RT;  // PW = warps per pipeline
   using W = WImg<NS>;
   using P = PipeFwd<NS>;
   extern __shared__ __align__(1024) uint8_t sm[];
   __shared__ Bars bars;
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5;
-  const uint32_t tmem = block_setup<NPIPE>(&bars, &tmem_slot, sm, staged + STAGED_OFF_FWD, W::BYTES, FWD_TMEM_COLS);
+  const uint32_t tmem = block_setup<NPIPE>(&bars, &tmem_slot, sm, staged + STAGED_OFF_FWD, W::BYTES, FWD_TMEM_COLS,
+                                           TP * RT);
   const uint32_t smem = umma::smem_u32(sm);
   const int tiles = (n + TP - 1) / TP;
   const int chains = gridDim.x * NPIPE;
   constexpr uint32_t ID64 = umma::idesc_bf16(TP, H, 0, 0), ID16 = umma::idesc_bf16(TP, KF, 0, 0);
 
-  if (warp == NPIPE * 4) {
+  if (warp == NPIPE * PW) {
     // ---------------- MMA warp (forward kernel: one dedicated issuing warp serves the pipelines'
     // wfull[p] requests in arrival order; measured ~8% faster here than per-pipeline issue)
     const Desc w0 = desc_kmajor(smem + W::OFF_W0, W0_SPLIT, H), w1 = desc_kmajor(smem + W::OFF_W1, W1_SPLIT, H),
@@ -498,16 +516,22 @@ constitutive_fwd_kernel(int kind, int n, const float* __restrict__ F, const uint
       }
     }
   } else {
-    // ---------------- compute threads: pipeline p, particle row r
-    const int p = warp >> 2, r = tid & (TP - 1);
+    // ---------------- compute threads: pipeline p, particle row r, column half `half`
+    const int p = warp / PW, w8 = warp % PW, quarter = w8 & 3, half = w8 >> 2;
+    const int r = quarter * 32 + (tid & 31);
+    const bool owner = half == 0;
     uint8_t* const pm = sm + W::BYTES + p * P::BYTES;
-    const uint32_t tacc = tmem + ((uint32_t)((warp & 3) * 32) << 16) + p * FWD_PIPE_COLS;
-    PipeSync ps{umma::smem_u32(&bars.done[p]), umma::smem_u32(&bars.wfull[p]), 0u, (uint32_t)(1 + p), 0u, 0u};
+    const uint32_t tacc = tmem + ((uint32_t)(quarter * 32) << 16) + p * FWD_PIPE_COLS;
+    PipeSync ps{umma::smem_u32(&bars.done[p]), umma::smem_u32(&bars.wfull[p]), 0u, (uint32_t)(1 + p), 0u, 0u,
+                (uint32_t)(TP * RT)};
     for (int tile = p * gridDim.x + blockIdx.x; tile < tiles; tile += chains) {
       const int pi = tile * TP + r;
-      Kinematics k;
-      kinematics(load_F_or_identity(F, pi, n), kind != 2, k);
-      {
+      Mat3 kF, kR;
+      if (owner) {
+        Kinematics k;
+        kinematics(load_F_or_identity(F, pi, n), kind != 2, k);
+        kF = k.F;
+        kR = k.R;
         float f[KF];
 #pragma unroll
         for (int i = 0; i < KF; ++i) f[i] = (i < NF) ? k.feat[i] : 0.f;
@@ -515,31 +539,33 @@ constitutive_fwd_kernel(int kind, int n, const float* __restrict__ F, const uint
         store_chunk<NS>(pm + P::OFF_FEAT, SMALL_SPLIT, 1, r, f + 8);
       }
       ps.publish_async();                                            // -> h1 = feat W0^T
-      prefetch_row(F, pi + chains * TP, n);
+      if (owner) prefetch_row(F, pi + chains * TP, n);
       ps.wait_done();
-      gelu_phase<NS, false>(tacc, pm + P::OFF_BIGA, r);
+      gelu_phase<NS, false, RT>(tacc, pm + P::OFF_BIGA, r, half);
       ps.publish_async();                                            // -> h2 = a1 W1^T
       ps.wait_done();
-      gelu_phase<NS, false>(tacc, pm + P::OFF_BIGA, r);
+      gelu_phase<NS, false, RT>(tacc, pm + P::OFF_BIGA, r, half);
       ps.publish_async();                                            // -> o = a2 W2^T
       ps.wait_done();
-      float o[16];
-      umma::tmem_ld16(tacc, o);
-      umma::tmem_wait_ld();
-      if (pi < n) {
-        const Mat3 X = head_to_sym(o);
-        const Mat3 Pm = mat3_mul(k.R, X);
-        Mat3 O;
-        if (kind == 1) {
+      if (owner) {
+        float o[16];
+        umma::tmem_ld16(tacc, o);
+        umma::tmem_wait_ld();
+        if (pi < n) {
+          const Mat3 X = head_to_sym(o);
+          const Mat3 Pm = mat3_mul(kR, X);
+          Mat3 O;
+          if (kind == 1) {
 #pragma unroll
-          for (int i = 0; i < 9; ++i) O.m[i] = alpha * Pm.m[i] + k.F.m[i];  // delta_Fp + F
-        } else {
-          O = mat3_mul_nt(Pm, k.F);  // cauchy = P F^T
-        }
-        mat3_store(out + (size_t)pi * 9, O);
-        if (fp.grid && fp.enabled[pi] != 0 && particle_selected(fp.c, fp.x[3 * pi + 2])) {
-          check_interior_class(fp.c, fp.x[3 * pi + 2], fp.box);
-          p2g_particle(fp.c, grid_map(fp.c, fp.box), pi, fp.x, fp.v, fp.C, O.m, fp.vol[pi], fp.rho[pi], fp.grid);
+            for (int i = 0; i < 9; ++i) O.m[i] = alpha * Pm.m[i] + kF.m[i];  // delta_Fp + F
+          } else {
+            O = mat3_mul_nt(Pm, kF);  // cauchy = P F^T
+          }
+          mat3_store(out + (size_t)pi * 9, O);
+          if (fp.grid && fp.enabled[pi] != 0 && particle_selected(fp.c, fp.x[3 * pi + 2])) {
+            check_interior_class(fp.c, fp.x[3 * pi + 2], fp.box);
+            p2g_particle(fp.c, grid_map(fp.c, fp.box), pi, fp.x, fp.v, fp.C, O.m, fp.vol[pi], fp.rho[pi], fp.grid);
+          }
         }
       }
     }
@@ -550,13 +576,13 @@ constitutive_fwd_kernel(int kind, int n, const float* __restrict__ F, const uint
 }
 
 // ------------------------------------------------------------------ backward
-template <bool WGRAD>
-__global__ void __launch_bounds__(BWD_THREADS, 1)
+template <bool WGRAD, int RT>
+__global__ void __launch_bounds__(bwd_threads<RT>(), 1)
 constitutive_bwd_kernel(int kind, int n, const float* __restrict__ F, const uint8_t* __restrict__ staged,
                         float alpha, const float* __restrict__ gout, float* __restrict__ gF,
                         float* __restrict__ gW0, float* __restrict__ gW1, float* __restrict__ gW2,
                         float* __restrict__ gWpart, int accumulate_gF, const FusedScatter fs) {
-  constexpr int NS = NS_BWD, NPIPE = NPIPE_BWD;
+  constexpr int NS = NS_BWD, NPIPE = NPIPE_BWD, PW = 4 * RT;  // PW = warps per pipeline
   using W = WImg<NS>;
   using P = PipeBwd<NS>;
   extern __shared__ __align__(1024) uint8_t sm[];
@@ -574,7 +600,8 @@ constitutive_bwd_kernel(int kind, int n, const float* __restrict__ F, const uint
 #else
 #define KPHASE(i)
 #endif
-  const uint32_t tmem = block_setup<NPIPE>(&bars, &tmem_slot, sm, staged + STAGED_OFF_BWD, W::BYTES, BWD_TMEM_COLS);
+  const uint32_t tmem = block_setup<NPIPE>(&bars, &tmem_slot, sm, staged + STAGED_OFF_BWD, W::BYTES, BWD_TMEM_COLS,
+                                           TP * RT);
   KPHASE(16);
   const uint32_t smem = umma::smem_u32(sm);
   const int tiles = (n + TP - 1) / TP;
@@ -583,7 +610,7 @@ constitutive_bwd_kernel(int kind, int n, const float* __restrict__ F, const uint
   constexpr uint32_t ID64_BT = umma::idesc_bf16(TP, H, 0, 1), ID16_BT = umma::idesc_bf16(TP, KF, 0, 1);
   constexpr uint32_t IDW64 = umma::idesc_bf16(64, H, 1, 1), IDW16 = umma::idesc_bf16(64, KF, 1, 1);
 
-  if (warp == NPIPE * 4) {
+  if (warp == NPIPE * PW) {
     // ---------------- weight-gradient warp: serves wfull[p] in arrival order
     if (WGRAD) {
       int njobs[NPIPE], job[NPIPE];
@@ -628,67 +655,84 @@ constitutive_bwd_kernel(int kind, int n, const float* __restrict__ F, const uint
       }
     }
   } else {
-    // ---------------- pipeline p, particle row r; the pipeline's first warp issues its GEMMs
-    const int p = warp >> 2, r = tid & (TP - 1);
-    const bool issuer = (warp & 3) == (p & 3);  // issuers of different pipelines sit on different SM sub-partitions
+    // ---------------- pipeline p, particle row r, column half `half`; one owner warp issues its GEMMs
+    const int p = warp / PW, w8 = warp % PW, quarter = w8 & 3, half = w8 >> 2;
+    const int r = quarter * 32 + (tid & 31);
+    const bool owner = half == 0;
+    const bool issuer = owner && quarter == (p & 3);  // issuers of different pipelines sit on different SM sub-partitions
     uint8_t* const pm = sm + W::BYTES + p * P::BYTES;
     const uint32_t pbase = smem + W::BYTES + p * P::BYTES;
     const uint32_t tp = tmem + p * BWD_PIPE_COLS;
-    const uint32_t tl = tp + ((uint32_t)((warp & 3) * 32) << 16);
-    const Desc w0 = desc_kmajor(smem + W::OFF_W0, W0_SPLIT, H), w1 = desc_kmajor(smem + W::OFF_W1, W1_SPLIT, H),
-               w2 = desc_kmajor(smem + W::OFF_W2, W2_SPLIT, KF);
-    // the same images read transposed: B operands of the data-gradient GEMMs
-    const Desc w0t = desc_mnmajor(smem + W::OFF_W0, W0_SPLIT, H), w1t = desc_mnmajor(smem + W::OFF_W1, W1_SPLIT, H),
-               w2t = desc_mnmajor(smem + W::OFF_W2, W2_SPLIT, KF);
-    const Desc feat = desc_kmajor(pbase + P::OFF_FEAT, SMALL_SPLIT, TP), go = desc_kmajor(pbase + P::OFF_GO, SMALL_SPLIT, TP),
-               biga = desc_kmajor(pbase + P::OFF_BIGA, BIG_SPLIT, TP), bigb = desc_kmajor(pbase + P::OFF_BIGB, BIG_SPLIT, TP);
+    const uint32_t tl = tp + ((uint32_t)(quarter * 32) << 16);
+    // RT = 2: F, U, V, sigma of row r parked in shared memory, [element][row]
+    float* const stash = reinterpret_cast<float*>(sm + W::BYTES + NPIPE * P::BYTES + p * STASH_BYTES) + r;
     const uint32_t dbar = umma::smem_u32(&bars.done[p]), wfull = umma::smem_u32(&bars.wfull[p]);
-    PipeSync ps{dbar, wfull, umma::smem_u32(&bars.wdone[p]), (uint32_t)(1 + p), 0u, 0u};
+    PipeSync ps{dbar, wfull, umma::smem_u32(&bars.wdone[p]), (uint32_t)(1 + p), 0u, 0u, (uint32_t)(TP * RT)};
     if (issuer) umma::mbar_wait(umma::smem_u32(&bars.w), 0);  // weight image has landed
+    // operand descriptors are rebuilt where they are used (issuer warp only): keeping ten of them
+    // live costs every thread 40 registers
+    auto wdesc = [&](int which, bool transposed) {
+      const uint32_t off = which == 0 ? W::OFF_W0 : (which == 1 ? W::OFF_W1 : W::OFF_W2);
+      const uint32_t split = which == 0 ? W0_SPLIT : (which == 1 ? W1_SPLIT : W2_SPLIT);
+      const int R = which == 2 ? KF : H;
+      return transposed ? desc_mnmajor(smem + off, split, R) : desc_kmajor(smem + off, split, R);
+    };
     bool first = true;
     PHASE_T0();
     for (int tile = p * gridDim.x + blockIdx.x; tile < tiles; tile += chains, first = false) {
       const int pi = tile * TP + r;
       const bool live = pi < n;
       Kinematics k;
-      kinematics(load_F_or_identity(F, pi, n), kind != 2, k);
+      if (owner) kinematics(load_F_or_identity(F, pi, n), kind != 2, k);
       PHASE(0);
       // FEAT / BIGA were last read by the previous tile's dW0 GEMM
       if (WGRAD && !first) ps.wait_wdone();
       PHASE(15);
-      {
+      if (owner) {
         float f[KF];
 #pragma unroll
         for (int i = 0; i < KF; ++i) f[i] = (i < NF && live) ? k.feat[i] : 0.f;
         store_chunk<NS>(pm + P::OFF_FEAT, SMALL_SPLIT, 0, r, f);
         store_chunk<NS>(pm + P::OFF_FEAT, SMALL_SPLIT, 1, r, f + 8);
+        if (RT == 2) {
+#pragma unroll
+          for (int i = 0; i < 9; ++i) {
+            stash[i * TP] = k.F.m[i];
+            stash[(9 + i) * TP] = k.U.m[i];
+            stash[(18 + i) * TP] = k.V.m[i];
+          }
+#pragma unroll
+          for (int i = 0; i < 3; ++i) stash[(27 + i) * TP] = k.sig[i];
+        }
       }
       ps.publish();
       if (issuer) {                                              // h1 = feat W0^T
         umma::fence_after_sync();
-        gemm_split<NS, 1>(tp + COL_H1, feat, w0, ID64, false);
+        gemm_split<NS, 1>(tp + COL_H1, desc_kmajor(pbase + P::OFF_FEAT, SMALL_SPLIT, TP), wdesc(0, false), ID64, false);
         umma::commit(dbar);
       }
-      prefetch_row(gout, pi, n);
-      prefetch_row(F, pi + chains * TP, n);
+      if (owner) {
+        prefetch_row(gout, pi, n);
+        prefetch_row(F, pi + chains * TP, n);
+      }
       PHASE(1);
       ps.wait_done();
       PHASE(2);
-      gelu_phase<NS, true>(tl + COL_H1, pm + P::OFF_BIGA, r);    // a1; gelu'(h1) stays in TMEM
+      gelu_phase<NS, true, RT>(tl + COL_H1, pm + P::OFF_BIGA, r, half);    // a1; gelu'(h1) stays in TMEM
       ps.publish();
       if (issuer) {                                              // h2 = a1 W1^T
         umma::fence_after_sync();
-        gemm_split<NS, 4>(tp + COL_H2, biga, w1, ID64, false);
+        gemm_split<NS, 4>(tp + COL_H2, desc_kmajor(pbase + P::OFF_BIGA, BIG_SPLIT, TP), wdesc(1, false), ID64, false);
         umma::commit(dbar);
       }
       PHASE(3);
       ps.wait_done();
       PHASE(4);
-      gelu_phase<NS, true>(tl + COL_H2, pm + P::OFF_BIGB, r);    // a2; gelu'(h2)
+      gelu_phase<NS, true, RT>(tl + COL_H2, pm + P::OFF_BIGB, r, half);    // a2; gelu'(h2)
       ps.publish();
       if (issuer) {                                              // o = a2 W2^T
         umma::fence_after_sync();
-        gemm_split<NS, 4>(tp + COL_S, bigb, w2, ID16, false);
+        gemm_split<NS, 4>(tp + COL_S, desc_kmajor(pbase + P::OFF_BIGB, BIG_SPLIT, TP), wdesc(2, false), ID16, false);
         umma::commit(dbar);
       }
       PHASE(5);
@@ -696,26 +740,40 @@ constitutive_bwd_kernel(int kind, int n, const float* __restrict__ F, const uint
       PHASE(6);
       // ---- output head: dL/dout -> dL/d(MLP output), dL/dR, direct dL/dF
       Mat3 gR, gFd;
-      {
+      if (owner) {
         float o[16], g9[KF];
         umma::tmem_ld16(tl + COL_S, o);
         umma::tmem_wait_ld();
 #pragma unroll
         for (int i = 0; i < KF; ++i) g9[i] = 0.f;
         if (live) {
+          Mat3 kF, kR;
+          if (RT == 2) {
+            Mat3 kU, kV;
+#pragma unroll
+            for (int i = 0; i < 9; ++i) {
+              kF.m[i] = stash[i * TP];
+              kU.m[i] = stash[(9 + i) * TP];
+              kV.m[i] = stash[(18 + i) * TP];
+            }
+            kR = mat3_mul_nt(kU, kV);
+          } else {
+            kF = k.F;
+            kR = k.R;
+          }
           const Mat3 X = head_to_sym(o);
-          const Mat3 Pm = mat3_mul(k.R, X);
+          const Mat3 Pm = mat3_mul(kR, X);
           const Mat3 G = mat3_load(gout + (size_t)pi * 9);
           Mat3 gP;  // out = P F^T (elastic)  |  out = F + alpha P (plastic)
           if (kind == 1) {
 #pragma unroll
             for (int i = 0; i < 9; ++i) { gP.m[i] = alpha * G.m[i]; gFd.m[i] = G.m[i]; }
           } else {
-            gP = mat3_mul(G, k.F);
+            gP = mat3_mul(G, kF);
             gFd = mat3_mul_tn(G, Pm);
           }
           gR = mat3_mul(gP, X);  // X symmetric
-          const Mat3 gXs = mat3_mul_tn(k.R, gP);
+          const Mat3 gXs = mat3_mul_tn(kR, gP);
 #pragma unroll
           for (int i = 0; i < 3; ++i)
 #pragma unroll
@@ -728,86 +786,104 @@ constitutive_bwd_kernel(int kind, int n, const float* __restrict__ F, const uint
       if (WGRAD) mbar_arrive(wfull);                             // -> dW2^T += a2^T go
       if (issuer) {                                              // dL/da2 = go W2
         umma::fence_after_sync();
-        gemm_split<NS, 1>(tp + COL_S, go, w2t, ID64_BT, false);
+        gemm_split<NS, 1>(tp + COL_S, desc_kmajor(pbase + P::OFF_GO, SMALL_SPLIT, TP), wdesc(2, true), ID64_BT, false);
         umma::commit(dbar);
       }
       PHASE(7);
       ps.wait_done();
       PHASE(8);
-      grad_phase<NS>(tl + COL_S, tl + COL_H2, pm + P::OFF_BIGB, r, ps, WGRAD);   // g2 over a2 (after dW2)
+      grad_phase<NS, RT>(tl + COL_S, tl + COL_H2, pm + P::OFF_BIGB, r, half, ps, WGRAD);   // g2 over a2 (after dW2)
       ps.publish();
       if (WGRAD) mbar_arrive(wfull);                             // -> dW1 += g2^T a1
       if (issuer) {                                              // dL/da1 = g2 W1
         umma::fence_after_sync();
-        gemm_split<NS, 4>(tp + COL_S, bigb, w1t, ID64_BT, false);
+        gemm_split<NS, 4>(tp + COL_S, desc_kmajor(pbase + P::OFF_BIGB, BIG_SPLIT, TP), wdesc(1, true), ID64_BT, false);
         umma::commit(dbar);
       }
       PHASE(9);
       ps.wait_done();
       PHASE(10);
-      grad_phase<NS>(tl + COL_S, tl + COL_H1, pm + P::OFF_BIGA, r, ps, WGRAD);   // g1 over a1 (after dW1)
+      grad_phase<NS, RT>(tl + COL_S, tl + COL_H1, pm + P::OFF_BIGA, r, half, ps, WGRAD);   // g1 over a1 (after dW1)
       ps.publish();
       if (WGRAD) mbar_arrive(wfull);                             // -> dW0 += g1^T feat
       if (issuer) {                                              // dL/dfeat = g1 W0
         umma::fence_after_sync();
-        gemm_split<NS, 4>(tp + COL_S, biga, w0t, ID16_BT, false);
+        gemm_split<NS, 4>(tp + COL_S, desc_kmajor(pbase + P::OFF_BIGA, BIG_SPLIT, TP), wdesc(0, true), ID16_BT, false);
         umma::commit(dbar);
       }
       PHASE(11);
       ps.wait_done();
       PHASE(12);
       // ---- invariants -> F
-      float gfeat[16];
-      umma::tmem_ld16(tl + COL_S, gfeat);
-      umma::tmem_wait_ld();
-      if (live) {
-        Mat3 gFt = gFd;
-        {  // FtF = F^T F : dF += F (G + G^T)
-          Mat3 Gs;
+      if (owner) {
+        float gfeat[16];
+        umma::tmem_ld16(tl + COL_S, gfeat);
+        umma::tmem_wait_ld();
+        if (live) {
+          Mat3 kF, kU, kV;
+          float sig[3];
+          if (RT == 2) {
 #pragma unroll
-          for (int i = 0; i < 3; ++i)
+            for (int i = 0; i < 9; ++i) {
+              kF.m[i] = stash[i * TP];
+              kU.m[i] = stash[(9 + i) * TP];
+              kV.m[i] = stash[(18 + i) * TP];
+            }
 #pragma unroll
-            for (int j = 0; j < 3; ++j) Gs(i, j) = gfeat[3 + 3 * i + j] + gfeat[3 + 3 * j + i];
-          const Mat3 t = mat3_mul(k.F, Gs);
+            for (int i = 0; i < 3; ++i) sig[i] = stash[(27 + i) * TP];
+          } else {
+            kF = k.F; kU = k.U; kV = k.V;
 #pragma unroll
-          for (int i = 0; i < 9; ++i) gFt.m[i] += t.m[i];
-        }
-        {  // det F : dF += gdet * cof(F)
-          const Mat3& A = k.F;
-          const float gd = gfeat[12];
-          gFt(0, 0) += gd * (A(1, 1) * A(2, 2) - A(1, 2) * A(2, 1));
-          gFt(0, 1) += gd * (A(1, 2) * A(2, 0) - A(1, 0) * A(2, 2));
-          gFt(0, 2) += gd * (A(1, 0) * A(2, 1) - A(1, 1) * A(2, 0));
-          gFt(1, 0) += gd * (A(0, 2) * A(2, 1) - A(0, 1) * A(2, 2));
-          gFt(1, 1) += gd * (A(0, 0) * A(2, 2) - A(0, 2) * A(2, 0));
-          gFt(1, 2) += gd * (A(0, 1) * A(2, 0) - A(0, 0) * A(2, 1));
-          gFt(2, 0) += gd * (A(0, 1) * A(1, 2) - A(0, 2) * A(1, 1));
-          gFt(2, 1) += gd * (A(0, 2) * A(1, 0) - A(0, 0) * A(1, 2));
-          gFt(2, 2) += gd * (A(0, 0) * A(1, 1) - A(0, 1) * A(1, 0));
-        }
-        {  // sigma and R = U V^T : dF += U (diag(gsig) + K) V^T
-          const Mat3 M = mat3_mul(mat3_mul_tn(k.U, gR), k.V);
-          Mat3 K;
+            for (int i = 0; i < 3; ++i) sig[i] = k.sig[i];
+          }
+          Mat3 gFt = gFd;
+          {  // FtF = F^T F : dF += F (G + G^T)
+            Mat3 Gs;
 #pragma unroll
-          for (int i = 0; i < 3; ++i)
+            for (int i = 0; i < 3; ++i)
 #pragma unroll
-            for (int j = 0; j < 3; ++j)
-              K(i, j) = (i == j) ? gfeat[i]
-                                 : (M(i, j) - M(j, i)) / signed_floor(k.sig[i] + k.sig[j], 1e-6f);
-          const Mat3 t = mat3_mul_nt(mat3_mul(k.U, K), k.V);
+              for (int j = 0; j < 3; ++j) Gs(i, j) = gfeat[3 + 3 * i + j] + gfeat[3 + 3 * j + i];
+            const Mat3 t = mat3_mul(kF, Gs);
 #pragma unroll
-          for (int i = 0; i < 9; ++i) gFt.m[i] += t.m[i];
-        }
-        if (accumulate_gF) {  // dL/dF += ... (the caller's gF already holds the MPM substep's part)
-          const Mat3 prev = mat3_load(gF + (size_t)pi * 9);
+            for (int i = 0; i < 9; ++i) gFt.m[i] += t.m[i];
+          }
+          {  // det F : dF += gdet * cof(F)
+            const Mat3& A = kF;
+            const float gd = gfeat[12];
+            gFt(0, 0) += gd * (A(1, 1) * A(2, 2) - A(1, 2) * A(2, 1));
+            gFt(0, 1) += gd * (A(1, 2) * A(2, 0) - A(1, 0) * A(2, 2));
+            gFt(0, 2) += gd * (A(1, 0) * A(2, 1) - A(1, 1) * A(2, 0));
+            gFt(1, 0) += gd * (A(0, 2) * A(2, 1) - A(0, 1) * A(2, 2));
+            gFt(1, 1) += gd * (A(0, 0) * A(2, 2) - A(0, 2) * A(2, 0));
+            gFt(1, 2) += gd * (A(0, 1) * A(2, 0) - A(0, 0) * A(2, 1));
+            gFt(2, 0) += gd * (A(0, 1) * A(1, 2) - A(0, 2) * A(1, 1));
+            gFt(2, 1) += gd * (A(0, 2) * A(1, 0) - A(0, 0) * A(1, 2));
+            gFt(2, 2) += gd * (A(0, 0) * A(1, 1) - A(0, 1) * A(1, 0));
+          }
+          {  // sigma and R = U V^T : dF += U (diag(gsig) + K) V^T
+            const Mat3 M = mat3_mul(mat3_mul_tn(kU, gR), kV);
+            Mat3 K;
 #pragma unroll
-          for (int i = 0; i < 9; ++i) gFt.m[i] += prev.m[i];
-        }
-        mat3_store(gF + (size_t)pi * 9, gFt);
-        if (fs.adj && fs.enabled[pi] != 0 && particle_selected(fs.c, fs.x[3 * pi + 2])) {
-          check_interior_class(fs.c, fs.x[3 * pi + 2], fs.box);
-          const G2PAdj g = g2p_adjoint_inputs(fs.c, pi, fs.x, fs.F, fs.clip, fs.v2, fs.gx2, fs.gv2, fs.gC2, gFt.m);
-          g2p_adjoint_scatter(fs.c, grid_map(fs.c, fs.box), pi, fs.x, g, fs.adj);
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+              for (int j = 0; j < 3; ++j)
+                K(i, j) = (i == j) ? gfeat[i]
+                                   : (M(i, j) - M(j, i)) / signed_floor(sig[i] + sig[j], 1e-6f);
+            const Mat3 t = mat3_mul_nt(mat3_mul(kU, K), kV);
+#pragma unroll
+            for (int i = 0; i < 9; ++i) gFt.m[i] += t.m[i];
+          }
+          if (accumulate_gF) {  // dL/dF += ... (the caller's gF already holds the MPM substep's part)
+            const Mat3 prev = mat3_load(gF + (size_t)pi * 9);
+#pragma unroll
+            for (int i = 0; i < 9; ++i) gFt.m[i] += prev.m[i];
+          }
+          mat3_store(gF + (size_t)pi * 9, gFt);
+          if (fs.adj && fs.enabled[pi] != 0 && particle_selected(fs.c, fs.x[3 * pi + 2])) {
+            check_interior_class(fs.c, fs.x[3 * pi + 2], fs.box);
+            const G2PAdj g = g2p_adjoint_inputs(fs.c, pi, fs.x, fs.F, fs.clip, fs.v2, fs.gx2, fs.gv2, fs.gC2, gFt.m);
+            g2p_adjoint_scatter(fs.c, grid_map(fs.c, fs.box), pi, fs.x, g, fs.adj);
+          }
         }
       }
       PHASE(13);
@@ -988,19 +1064,65 @@ reduce_partials_kernel(int slots, float* __restrict__ part, float* __restrict__ 
   }
 }
 
+// threads per particle row of the fused kernels: NEUMA_ROW_THREADS=1|2 (default 2; 1 = round-1 shape)
+int row_threads() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("NEUMA_ROW_THREADS");
+    v = (e && e[0] == '1') ? 1 : 2;
+  }
+  return v;
+}
+
 int set_attrs(neuma_ctx* ctx) {
   if (ctx->attrs_set) return 0;
   int cur = -1;
   cudaGetDevice(&cur);
   if (cur != ctx->device) NEUMA_CUDA(ctx, cudaSetDevice(ctx->device));
-  NEUMA_CUDA(ctx, cudaFuncSetAttribute(constitutive_fwd_kernel,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM));
-  NEUMA_CUDA(ctx, cudaFuncSetAttribute(constitutive_bwd_kernel<true>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM));
-  NEUMA_CUDA(ctx, cudaFuncSetAttribute(constitutive_bwd_kernel<false>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM));
+  const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
+  NEUMA_CUDA(ctx, cudaFuncSetAttribute(constitutive_fwd_kernel<1>, attr, (int)FWD_SMEM));
+  NEUMA_CUDA(ctx, cudaFuncSetAttribute(constitutive_fwd_kernel<2>, attr, (int)FWD_SMEM));
+  NEUMA_CUDA(ctx, cudaFuncSetAttribute(constitutive_bwd_kernel<true, 1>, attr, (int)bwd_smem<1>()));
+  NEUMA_CUDA(ctx, cudaFuncSetAttribute(constitutive_bwd_kernel<false, 1>, attr, (int)bwd_smem<1>()));
+  NEUMA_CUDA(ctx, cudaFuncSetAttribute(constitutive_bwd_kernel<true, 2>, attr, (int)bwd_smem<2>()));
+  NEUMA_CUDA(ctx, cudaFuncSetAttribute(constitutive_bwd_kernel<false, 2>, attr, (int)bwd_smem<2>()));
   ctx->attrs_set = 1;
   if (cur >= 0 && cur != ctx->device) cudaSetDevice(cur);
+  return 0;
+}
+
+// one place that picks the instantiation
+int launch_fwd(neuma_ctx* ctx, int kind, int n, const float* F, const void* staged, float alpha, float* out,
+               const FusedP2G& fp, cudaStream_t st) {
+  const int tiles = (n + TP - 1) / TP;
+  const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
+  if (row_threads() == 2)
+    NEUMA_CUDA(ctx, neuma_launch(constitutive_fwd_kernel<2>, dim3(grid), dim3(fwd_threads<2>()), FWD_SMEM, st, kind, n,
+                                 F, (const uint8_t*)staged, alpha, out, fp));
+  else
+    NEUMA_CUDA(ctx, neuma_launch(constitutive_fwd_kernel<1>, dim3(grid), dim3(fwd_threads<1>()), FWD_SMEM, st, kind, n,
+                                 F, (const uint8_t*)staged, alpha, out, fp));
+  NEUMA_LAUNCH_CHECK(ctx, "constitutive_fwd_kernel");
+  return 0;
+}
+
+int launch_bwd(neuma_ctx* ctx, bool wgrad, int kind, int n, const float* F, const void* staged, float alpha,
+               const float* gout, float* gF, float* gW0, float* gW1, float* gW2, float* gWpart, int accumulate_gF,
+               const FusedScatter& fs, cudaStream_t st) {
+  const int tiles = (n + TP - 1) / TP;
+  const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
+  const uint8_t* sg = (const uint8_t*)staged;
+#define NEUMA_BWD(WG, RTV)                                                                                       \
+  NEUMA_CUDA(ctx, neuma_launch(constitutive_bwd_kernel<WG, RTV>, dim3(grid), dim3(bwd_threads<RTV>()),            \
+                               bwd_smem<RTV>(), st, kind, n, F, sg, alpha, gout, gF, gW0, gW1, gW2, gWpart,       \
+                               accumulate_gF, fs))
+  if (row_threads() == 2) {
+    if (wgrad) NEUMA_BWD(true, 2); else NEUMA_BWD(false, 2);
+  } else {
+    if (wgrad) NEUMA_BWD(true, 1); else NEUMA_BWD(false, 1);
+  }
+#undef NEUMA_BWD
+  NEUMA_LAUNCH_CHECK(ctx, "constitutive_bwd_kernel");
   return 0;
 }
 
@@ -1065,14 +1187,9 @@ int neuma_constitutive_fwd_staged(neuma_ctx* ctx, int kind, int n, int hidden, c
   if (int r = check_args(ctx, kind, hidden)) return r;
   if (n <= 0) return 0;
   if (int r = set_attrs(ctx)) return r;
-  const int tiles = (n + TP - 1) / TP;
-  const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
   FusedP2G none;
   memset(&none, 0, sizeof(none));
-  NEUMA_CUDA(ctx, neuma_launch(constitutive_fwd_kernel, dim3(grid), dim3(FWD_THREADS), FWD_SMEM, (cudaStream_t)stream,
-                               kind, n, F, (const uint8_t*)staged, alpha, out, none));
-  NEUMA_LAUNCH_CHECK(ctx, "constitutive_fwd_kernel");
-  return 0;
+  return launch_fwd(ctx, kind, n, F, staged, alpha, out, none, (cudaStream_t)stream);
 }
 
 int neuma_constitutive_fwd_p2g(neuma_ctx* ctx, int kind, int n, int hidden, const float* F, const void* staged,
@@ -1087,13 +1204,8 @@ int neuma_constitutive_fwd_p2g(neuma_ctx* ctx, int kind, int n, int hidden, cons
     return neuma_fail_msg(ctx, "neuma_constitutive_fwd_p2g: a compact grid / sel_mode 3 needs the box");
   if (n <= 0) return 0;
   if (int r = set_attrs(ctx)) return r;
-  const int tiles = (n + TP - 1) / TP;
-  const int grid_dim = tiles < ctx->num_sms ? tiles : ctx->num_sms;
   FusedP2G fp{*c, x, v, C, vol, rho, enabled, box, (float4*)grid};
-  NEUMA_CUDA(ctx, neuma_launch(constitutive_fwd_kernel, dim3(grid_dim), dim3(FWD_THREADS), FWD_SMEM,
-                               (cudaStream_t)stream, kind, n, F, (const uint8_t*)staged, 0.0f, stress, fp));
-  NEUMA_LAUNCH_CHECK(ctx, "constitutive_fwd_kernel");
-  return 0;
+  return launch_fwd(ctx, kind, n, F, staged, 0.0f, stress, fp, (cudaStream_t)stream);
 }
 
 int neuma_constitutive_bwd_staged(neuma_ctx* ctx, int kind, int n, int hidden, const float* F,
@@ -1105,19 +1217,10 @@ int neuma_constitutive_bwd_staged(neuma_ctx* ctx, int kind, int n, int hidden, c
   const bool wgrad = gW0 && gW1 && gW2;
   if (!wgrad && (gW0 || gW1 || gW2))
     return neuma_fail_msg(ctx, "neuma_constitutive_bwd: pass all of gW0,gW1,gW2 or none");
-  const int tiles = (n + TP - 1) / TP;
-  const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
-  cudaStream_t st = (cudaStream_t)stream;
   FusedScatter none;
   memset(&none, 0, sizeof(none));
-  if (wgrad)
-    constitutive_bwd_kernel<true><<<grid, BWD_THREADS, BWD_SMEM, st>>>(
-        kind, n, F, (const uint8_t*)staged, alpha, gout, gF, gW0, gW1, gW2, nullptr, 0, none);
-  else
-    constitutive_bwd_kernel<false><<<grid, BWD_THREADS, BWD_SMEM, st>>>(
-        kind, n, F, (const uint8_t*)staged, alpha, gout, gF, gW0, gW1, gW2, nullptr, 0, none);
-  NEUMA_LAUNCH_CHECK(ctx, "constitutive_bwd_kernel");
-  return 0;
+  return launch_bwd(ctx, wgrad, kind, n, F, staged, alpha, gout, gF, gW0, gW1, gW2, nullptr, 0, none,
+                    (cudaStream_t)stream);
 }
 
 int neuma_constitutive_partials_floats(neuma_ctx* ctx) { return ctx ? ctx->num_sms * GW_FLOATS : 0; }
@@ -1129,15 +1232,10 @@ int neuma_constitutive_bwd_partials(neuma_ctx* ctx, int kind, int n, int hidden,
   if (!gWpart) return neuma_fail_msg(ctx, "neuma_constitutive_bwd_partials: gWpart is NULL");
   if (n <= 0) return 0;
   if (int r = set_attrs(ctx)) return r;
-  const int tiles = (n + TP - 1) / TP;
-  const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
   FusedScatter none;
   memset(&none, 0, sizeof(none));
-  NEUMA_CUDA(ctx, neuma_launch(constitutive_bwd_kernel<true>, dim3(grid), dim3(BWD_THREADS), BWD_SMEM,
-                               (cudaStream_t)stream, kind, n, F, (const uint8_t*)staged, alpha, gout, gF,
-                               (float*)nullptr, (float*)nullptr, (float*)nullptr, gWpart, accumulate_gF, none));
-  NEUMA_LAUNCH_CHECK(ctx, "constitutive_bwd_kernel");
-  return 0;
+  return launch_bwd(ctx, true, kind, n, F, staged, alpha, gout, gF, nullptr, nullptr, nullptr, gWpart,
+                    accumulate_gF, none, (cudaStream_t)stream);
 }
 
 int neuma_constitutive_bwd_scatter(neuma_ctx* ctx, int n, int hidden, const float* Ftrial, const void* staged,
@@ -1153,14 +1251,9 @@ int neuma_constitutive_bwd_scatter(neuma_ctx* ctx, int n, int hidden, const floa
     return neuma_fail_msg(ctx, "neuma_constitutive_bwd_scatter: a compact grid / sel_mode 3 needs the box");
   if (n <= 0) return 0;
   if (int r = set_attrs(ctx)) return r;
-  const int tiles = (n + TP - 1) / TP;
-  const int grid_dim = tiles < ctx->num_sms ? tiles : ctx->num_sms;
   FusedScatter fs{*c, x, F, clip_bound, v2, gx2, gv2, gC2, enabled, box, (float4*)adj};
-  NEUMA_CUDA(ctx, neuma_launch(constitutive_bwd_kernel<true>, dim3(grid_dim), dim3(BWD_THREADS), BWD_SMEM,
-                               (cudaStream_t)stream, 1, n, Ftrial, (const uint8_t*)staged, alpha, gout, gFtrial,
-                               (float*)nullptr, (float*)nullptr, (float*)nullptr, gWpart, 0, fs));
-  NEUMA_LAUNCH_CHECK(ctx, "constitutive_bwd_kernel");
-  return 0;
+  return launch_bwd(ctx, true, 1, n, Ftrial, staged, alpha, gout, gFtrial, nullptr, nullptr, nullptr, gWpart, 0,
+                    fs, (cudaStream_t)stream);
 }
 
 int neuma_constitutive_reduce_partials(neuma_ctx* ctx, int hidden, float* gWpart, float* gW0,
