@@ -1064,12 +1064,16 @@ reduce_partials_kernel(int slots, float* __restrict__ part, float* __restrict__ 
   }
 }
 
-// threads per particle row of the fused kernels: NEUMA_ROW_THREADS=1|2 (default 2; 1 = round-1 shape)
+// threads per particle row of the fused kernels: NEUMA_ROW_THREADS=1|2.  Default 1: measured on the
+// B200 (profiles/r02i_phase_timing.txt) the GELU phases take the same 3.9 k cycles per tile with one
+// or two threads per row -- they are bound by the XU pipe (rcp + ex2 + cvt.bf16x2 per value, quarter
+// rate) and the FMA pipe together, not by per-warp latency -- and the backward is 8 % slower with
+// two (register spills at 96 regs/thread).  Kept as a measured A/B.
 int row_threads() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("NEUMA_ROW_THREADS");
-    v = (e && e[0] == '1') ? 1 : 2;
+    v = (e && e[0] == '2') ? 2 : 1;
   }
   return v;
 }
