@@ -39,12 +39,26 @@ class FusedFrame:
                  alpha: float, substeps: int, device, bind=None, gaussians=None,
                  settings: Optional[RasterSettingsC] = None, center=None, size=None,
                  elastic_kind: int = ops.KIND_ELASTIC, use_graphs: bool = True, sort: bool = True,
-                 compact: bool = True, grid_margin: int = 6, cap_nodes: Optional[int] = None, fuse: bool = True):
-        """compact: saved grids hold the node bounding box only; their capacity is fixed at the first
+                 compact: bool = True, grid_margin: int = 6, cap_nodes: Optional[int] = None, fuse: bool = True,
+                 frames: int = 1, views: Optional[Sequence[RasterSettingsC]] = None, loss: str = "l2",
+                 force_mask_data: bool = False):
+        """frames: rendered frames this engine rolls out before ONE backward over all of them
+        (finetune.py:360-414: loss.backward() comes after nsteps = frames x substeps substeps); the state
+        of every substep of every frame stays resident.  views: one GaussianRasterizationSettings per
+        camera rendered at each frame (`for view in used_views`, finetune.py:377; default [settings]).
+        loss: "l2" | "l1" (loss_utils.py:17-24).  force_mask_data: render with colors_precomp = 1 instead
+        of the SH colours (tune/utils.py:390-404).
+        compact: saved grids hold the node bounding box only; their capacity is fixed at the first
         load_state() from that state's box widened by `grid_margin` nodes on every side (room for
         the cloud to move / deform over the frames this engine will see), or given as cap_nodes.
         A later box that does not fit is reported by check() -- nothing is written out of bounds."""
         self.n, self.S, self.dev = int(n), int(substeps), device
+        self.frames = int(frames)
+        self.T = self.S * self.frames                   # substeps resident for one backward
+        if loss not in ("l1", "l2"):
+            raise ValueError("loss must be 'l1' or 'l2'")
+        self.loss_kind, self.force_mask = loss, bool(force_mask_data)
+        self.views = list(views) if views is not None else ([settings] if settings is not None else [])
         self.c = cconst
         self._statics_in = tuple(t.contiguous() for t in statics)
         # statics in the engine's (cell-sorted) particle order; refreshed by load_state()
@@ -62,14 +76,14 @@ class FusedFrame:
         self.kind_e = elastic_kind
         self.bind, self.gs, self.settings = bind, gaussians, settings
         f = dict(device=device, dtype=torch.float32)
-        S = self.S
-        # state[s] = inputs of substep s (s = 0..S-1), state[S] = frame output
-        self.x = torch.empty(S + 1, n, 3, **f)
-        self.v = torch.empty(S + 1, n, 3, **f)
-        self.C = torch.empty(S + 1, n, 3, 3, **f)
-        self.F = torch.empty(S + 1, n, 3, 3, **f)
-        self.stress = torch.empty(S, n, 3, 3, **f)
-        self.Ftrial = torch.empty(S, n, 3, 3, **f)
+        S, T = self.S, self.T
+        # state[s] = inputs of substep s (s = 0..T-1), state[(f + 1) S] = output of frame f
+        self.x = torch.empty(T + 1, n, 3, **f)
+        self.v = torch.empty(T + 1, n, 3, **f)
+        self.C = torch.empty(T + 1, n, 3, 3, **f)
+        self.F = torch.empty(T + 1, n, 3, 3, **f)
+        self.stress = torch.empty(T, n, 3, 3, **f)
+        self.Ftrial = torch.empty(T, n, 3, 3, **f)
         # adjoint buffers (ping-pong) and weight-gradient accumulators
         self.g = [[torch.zeros(n, 3, **f), torch.zeros(n, 3, **f), torch.zeros(n, 3, 3, **f),
                    torch.zeros(n, 3, 3, **f)] for _ in range(2)]
@@ -86,11 +100,11 @@ class FusedFrame:
         self._size_h = [float(v) for v in self.size.cpu().tolist()]
         self.use_graphs = use_graphs
         self._side = torch.cuda.Stream(device)
-        self._g_fwd = self._g_bwd = None
+        self._g_fwd, self._g_bwd = {}, {}                # CUDA graphs, one per frame segment
         self._ctx = ops._ctx(self.x)
         # per-substep packed grids ((mv, m) -> (v, m) in place), adjoint scatter targets, boxes
         self.compact, self.grid_margin = bool(compact), int(grid_margin)
-        self.box = torch.zeros(S + 1, 8, device=device, dtype=torch.int32)
+        self.box = torch.zeros(T + 1, 8, device=device, dtype=torch.int32)
         self.grid = self.adj = None
         if not self.compact:
             self._alloc_grids(cconst.nz * cconst.num_grids * cconst.num_grids)
@@ -102,7 +116,7 @@ class FusedFrame:
         if self.compact:
             self.c = self.c.variant(compact=1, cap_nodes=int(nodes))
         self.cap_nodes = int(nodes)
-        self.grid = torch.empty(self.S, nodes, 4, **f)
+        self.grid = torch.empty(self.T, nodes, 4, **f)
         # ONE adjoint scatter target, cleared (over the substep's box) inside the backward itself
         self.adj = torch.empty(nodes, 4, **f)
 
@@ -129,11 +143,12 @@ class FusedFrame:
                                  f"(cap_nodes={self.cap_nodes}); build the engine with a larger grid_margin / cap_nodes")
 
     # ------------------------------------------------------------------ sim
-    def _sim_forward(self) -> None:
+    def _sim_forward(self, frame: int = 0) -> None:
         c = self.c
         main = torch.cuda.current_stream(self.dev)
-        ops.mpm_box_clear(c, self.box[0], self.grid[0], None, self.box[1])
-        for s in range(self.S):
+        s0, s1 = frame * self.S, (frame + 1) * self.S
+        ops.mpm_box_clear(c, self.box[s0], self.grid[s0], None, self.box[s0 + 1])
+        for s in range(s0, s1):
             if self.fuse:
                 # elasticity + P2G in ONE kernel: the particle is scattered by the thread that just
                 # computed its stress (csrc/constitutive.cu, FusedP2G)
@@ -147,25 +162,26 @@ class FusedFrame:
             ops.mpm_g2p_from(c, self.x[s], self.F[s], self.clip, self.enabled, self.grid[s],
                              (self.x[s + 1], self.v[s + 1], self.C[s + 1], self.Ftrial[s]), self.box[s + 1],
                              box=self.box[s])
-            if s + 1 < self.S:
+            if s + 1 < s1:
                 # the box clear of the NEXT substep's grid slot runs on a side branch next to the
                 # plasticity kernel (both only need this substep's G2P)
                 self._side.wait_stream(main)
                 with torch.cuda.stream(self._side):
                     ops.mpm_box_clear(c, self.box[s + 1], self.grid[s + 1], None, self.box[s + 2])
             ops.constitutive_fwd_staged(ops.KIND_PLASTIC, self.Ftrial[s], self.Wp_st, self.alpha, self.F[s + 1])
-            if s + 1 < self.S:
+            if s + 1 < s1:
                 main.wait_stream(self._side)
 
-    def _sim_backward(self) -> None:
-        """Consumes self.g[0] = dL/d(state[S]); leaves dL/d(state[0]) in self.g[0]
-        and accumulates dL/dW_eff into gWe / gWp."""
+    def _sim_backward(self, frame: int = 0) -> None:
+        """Consumes self.g[0] = dL/d(state after frame `frame`); leaves dL/d(state at its start) in
+        self.g[0] and accumulates dL/dW_eff into the partial-sum buffers (reduced by the caller)."""
         c = self.c
         main = torch.cuda.current_stream(self.dev)
+        s0, s1 = frame * self.S, (frame + 1) * self.S
         cur, nxt = 0, 1
         # the ONE adjoint scatter target is cleared over a substep's box inside the backward itself
-        ops.mpm_box_clear(c, self.box[self.S - 1], self.adj, None, None)
-        for s in reversed(range(self.S)):
+        ops.mpm_box_clear(c, self.box[s1 - 1], self.adj, None, None)
+        for s in reversed(range(s0, s1)):
             gx2, gv2, gC2, gF_next = self.g[cur]
             gx, gv, gC, gF = self.g[nxt]
             # plasticity: F[s+1] = P(Ftrial[s]); then adj(G2P) scatters dL/dv_node into adj
@@ -181,7 +197,7 @@ class FusedFrame:
             ops.mpm_bwd_node_gather(c, self.x[s], self.v[s], self.C[s], self.F[s], self.stress[s], self.vol,
                                     self.rho, self.clip, self.enabled, self.v[s + 1], self.C[s + 1], gx2, gv2, gC2,
                                     self.gFtrial, self.grid[s], self.adj, self.box[s], gx, gv, gC, gF, self.gstress)
-            if s > 0:
+            if s > s0:
                 # adj was last read by the gather above: clear it for substep s - 1 next to the
                 # elasticity backward
                 self._side.wait_stream(main)
@@ -190,11 +206,12 @@ class FusedFrame:
             # elasticity: stress[s] = E(F[s]);  dL/dF[s] += E'(F[s])^T gstress
             ops.constitutive_bwd_partials(self.kind_e, self.F[s], self.We_st, 0.0, self.gstress, gF,
                                           self.gWe_part, accumulate_gF=True)
-            if s > 0:
+            if s > s0:
                 main.wait_stream(self._side)
             cur, nxt = nxt, cur
-        ops.constitutive_reduce_partials(self.gWe_part, *self.gWe)
-        ops.constitutive_reduce_partials(self.gWp_part, *self.gWp)
+        if frame == 0:                       # the rollout's reverse pass ends here: fold the per-CTA partials
+            ops.constitutive_reduce_partials(self.gWe_part, *self.gWe)
+            ops.constitutive_reduce_partials(self.gWp_part, *self.gWp)
         if cur != 0:
             for a, b in zip(self.g[0], self.g[1]):
                 a.copy_(b)
@@ -251,17 +268,18 @@ class FusedFrame:
             return out
         return t
 
-    def sim_forward(self, return_state: bool = True):
+    def sim_forward(self, return_state: bool = True, frame: int = 0):
+        """S substeps of frame `frame` (its input state is state[frame S]: load_state() for frame 0,
+        the previous frame's output otherwise)."""
         if not self.use_graphs:
-            self._sim_forward()
+            self._sim_forward(frame)
         else:
-            if self._g_fwd is None:
-                self._g_fwd = self._capture(self._sim_forward)   # slot 0 (state, box) is read-only: replay-safe
-            self._g_fwd.replay()
+            if frame not in self._g_fwd:          # the segment's first slot (state, box) is read-only: replay-safe
+                self._g_fwd[frame] = self._capture(lambda: self._sim_forward(frame))
+            self._g_fwd[frame].replay()
         if not return_state:
             return None
-        S = self.S
-        return tuple(self._to_caller(t[S]) for t in (self.x, self.v, self.C, self.F))
+        return self.final_state(frame)
 
     def sim_backward(self, gx, gv, gC, gF):
         """Reverse pass of the LAST sim_forward() (may be called again: the adjoint scatter target is
@@ -273,20 +291,20 @@ class FusedFrame:
                 self._to_sorted(src, out=dst)
         return self._run_backward()
 
-    def _run_backward(self, want_g0: bool = True):
-        """self.g[0] holds dL/d(state[S]) in the engine's (cell) order."""
+    def _run_backward(self, want_g0: bool = True, frame: int = 0):
+        """self.g[0] holds dL/d(state after frame `frame`) in the engine's (cell) order."""
         if not self.use_graphs:
-            self._sim_backward()
+            self._sim_backward(frame)
         else:
-            if self._g_bwd is None:
+            if frame not in self._g_bwd:
                 keep = [t.clone() for t in self.g[0]]
-                keep_w = [t.clone() for t in self.gWe + self.gWp]
-                self._g_bwd = self._capture(self._sim_backward)
+                keep_w = [t.clone() for t in self.gWe + self.gWp + [self.gWe_part, self.gWp_part]]
+                self._g_bwd[frame] = self._capture(lambda: self._sim_backward(frame))
                 for dst, src in zip(self.g[0], keep):
                     dst.copy_(src)
-                for dst, src in zip(self.gWe + self.gWp, keep_w):
+                for dst, src in zip(self.gWe + self.gWp + [self.gWe_part, self.gWp_part], keep_w):
                     dst.copy_(src)
-            self._g_bwd.replay()
+            self._g_bwd[frame].replay()
         return [self._to_caller(t) for t in self.g[0]] if want_g0 else None
 
     def set_weights(self, We=None, Wp=None) -> None:
@@ -304,37 +322,63 @@ class FusedFrame:
             t.zero_()
 
     # ------------------------------------------------------------------ sim -> render
-    def render_forward(self, de_x_prev: torch.Tensor, k_prev: torch.Tensor):
-        """particles -> Gaussians (denormalise, both bindings, covariance deformation: ONE launch,
-        SURVEY 8f.4) + rasterization of the frame's final state."""
-        b, gs, S = self.bind, self.gs, self.S
+    def _raster(self, settings, means3D, cov):
+        gs = self.gs
+        if self.force_mask:                 # tune/utils.py:390-404: colors_precomp = ones, no SH
+            if getattr(self, "_ones_rgb", None) is None:
+                self._ones_rgb = torch.ones(means3D.shape[0], 3, device=self.dev)
+            return ops.raster_fwd(settings, means3D, None, self._ones_rgb, gs["opac"], cov)
+        return ops.raster_fwd(settings, means3D, gs["shs"], None, gs["opac"], cov)
+
+    def _raster_bwd(self, settings, means3D, cov, radii, dL_dimage):
+        gs = self.gs
+        if self.force_mask:
+            return ops.raster_bwd(settings, means3D, None, self._ones_rgb, gs["opac"], cov, radii, dL_dimage)[0]
+        return ops.raster_bwd(settings, means3D, gs["shs"], None, gs["opac"], cov, radii, dL_dimage)[0]
+
+    def gaussians_at(self, de_x_prev: torch.Tensor, k_prev: torch.Tensor, frame: int = 0):
+        """particles -> Gaussians at the end of frame `frame` (denormalise, both bindings, covariance
+        deformation: ONE launch): means3D [K,3], deformed cov [K,6]."""
+        b, gs, s = self.bind, self.gs, (frame + 1) * self.S
         means3D, cov, _ = ops.particles_to_gaussians(b.rowptr, b.col, b.w, self.inv if self.sort else None,
-                                                     self.x[S], self.F[S], self._center_h, self._size_h,
+                                                     self.x[s], self.F[s], self._center_h, self._size_h,
                                                      de_x_prev, k_prev, gs["cov6"])
-        image, radii = ops.raster_fwd(self.settings, means3D, gs["shs"], None, gs["opac"], cov)
-        self._render_saved = (means3D, cov, radii)
+        return means3D, cov
+
+    def render_forward(self, de_x_prev: torch.Tensor, k_prev: torch.Tensor, frame: int = 0, view: int = 0):
+        """gaussians_at() + rasterization of one view."""
+        means3D, cov = self.gaussians_at(de_x_prev, k_prev, frame)
+        image, radii = self._raster(self.views[view], means3D, cov)
+        self._render_saved = (means3D, cov, radii, view)
         return image, means3D
 
     def render_backward(self, dL_dimage: torch.Tensor, accumulate_into_state_grad: bool = False):
-        """dL/dimage -> dL/dmeans3D [K,3] (cov3D carries no gradient).  With
-        accumulate_into_state_grad the transpose binding adds it straight into the engine's
-        dL/dx buffer (cell order), ready for _run_backward()."""
-        b, gs = self.bind, self.gs
-        means3D, cov, radii = self._render_saved
-        g3, _g2, *_ = ops.raster_bwd(self.settings, means3D, gs["shs"], None, gs["opac"], cov, radii, dL_dimage)
+        """dL/dimage of the LAST render_forward -> dL/dmeans3D [K,3] (cov3D carries no gradient,
+        SURVEY 0.4).  With accumulate_into_state_grad the transpose binding adds it straight into the
+        engine's dL/dx buffer (cell order), ready for _run_backward()."""
+        b = self.bind
+        means3D, cov, radii, view = self._render_saved
+        g3 = self._raster_bwd(self.views[view], means3D, cov, radii, dL_dimage)
         if accumulate_into_state_grad:
             ops.gaussians_to_particles(b.rowptr, b.col, b.w, self.inv if self.sort else None, g3, self._size_h,
                                        self.g[0][0])
         return g3
 
+    def _pixel_loss(self, image: torch.Tensor, gt: torch.Tensor, weight: float):
+        """weight * l1 | l2 (loss_utils.py:17-24) and its dL/dimage."""
+        diff = image - gt
+        if self.loss_kind == "l2":
+            return weight * (diff * diff).mean(), diff * (2.0 * weight / diff.numel())
+        return weight * diff.abs().mean(), torch.sign(diff) * (weight / diff.numel())
+
     # ------------------------------------------------------------------ one frame, forward + backward
-    def final_state(self):
-        """(x, v, C, F) after the S substeps, caller order (the next frame's load_state input)."""
-        S = self.S
-        return tuple(self._to_caller(t[S]) for t in (self.x, self.v, self.C, self.F))
+    def final_state(self, frame: int = 0):
+        """(x, v, C, F) after frame `frame`, caller order (the next frame's load_state input)."""
+        s = (frame + 1) * self.S
+        return tuple(self._to_caller(t[s]) for t in (self.x, self.v, self.C, self.F))
 
     def frame_forward(self, gt: torch.Tensor, de_x_prev, k_prev, gt_ready: Optional[torch.cuda.Event] = None):
-        """S substeps + render + l2 loss (finetune.py:360-389).  Returns (loss, means3D): means3D is the
+        """S substeps + render + pixel loss (finetune.py:360-389).  Returns (loss, means3D): means3D is the
         next frame's k_prev, (final_state()[0] - center) / size its de_x_prev (both enter detached,
         tune/utils.py:441-446).  gt_ready: event after which `gt` is valid (a host->device copy of the
         ground-truth image issued on another stream overlaps the simulation)."""
@@ -342,9 +386,7 @@ class FusedFrame:
         image, means3D = self.render_forward(de_x_prev, k_prev)
         if gt_ready is not None:
             torch.cuda.current_stream(self.dev).wait_event(gt_ready)
-        diff = image - gt
-        loss = (diff * diff).mean()
-        self._dL_dimage = diff * (2.0 / diff.numel())
+        loss, self._dL_dimage = self._pixel_loss(image, gt, 1.0)
         return loss, means3D
 
     def frame_backward(self, g_state_next=None, want_g0: bool = True):
@@ -365,3 +407,60 @@ class FusedFrame:
         """frame_forward + frame_backward.  Returns (loss, dL/d(state at frame start))."""
         loss, _ = self.frame_forward(gt, de_x_prev, k_prev, gt_ready)
         return loss, self.frame_backward(g_state_next, want_g0)
+
+    # ------------------------------------------------------------------ the whole rollout of an epoch
+    def rollout_fwd_bwd(self, gts, weights=None, de_x_prev=None, k_prev=None, want_g0: bool = True):
+        """One epoch of finetune_constitutive (finetune.py:360-414) with ONE engine: `frames` frames of S
+        substeps each from the state given to load_state(); after every frame the Gaussians are moved
+        with their bound particles and rendered from every view, the weighted pixel losses summed;
+        then ONE reverse pass over all frames x substeps.
+
+          gts[f][v]   ground-truth image [3,H,W] (device) of frame f, view v; gts[f] = None skips the
+                      frame (`exclude_steps`, finetune.py:369-371): no loss, and the binding reference
+                      (de_x_prev, g_prev) is NOT advanced, exactly as the reference's `continue`;
+          weights[f]  rollout_decay_rate of frame f (finetune.py:388-389; default 1).
+        The loss is a plain weighted sum, so dL/dimage of a view is known as soon as it is rendered:
+        its rasterizer backward runs right away and only dL/dmeans3D [K,3] per frame is kept for the
+        reverse pass (no rasterizer state is saved).  Returns (loss, dL/d(state0) in the caller's
+        order or None); dL/dW_eff are ADDED into gWe / gWp."""
+        assert len(gts) == self.frames, "one entry of gts per frame"
+        b = self.bind
+        dev = self.dev
+        if de_x_prev is None:
+            x0 = self._to_caller(self.x[0])
+            de_x_prev = (x0 - self.center) / self.size
+        if k_prev is None:
+            raise ValueError("k_prev (the kernels' positions at the start, gaussians.get_xyz) is required")
+        loss = torch.zeros((), device=dev)
+        if getattr(self, "_gk", None) is None:
+            self._gk = torch.zeros(self.frames, k_prev.shape[0], 3, device=dev)
+        rendered = []
+        for f in range(self.frames):
+            self.sim_forward(return_state=False, frame=f)
+            if gts[f] is None:
+                continue
+            w = 1.0 if weights is None else float(weights[f])
+            means3D, cov = self.gaussians_at(de_x_prev, k_prev, f)
+            gk = self._gk[f]
+            for vi, gt in enumerate(gts[f]):
+                image, radii = self._raster(self.views[vi], means3D, cov)
+                l, dimg = self._pixel_loss(image, gt, w)
+                loss = loss + l
+                g3 = self._raster_bwd(self.views[vi], means3D, cov, radii, dimg)
+                if vi == 0:
+                    gk.copy_(g3)
+                else:
+                    gk.add_(g3)
+            rendered.append(f)
+            xs = self._to_caller(self.x[(f + 1) * self.S])
+            de_x_prev = (xs - self.center) / self.size
+            k_prev = means3D
+        # ---- reverse pass
+        for dst in self.g[0]:
+            dst.zero_()
+        for f in reversed(range(self.frames)):
+            if f in rendered:
+                ops.gaussians_to_particles(b.rowptr, b.col, b.w, self.inv if self.sort else None, self._gk[f],
+                                           self._size_h, self.g[0][0])
+            g0 = self._run_backward(want_g0 and f == 0, frame=f)
+        return loss, g0

@@ -263,7 +263,7 @@ class SlabRollout:
     def __init__(self, G: int, dt: float, We, Wp, alpha: float, substeps: int, device, group=None,
                  bound: int = 1, gravity=(0.0, -9.8, 0.0), eps: float = 6e-7, bc: str = "noslip",
                  halo_k: int = 1, elastic_kind: int = 0, halo: str = "fused", use_graphs: Optional[bool] = None,
-                 overlap="split", standalone: bool = False, fuse: bool = True):
+                 overlap="none", standalone: bool = False, fuse: bool = True):
         from . import ops
         self.ops = ops
         self.G, self.dt, self.S, self.dev, self.group = int(G), float(dt), int(substeps), device, group
@@ -303,6 +303,8 @@ class SlabRollout:
         #              the exchange on a side stream under elasticity + P2G of the interior range
         #              (backward: plasticity backward + adjoint scatter likewise).  An interior-range
         #              particle that touches a shared plane after all is counted on the device.
+        # Measured on 2 and 8 B200s (profiles/r02k_slab_scaling.txt): none of the three hides the ~25-30 us
+        # an exchange costs -- the split launches cost what the overlap saves -- so "none" is the default.
         overlap = {True: "split", False: "none", None: "none"}.get(overlap, overlap)
         if overlap not in ("none", "scatter", "full", "split"):
             raise ValueError("overlap must be 'none', 'split', 'scatter' or 'full'")

@@ -26,8 +26,12 @@ def rollout_loss(c: MO.MPMConst, x, v, C, F, vol, rho, clip, enabled,
                  We, lora_e, Wp, lora_p, alpha: float,
                  B_sparse, k0, cov6, opac, shs, settings: RO.Settings, gts: Sequence[torch.Tensor],
                  substeps: int, center, size, dtype=torch.float64, loss="l2", colors_precomp=None,
-                 return_images=False):
-    """One epoch of finetune_constitutive over len(gts) frames; returns the scalar loss."""
+                 return_images=False, weights=None):
+    """One epoch of finetune_constitutive over len(gts) frames; returns the scalar loss.
+    `settings` may be a list of cameras (`for view in used_views`, finetune.py:377): gts[f] is then a
+    list with one image per view.  gts[f] = None: the frame is in `exclude_steps` -- `continue`
+    BEFORE the binding reference is advanced (finetune.py:369-371).  weights[f] = the frame's
+    rollout_decay_rate (finetune.py:388-389)."""
     cast = lambda t: None if t is None else t.to(dtype)
     x, v, C, F = map(cast, (x, v, C, F))
     vol, rho, clip = map(cast, (vol, rho, clip))
@@ -36,20 +40,27 @@ def rollout_loss(c: MO.MPMConst, x, v, C, F, vol, rho, clip, enabled,
     k_prev = cast(k0).detach()
     total = torch.zeros((), dtype=dtype)
     images = []
-    for gt in gts:
+    cams = settings if isinstance(settings, (list, tuple)) else [settings]
+    for fi, gt in enumerate(gts):
         for _ in range(substeps):
             stress = CO.elasticity(F, We, lora_e)
             x, v, C, F = MO.substep_fwd(c, x, v, C, F, stress, vol, rho, clip, enabled)
             F = CO.plasticity(F, Wp, alpha, lora_p)
+        if gt is None:
+            continue
+        w = 1.0 if weights is None else float(weights[fi])
         de_x = (x - center) / size
         means3D = RO.bindings_xyz(de_x, de_x_prev, k_prev, B_sparse)
         Fk = RO.bindings_F(F, B_sparse)
         cov_def = RO.deform_cov(cast(cov6), Fk.detach()).detach()
-        binning = RO.bin_np(settings, means3D.detach().float().numpy(), cov_def.float().numpy())
-        img = RO.render_torch(settings, binning, means3D, cast(shs), cast(colors_precomp), cast(opac), cov_def, dtype)
-        diff = img - cast(gt)
-        total = total + ((diff ** 2).mean() if loss == "l2" else diff.abs().mean())
-        images.append(img.detach())
+        gt_views = gt if isinstance(gt, (list, tuple)) else [gt]
+        for cam, gtv in zip(cams, gt_views):
+            binning = RO.bin_np(cam, means3D.detach().float().numpy(), cov_def.float().numpy())
+            img = RO.render_torch(cam, binning, means3D, None if colors_precomp is not None else cast(shs),
+                                  cast(colors_precomp), cast(opac), cov_def, dtype)
+            diff = img - cast(gtv)
+            total = total + w * ((diff ** 2).mean() if loss == "l2" else diff.abs().mean())
+            images.append(img.detach())
         de_x_prev = de_x.detach()
         k_prev = means3D.detach()
     if return_images:

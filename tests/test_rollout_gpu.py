@@ -1,0 +1,111 @@
+"""FusedFrame.rollout_fwd_bwd: the WHOLE epoch of finetune_constitutive with one engine
+(/root/reference/experiments/finetune.py:360-414): several rendered frames of S substeps, V views per
+frame, per-frame rollout_decay weights, l1 | l2 pixel loss, an excluded frame, mask mode, and ONE
+reverse pass over all frames x substeps -- against torch autograd over the CPU oracle (fp64)."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from test_fused_frame_gpu import _setup
+
+pytestmark = pytest.mark.gpu
+
+
+def _views(IM, eyes):
+    from neuma_b200 import ops, synthetic as S
+    from oracle import raster_oracle as RO
+    cs, os_ = [], []
+    for eye in eyes:
+        cam = S.make_camera(IM, IM, eye=eye)
+        tan = math.tan(cam.FoVx * 0.5)
+        cs.append(ops.raster_settings(IM, IM, tan, tan, [1.0, 1.0, 1.0], 1.0, cam.world_view_transform,
+                                      cam.full_proj_transform, 3, cam.camera_center))
+        os_.append(RO.Settings(IM, IM, tan, tan, np.ones(3, np.float32), cam.world_view_transform.numpy(),
+                               cam.full_proj_transform.numpy(), 3, cam.camera_center.numpy()))
+    return cs, os_
+
+
+@pytest.mark.parametrize("loss,mask,graphs", [("l2", False, True), ("l1", False, False), ("l2", True, True)])
+def test_rollout_views_weights_exclusion_against_oracle(cuda_dev, loss, mask, graphs):
+    from neuma_b200.pipeline import FusedFrame
+    from oracle import mpm_oracle as MO, pipeline_oracle as PO
+    n, G, IM, Ssub, frames = 1500, 32, 48, 2, 3
+    spec, cc, d, W, alpha, settings, bind, gs, F0, gt, kxyz = _setup(cuda_dev, n=n, G=G, IM=IM)
+    center, size = torch.tensor([0.1, 0.0, 0.1]), torch.tensor([0.8, 0.9, 0.8])
+    views, oviews = _views(IM, [(0.5, 0.5, 2.5), (0.62, 0.5, 2.4), (0.4, 0.58, 2.6)])
+    gen = torch.Generator().manual_seed(9)
+    gts = [[torch.rand(3, IM, IM, generator=gen) for _ in views] for _ in range(frames)]
+    gts[1] = None                                        # exclude_steps: frame 1 carries no loss
+    weights = [1.0, 0.8, 0.64]                           # decay_rate ** ((cur_step - 1) // decay_steps)
+    eng = FusedFrame(n, cc, (d["vol"], d["rho"], d["clip"], d["enabled"]), W["elastic"], W["plastic"], alpha, Ssub,
+                     cuda_dev, bind=bind, gaussians=gs, views=views, center=center, size=size, frames=frames,
+                     loss=loss, force_mask_data=mask, use_graphs=graphs)
+    dev_gts = [None if g is None else [t.to(cuda_dev) for t in g] for g in gts]
+    for rep in range(2):                                 # the second epoch replays the captured graphs
+        eng.load_state(d["x"], d["v"], d["C"], F0)
+        eng.zero_weight_grads()
+        total, g0 = eng.rollout_fwd_bwd(dev_gts, weights, k_prev=kxyz)
+    eng.check()
+    gW = [t.clone() for t in eng.gWe + eng.gWp]
+    # ---- oracle
+    p = {k: v.cpu() for k, v in d.items()}
+    B = torch.sparse_csr_tensor(bind.rowptr.cpu().long(), bind.col.cpu().long(), bind.w.cpu().double(),
+                                (bind.n_kernels, n)).to_sparse_coo()
+    x0 = p["x"].double().requires_grad_(True)
+    v0 = p["v"].double().requires_grad_(True)
+    C0 = p["C"].double().requires_grad_(True)
+    F0d = F0.cpu().double().requires_grad_(True)
+    We = [w.cpu().double().requires_grad_(True) for w in W["elastic"]]
+    Wp = [w.cpu().double().requires_grad_(True) for w in W["plastic"]]
+    co = MO.MPMConst(num_grids=G, dt=1e-3, bound=1, eps=6e-7, bc="noslip")
+    ones = torch.ones(bind.n_kernels, 3) if mask else None
+    oloss = PO.rollout_loss(co, x0, v0, C0, F0d, p["vol"], p["rho"], p["clip"], p["enabled"], We, None, Wp, None, alpha,
+                            B, kxyz.cpu(), gs["cov6"].cpu(), gs["opac"].cpu(), gs["shs"].cpu(), oviews, gts, Ssub,
+                            center, size, loss=loss, colors_precomp=ones, weights=weights)
+    og = torch.autograd.grad(oloss, [x0, v0, C0, F0d] + We + Wp)
+    assert abs(float(total) - float(oloss.detach())) / float(oloss.detach()) < 1e-4
+    rel = lambda a, b: float((a.cpu().double() - b).norm() / (b.norm() + 1e-30))
+    errs = {name: rel(a, b) for a, b, name in zip(g0, og[:4], ["gx", "gv", "gC", "gF"])}
+    errs.update({f"gW{i}": rel(a, b) for i, (a, b) in enumerate(zip(gW, og[4:]))})
+    print("relative L2 errors vs the fp64 oracle:", {k: f"{v:.2e}" for k, v in errs.items()})
+    # same bounds as test_two_chained_frames_against_oracle (fp32 device rollout, 48x48 images with
+    # alpha / transmittance threshold flips, l1's sign() is discontinuous on top)
+    assert max(v for k, v in errs.items() if k.startswith("gW")) < (2e-2 if loss == "l2" else 5e-2), errs
+    assert max(v for k, v in errs.items() if not k.startswith("gW")) < (5e-2 if loss == "l2" else 1e-1), errs
+
+
+def test_rollout_memory_400_substeps(cuda_dev):
+    """a 400-substep rollout at 100 k particles (finetune-jd: 400 steps before the one
+    backward) keeps < 10 GB resident, below the reference's 528 B/particle/substep (21 GB)."""
+    from neuma_b200 import ops, synthetic as S
+    from neuma_b200.pipeline import FusedFrame
+    spec = S.WORKLOADS["jellyduck-100k-128"]
+    p = S.make_particles(spec, 42)
+    z = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden",
+                             "material_jelly.npz"))
+    W = {t: [torch.from_numpy(z[f"param_{t}.{l}.fc.weight"]).float().to(cuda_dev)
+             for l in ("layers.0", "layers.1", "final_layer")] for t in ("elastic", "plastic")}
+    d = {k: v.to(cuda_dev) for k, v in p.items()}
+    cc = ops.mpm_const(spec["G"], spec["dt"], 1, (0.0, -9.8, 0.0), 6e-7, "noslip")
+    torch.cuda.synchronize()
+    torch.cuda.reset_peak_memory_stats()
+    base = torch.cuda.memory_allocated()
+    eng = FusedFrame(spec["n"], cc, (d["vol"], d["rho"], d["clip"], d["enabled"]), W["elastic"], W["plastic"],
+                     float(z["alpha"]), 20, cuda_dev, frames=20, use_graphs=False)
+    eng.load_state(d["x"], d["v"], d["C"], d["F"])
+    for f in range(20):
+        eng.sim_forward(return_state=False, frame=f)
+    eng.check()                                          # the falling cloud stayed inside the compact grid slots
+    for g in eng.g[0]:
+        g.normal_()
+    for f in reversed(range(20)):
+        eng._run_backward(False, frame=f)
+    torch.cuda.synchronize()
+    resident = torch.cuda.memory_allocated() - base
+    mem = eng.memory_bytes_per_substep()
+    assert mem["per_particle"] < 528
+    assert resident < 10e9, resident
+    assert torch.isfinite(eng.g[0][0]).all() and torch.isfinite(eng.gWe[1]).all()
