@@ -14,16 +14,16 @@ from test_fused_frame_gpu import _setup
 pytestmark = pytest.mark.gpu
 
 
-def _views(IM, eyes):
+def _views(IM, eyes, bg=1.0):
     from neuma_b200 import ops, synthetic as S
     from oracle import raster_oracle as RO
     cs, os_ = [], []
     for eye in eyes:
         cam = S.make_camera(IM, IM, eye=eye)
         tan = math.tan(cam.FoVx * 0.5)
-        cs.append(ops.raster_settings(IM, IM, tan, tan, [1.0, 1.0, 1.0], 1.0, cam.world_view_transform,
+        cs.append(ops.raster_settings(IM, IM, tan, tan, [bg, bg, bg], 1.0, cam.world_view_transform,
                                       cam.full_proj_transform, 3, cam.camera_center))
-        os_.append(RO.Settings(IM, IM, tan, tan, np.ones(3, np.float32), cam.world_view_transform.numpy(),
+        os_.append(RO.Settings(IM, IM, tan, tan, np.full(3, bg, np.float32), cam.world_view_transform.numpy(),
                                cam.full_proj_transform.numpy(), 3, cam.camera_center.numpy()))
     return cs, os_
 
@@ -35,7 +35,9 @@ def test_rollout_views_weights_exclusion_against_oracle(cuda_dev, loss, mask, gr
     n, G, IM, Ssub, frames = 1500, 32, 48, 2, 3
     spec, cc, d, W, alpha, settings, bind, gs, F0, gt, kxyz = _setup(cuda_dev, n=n, G=G, IM=IM)
     center, size = torch.tensor([0.1, 0.0, 0.1]), torch.tensor([0.8, 0.9, 0.8])
-    views, oviews = _views(IM, [(0.5, 0.5, 2.5), (0.62, 0.5, 2.4), (0.4, 0.58, 2.6)])
+    # mask mode renders colour 1 everywhere: on a white background the image would not depend on the
+    # scene at all, so that case uses a black one (the real-world configs do, finetune-dog.yaml)
+    views, oviews = _views(IM, [(0.5, 0.5, 2.5), (0.62, 0.5, 2.4), (0.4, 0.58, 2.6)], bg=0.0 if mask else 1.0)
     gen = torch.Generator().manual_seed(9)
     gts = [[torch.rand(3, IM, IM, generator=gen) for _ in views] for _ in range(frames)]
     gts[1] = None                                        # exclude_steps: frame 1 carries no loss
