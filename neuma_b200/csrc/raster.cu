@@ -12,42 +12,147 @@
 // skip alpha < 1/255, stop before T < 1e-4; pixel = sum c alpha T + T_final bg;
 // SH degree <= 3 with +0.5 and clamp at 0.
 //
-// B200 notes: the per-pixel blend keeps the classic one-CTA-per-tile shape
-// (the work is latency/occupancy bound at NeuMA's ~200 active tiles); the
-// backward reduces the per-Gaussian gradient contributions of a warp's 32 pixels
-// with shuffles before one atomic per warp (instead of 32), and the per-Gaussian
-// records are read as 128-bit vectors.
+// B200 notes: binning is a two-level bucket sort instead of upstream's global 64-bit radix
+// sort of (tile << 32 | depth) keys: tile counts by atomics in the preprocess, a one-CTA scan,
+// a scatter into per-tile buckets, then ONE CTA per tile sorts its bucket by
+// (depth bits << 32 | Gaussian id) in shared memory -- the same total order, no library sort,
+// ~1/6 of the key traffic, and NO host round trip: the instance count never leaves the device
+// (buffers have a capacity; an overflow is flagged and reported by the next call), so the
+// whole forward is capturable into a CUDA graph.  The per-pixel blend keeps the classic
+// one-CTA-per-tile shape (latency/occupancy bound at NeuMA's ~200 active tiles); the backward
+// reduces the per-Gaussian gradient contributions of a warp's 32 pixels with shuffles before
+// one atomic per warp (instead of 32), and the per-Gaussian records are read as 128-bit
+// vectors.
 #include "raster_common.cuh"
-#include <cub/cub.cuh>
 
 void neuma_raster_state_free(RasterState* s) {
   if (!s) return;
   cudaFree(s->depths); cudaFree(s->xy); cudaFree(s->conic_o); cudaFree(s->rgb);
-  cudaFree(s->clamped); cudaFree(s->tiles_touched); cudaFree(s->offsets);
-  cudaFree(s->dconic); cudaFree(s->dcolor);
-  cudaFree(s->keys_a); cudaFree(s->keys_b); cudaFree(s->vals_a); cudaFree(s->vals_b);
-  cudaFree(s->ranges); cudaFree(s->final_T); cudaFree(s->n_contrib); cudaFree(s->temp);
-  if (s->num_rendered_pinned) cudaFreeHost(s->num_rendered_pinned);
+  cudaFree(s->clamped); cudaFree(s->dconic); cudaFree(s->dcolor);
+  cudaFree(s->keys); cudaFree(s->plist);
+  cudaFree(s->tile_count); cudaFree(s->tile_start); cudaFree(s->tile_cursor);
+  cudaFree(s->ranges); cudaFree(s->final_T); cudaFree(s->n_contrib); cudaFree(s->d_num);
+  if (s->h_num) cudaFreeHost(s->h_num);
+  if (s->num_ready) cudaEventDestroy(s->num_ready);
   delete s;
 }
 
 namespace {
 
-__global__ void __launch_bounds__(256)
-tile_ranges_kernel(int L, const uint64_t* __restrict__ keys, uint2* __restrict__ ranges) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= L) return;
-  const uint32_t t = (uint32_t)(keys[i] >> 32);
-  if (i == 0) {
-    ranges[t].x = 0;
-  } else {
-    const uint32_t tp = (uint32_t)(keys[i - 1] >> 32);
-    if (t != tp) {
-      ranges[tp].y = i;
-      ranges[t].x = i;
+// exclusive scan of the per-tile instance counts (ONE CTA; tiles <= a few 10^4), total into
+// d_num[0]; also zeroes the scatter cursors.
+constexpr int SCAN_THREADS = 1024;
+__global__ void __launch_bounds__(SCAN_THREADS)
+tile_scan_kernel(int tiles, const uint32_t* __restrict__ count, uint32_t* __restrict__ start,
+                 uint32_t* __restrict__ cursor, int32_t* __restrict__ d_num) {
+  __shared__ uint32_t warp_sum[SCAN_THREADS / 32];
+  __shared__ uint32_t carry_s;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < tiles; base += SCAN_THREADS) {
+    const int i = base + tid;
+    const uint32_t v = i < tiles ? count[i] : 0u;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_sum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t w = warp_sum[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += t;
+      }
+      warp_sum[lane] = w;  // inclusive over warps
+    }
+    __syncthreads();
+    const uint32_t carry = carry_s;
+    const uint32_t excl = carry + (warp ? warp_sum[warp - 1] : 0u) + incl - v;
+    if (i < tiles) {
+      start[i] = excl;
+      cursor[i] = 0;
+    }
+    __syncthreads();
+    if (tid == SCAN_THREADS - 1) carry_s = carry + warp_sum[SCAN_THREADS / 32 - 1];
+    __syncthreads();
+  }
+  if (tid == 0) {
+    start[tiles] = carry_s;
+    d_num[0] = (int32_t)carry_s;   // d_num[1], the overflow flag, is sticky: only the host clears it
+  }
+}
+
+// ONE CTA per tile: sort the tile's bucket by (depth bits << 32 | Gaussian id) ascending -- depth
+// order with ties broken by Gaussian index, i.e. exactly what a stable sort of the duplication
+// order by (tile << 32 | depth) gives -- and emit the blend-order id list and the tile's range.
+// Buckets up to SORT_SMEM keys are sorted in shared memory, larger ones in place in global memory;
+// both by the same all-ascending bitonic network, which needs no padding for arbitrary n.
+constexpr int SORT_THREADS = 256, SORT_SMEM = 4096;
+__device__ __forceinline__ void bitonic_all_ascending(uint64_t* k, int n) {
+  int P = 1;
+  while (P < n) P <<= 1;
+  for (int size = 2; size <= P; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = threadIdx.x; t < (P >> 1); t += blockDim.x) {
+        // pair (i, j), i < j: first step of a merge mirrors (j = i ^ (size - 1)), the rest are j = i ^ stride
+        int i, j;
+        if (stride == (size >> 1)) {
+          const int blk = t / stride, off = t - blk * stride;
+          i = blk * size + off;
+          j = blk * size + size - 1 - off;
+        } else {
+          i = ((t / stride) * stride << 1) + (t % stride);
+          j = i + stride;
+        }
+        if (j < n) {  // elements >= n are virtual +inf: never exchanged
+          const uint64_t a = k[i], b = k[j];
+          if (a > b) { k[i] = b; k[j] = a; }
+        }
+      }
+      __syncthreads();
     }
   }
-  if (i == L - 1) ranges[t].y = L;
+}
+__global__ void __launch_bounds__(SORT_THREADS)
+tile_sort_kernel(int tiles, const uint32_t* __restrict__ tile_start, uint64_t* __restrict__ keys,
+                 uint32_t* __restrict__ plist, uint2* __restrict__ ranges, uint32_t cap) {
+  __shared__ uint64_t sk[SORT_SMEM];
+  const int t = blockIdx.x;
+  const uint32_t s0 = min(tile_start[t], cap), s1 = min(tile_start[t + 1], cap);
+  const int n = (int)(s1 - s0);
+  if (threadIdx.x == 0) ranges[t] = n > 0 ? make_uint2(s0, s1) : make_uint2(0u, 0u);
+  if (n <= 0) return;
+  uint64_t* g = keys + s0;
+  if (n <= SORT_SMEM) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) sk[i] = g[i];
+    __syncthreads();
+    bitonic_all_ascending(sk, n);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const uint64_t k = sk[i];
+      g[i] = k;
+      plist[s0 + i] = (uint32_t)k;
+    }
+  } else {
+    __syncthreads();
+    bitonic_all_ascending(g, n);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) plist[s0 + i] = (uint32_t)g[i];
+  }
+}
+
+// neuma_raster_export_binning: upstream's sorted (tile << 32 | depth bits) keys rebuilt from the buckets
+__global__ void __launch_bounds__(256)
+export_keys_kernel(int tiles, const uint2* __restrict__ ranges, const uint64_t* __restrict__ keys,
+                   uint64_t* __restrict__ out) {
+  const int t = blockIdx.x;
+  if (t >= tiles) return;
+  const uint2 r = ranges[t];
+  for (uint32_t i = r.x + threadIdx.x; i < r.y; i += blockDim.x)
+    out[i] = ((uint64_t)t << 32) | (keys[i] >> 32);
 }
 
 
@@ -398,20 +503,24 @@ int grow(neuma_ctx* ctx, T*& ptr, size_t count) {
 int ensure_state(neuma_ctx* ctx, int K, int tiles, int pix) {
   if (!ctx->raster) {
     ctx->raster = new RasterState();
-    NEUMA_CUDA(ctx, cudaMallocHost(&ctx->raster->num_rendered_pinned, sizeof(int)));
+    NEUMA_CUDA(ctx, cudaMallocHost(&ctx->raster->h_num, 2 * sizeof(int32_t)));
+    NEUMA_CUDA(ctx, cudaMalloc(&ctx->raster->d_num, 2 * sizeof(int32_t)));
+    NEUMA_CUDA(ctx, cudaMemset(ctx->raster->d_num, 0, 2 * sizeof(int32_t)));
+    NEUMA_CUDA(ctx, cudaEventCreateWithFlags(&ctx->raster->num_ready, cudaEventDisableTiming));
   }
   RasterState* s = ctx->raster;
   if (K > s->capK) {
     const int cap = K + K / 4 + 1024;
     if (grow(ctx, s->depths, cap) || grow(ctx, s->xy, cap) || grow(ctx, s->conic_o, cap) ||
         grow(ctx, s->rgb, (size_t)cap * 3) || grow(ctx, s->clamped, (size_t)cap * 3) ||
-        grow(ctx, s->tiles_touched, cap) || grow(ctx, s->offsets, cap) ||
         grow(ctx, s->dconic, cap) || grow(ctx, s->dcolor, (size_t)cap * 3))
       return 1;
     s->capK = cap;
   }
   if (tiles > s->capT) {
-    if (grow(ctx, s->ranges, tiles)) return 1;
+    if (grow(ctx, s->ranges, tiles) || grow(ctx, s->tile_count, tiles) || grow(ctx, s->tile_start, tiles + 1) ||
+        grow(ctx, s->tile_cursor, tiles))
+      return 1;
     s->capT = tiles;
   }
   if (pix > s->capPix) {
@@ -421,15 +530,17 @@ int ensure_state(neuma_ctx* ctx, int K, int tiles, int pix) {
   return 0;
 }
 
-int ensure_temp(neuma_ctx* ctx, size_t bytes) {
+int ensure_instances(neuma_ctx* ctx, size_t cap) {
   RasterState* s = ctx->raster;
-  if (bytes <= s->temp_bytes) return 0;
-  if (s->temp) cudaFree(s->temp);
-  s->temp = nullptr;
-  s->temp_bytes = 0;
-  NEUMA_CUDA(ctx, cudaMalloc(&s->temp, bytes + bytes / 4));
-  s->temp_bytes = bytes + bytes / 4;
+  if (cap <= s->capD) return 0;
+  if (grow(ctx, s->keys, cap) || grow(ctx, s->plist, cap)) return 1;
+  s->capD = cap;
   return 0;
+}
+
+bool stream_capturing(cudaStream_t st) {
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  return cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone;
 }
 
 int check_settings(neuma_ctx* ctx, const neuma_raster_settings* s, int K, int M) {
@@ -444,6 +555,25 @@ int check_settings(neuma_ctx* ctx, const neuma_raster_settings* s, int K, int M)
 
 extern "C" {
 
+// host side of the instance count: folds a finished asynchronous read-back into the state and
+// reports a forward whose instances did not fit the buffers
+static int absorb_count(neuma_ctx* ctx, bool wait) {
+  RasterState* s = ctx->raster;
+  if (!s->num_pending) return 0;
+  if (wait) NEUMA_CUDA(ctx, cudaEventSynchronize(s->num_ready));
+  else if (cudaEventQuery(s->num_ready) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+  s->num_pending = false;
+  s->num_rendered = s->h_num[0] < (int32_t)s->capD ? s->h_num[0] : (int)s->capD;
+  if (s->h_num[1]) {
+    snprintf(ctx->err, sizeof(ctx->err),
+             "raster: a previous forward produced %d tile instances, more than the buffers hold (%zu): that "
+             "image is incomplete; the capacity has been raised, run the forward again", s->h_num[0], s->capD);
+    s->h_num[1] = 0;
+    return 6;
+  }
+  return 0;
+}
+
 int neuma_raster_fwd(neuma_ctx* ctx, const neuma_raster_settings* set, int K, int M,
                      const float* means3D, const float* shs, const float* colors_precomp,
                      const float* opacities, const float* cov6, float* image, int32_t* radii,
@@ -456,52 +586,68 @@ int neuma_raster_fwd(neuma_ctx* ctx, const neuma_raster_settings* set, int K, in
   const Cam cam = make_cam(set);
   cudaStream_t st = (cudaStream_t)stream;
   const int tiles = cam.tiles_x * cam.tiles_y, pix = cam.W * cam.H;
-  if (int r = ensure_state(ctx, K > 0 ? K : 1, tiles, pix)) return r;
+  const bool capturing = stream_capturing(st);
+  if (!capturing) {
+    if (int r = ensure_state(ctx, K > 0 ? K : 1, tiles, pix)) return r;
+  } else if (!ctx->raster || K > ctx->raster->capK || tiles > ctx->raster->capT || pix > ctx->raster->capPix) {
+    return neuma_fail_msg(ctx, "raster: run one forward of this size before capturing it into a CUDA graph");
+  }
   RasterState* s = ctx->raster;
+  if (!capturing) {
+    // the previous forward's instance count, if its read-back has landed: overflow report + sizing
+    const int rc = absorb_count(ctx, false);
+    if (rc == 6) {
+      if (int r = ensure_instances(ctx, (size_t)s->h_num[0] * 2 + 4096)) return r;
+      NEUMA_CUDA(ctx, cudaMemsetAsync(s->d_num + 1, 0, sizeof(int32_t), st));
+      return rc;
+    }
+    if (rc) return rc;
+    const size_t want = s->num_rendered > 0 ? (size_t)s->num_rendered * 2 + 4096 : 0;
+    if (s->capD == 0) {
+      // first forward of this ctx: no history to size the buffers from -- a generous guess, then ONE
+      // synchronising read-back below (never again afterwards)
+      if (int r = ensure_instances(ctx, (size_t)K * 16 + (size_t)tiles * 4 + 65536)) return r;
+    } else if (want > s->capD) {
+      if (int r = ensure_instances(ctx, want)) return r;   // stay 2x above what the scene produces
+    }
+  }
+  const bool first = !capturing && s->num_rendered < 0 && !s->num_pending;
   s->K = K; s->tiles_x = cam.tiles_x; s->tiles_y = cam.tiles_y; s->W = cam.W; s->Himg = cam.H;
-  s->num_rendered = 0;
-  NEUMA_CUDA(ctx, cudaMemsetAsync(s->ranges, 0, (size_t)tiles * sizeof(uint2), st));
+  NEUMA_CUDA(ctx, cudaMemsetAsync(s->tile_count, 0, (size_t)tiles * sizeof(uint32_t), st));
   if (K > 0) {
     neuma_launch_preprocess(cam, K, M, means3D, shs, colors_precomp, opacities, cov6, radii, s, st);
     NEUMA_LAUNCH_CHECK(ctx, "preprocess_kernel");
-    size_t tb = 0;
-    cub::DeviceScan::InclusiveSum(nullptr, tb, s->tiles_touched, s->offsets, K, st);
-    if (int r = ensure_temp(ctx, tb)) return r;
-    NEUMA_CUDA(ctx, cub::DeviceScan::InclusiveSum(s->temp, s->temp_bytes, s->tiles_touched,
-                                                  s->offsets, K, st));
-    ctx->launches++;
-    // the instance count sizes the sort: one 4-byte D2H + stream sync, as upstream does
-    NEUMA_CUDA(ctx, cudaMemcpyAsync(s->num_rendered_pinned, s->offsets + (K - 1), sizeof(int),
-                                    cudaMemcpyDeviceToHost, st));
-    NEUMA_CUDA(ctx, cudaStreamSynchronize(st));
-    s->num_rendered = *s->num_rendered_pinned;
   }
-  const int L = s->num_rendered;
-  if (L > 0) {
-    if ((size_t)L > s->capD) {
-      const size_t cap = (size_t)L + L / 2 + 4096;
-      if (grow(ctx, s->keys_a, cap) || grow(ctx, s->keys_b, cap) || grow(ctx, s->vals_a, cap) ||
-          grow(ctx, s->vals_b, cap))
-        return 1;
-      s->capD = cap;
-    }
-    neuma_launch_duplicate(cam, K, radii, s, st);
-    NEUMA_LAUNCH_CHECK(ctx, "duplicate_kernel");
-    int tile_bits = 0;
-    while ((1 << tile_bits) < tiles) ++tile_bits;
-    size_t tb = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tb, s->keys_a, s->keys_b, s->vals_a, s->vals_b, L, 0,
-                                    32 + tile_bits, st);
-    if (int r = ensure_temp(ctx, tb)) return r;
-    NEUMA_CUDA(ctx, cub::DeviceRadixSort::SortPairs(s->temp, s->temp_bytes, s->keys_a, s->keys_b,
-                                                    s->vals_a, s->vals_b, L, 0, 32 + tile_bits, st));
-    ctx->launches += 4;
-    tile_ranges_kernel<<<(L + 255) / 256, 256, 0, st>>>(L, s->keys_b, s->ranges);
-    NEUMA_LAUNCH_CHECK(ctx, "tile_ranges_kernel");
+  tile_scan_kernel<<<1, SCAN_THREADS, 0, st>>>(tiles, s->tile_count, s->tile_start, s->tile_cursor, s->d_num);
+  NEUMA_LAUNCH_CHECK(ctx, "tile_scan_kernel");
+  if (K > 0) {
+    neuma_launch_bucket_scatter(cam, K, radii, s, st);
+    NEUMA_LAUNCH_CHECK(ctx, "bucket_scatter_kernel");
   }
+  tile_sort_kernel<<<tiles, SORT_THREADS, 0, st>>>(tiles, s->tile_start, s->keys, s->plist, s->ranges,
+                                                   (uint32_t)s->capD);
+  NEUMA_LAUNCH_CHECK(ctx, "tile_sort_kernel");
   render_fwd_kernel<<<dim3(cam.tiles_x, cam.tiles_y), dim3(BX, BY), 0, st>>>(
-      cam, s->ranges, s->vals_b, s->xy, s->rgb, s->conic_o, s->final_T, s->n_contrib, image);
+      cam, s->ranges, s->plist, s->xy, s->rgb, s->conic_o, s->final_T, s->n_contrib, image);
   NEUMA_LAUNCH_CHECK(ctx, "render_fwd_kernel");
+  if (!capturing) {
+    // the count travels to the host behind the kernels; nobody waits for it here
+    NEUMA_CUDA(ctx, cudaMemcpyAsync(s->h_num, s->d_num, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    NEUMA_CUDA(ctx, cudaEventRecord(s->num_ready, st));
+    s->num_pending = true;
+    s->num_rendered = -1;
+    if (first) {
+      // calibration of a fresh ctx: learn the scene's instance count once; re-run if the guess was short
+      const int rc = absorb_count(ctx, true);
+      if (rc == 6) {
+        if (int r = ensure_instances(ctx, (size_t)s->h_num[0] * 2 + 4096)) return r;
+        NEUMA_CUDA(ctx, cudaMemsetAsync(s->d_num + 1, 0, sizeof(int32_t), st));
+        return neuma_raster_fwd(ctx, set, K, M, means3D, shs, colors_precomp, opacities, cov6, image, radii,
+                                stream);
+      }
+      if (rc) return rc;
+    }
+  }
   return 0;
 }
 
@@ -536,8 +682,8 @@ int neuma_raster_bwd(neuma_ctx* ctx, const neuma_raster_settings* set, int K, in
   } else {
     if (s->K != K || s->W != set->image_width || s->Himg != set->image_height)
       return neuma_fail_msg(ctx, "raster_bwd: no matching forward state in this ctx");
-    xy = s->xy; conic_o = s->conic_o; rgb = s->rgb; clamped = s->clamped; plist = s->vals_b;
-    ranges = s->ranges; final_T = s->final_T; n_contrib = s->n_contrib; L = s->num_rendered;
+    xy = s->xy; conic_o = s->conic_o; rgb = s->rgb; clamped = s->clamped; plist = s->plist;
+    ranges = s->ranges; final_T = s->final_T; n_contrib = s->n_contrib; L = 1;  // empty tiles have empty ranges
   }
   cudaStream_t st = (cudaStream_t)stream;
   NEUMA_CUDA(ctx, cudaMemsetAsync(dL_dmeans2D, 0, (size_t)K * 3 * sizeof(float), st));
@@ -560,6 +706,7 @@ int neuma_raster_state_bytes(neuma_ctx* ctx, size_t* out_host) {
   if (!ctx || !out_host) return 2;
   RasterState* s = ctx->raster;
   if (!s) return neuma_fail_msg(ctx, "raster_state_bytes: no forward has run in this ctx");
+  if (int r = absorb_count(ctx, true)) return r;     // synchronises on the last forward's count
   *out_host = blob_layout(s->K, s->num_rendered, s->tiles_x * s->tiles_y, s->W * s->Himg).total;
   return 0;
 }
@@ -568,6 +715,7 @@ int neuma_raster_state_save(neuma_ctx* ctx, void* dst, void* stream) {
   if (!ctx || !dst) return 2;
   RasterState* s = ctx->raster;
   if (!s) return neuma_fail_msg(ctx, "raster_state_save: no forward has run in this ctx");
+  if (int r = absorb_count(ctx, true)) return r;
   const int K = s->K, L = s->num_rendered, tiles = s->tiles_x * s->tiles_y, pix = s->W * s->Himg;
   const BlobLayout b = blob_layout(K, L, tiles, pix);
   char* base = (char*)dst;
@@ -579,7 +727,7 @@ int neuma_raster_state_save(neuma_ctx* ctx, void* dst, void* stream) {
   NEUMA_CUDA(ctx, cp(b.conic, s->conic_o, (size_t)K * sizeof(float4)));
   NEUMA_CUDA(ctx, cp(b.rgb, s->rgb, (size_t)K * 3 * sizeof(float)));
   NEUMA_CUDA(ctx, cp(b.clamped, s->clamped, (size_t)K * 3));
-  NEUMA_CUDA(ctx, cp(b.plist, s->vals_b, (size_t)L * sizeof(uint32_t)));
+  NEUMA_CUDA(ctx, cp(b.plist, s->plist, (size_t)L * sizeof(uint32_t)));
   NEUMA_CUDA(ctx, cp(b.ranges, s->ranges, (size_t)tiles * sizeof(uint2)));
   NEUMA_CUDA(ctx, cp(b.final_T, s->final_T, (size_t)pix * sizeof(float)));
   NEUMA_CUDA(ctx, cp(b.n_contrib, s->n_contrib, (size_t)pix * sizeof(uint32_t)));
@@ -589,7 +737,10 @@ int neuma_raster_state_save(neuma_ctx* ctx, void* dst, void* stream) {
 int neuma_raster_num_rendered(neuma_ctx* ctx, void* stream, int* out_host) {
   if (!ctx || !out_host) return 2;
   (void)stream;
-  *out_host = ctx->raster ? ctx->raster->num_rendered : 0;
+  *out_host = 0;
+  if (!ctx->raster) return 0;
+  if (int r = absorb_count(ctx, true)) return r;       // the one place that waits for the count
+  *out_host = ctx->raster->num_rendered > 0 ? ctx->raster->num_rendered : 0;
   return 0;
 }
 
@@ -598,15 +749,18 @@ int neuma_raster_export_binning(neuma_ctx* ctx, uint64_t* keys, int32_t* gaussia
   if (!ctx || !ctx->raster) return neuma_fail_msg(ctx, "raster_export_binning: no forward state");
   RasterState* s = ctx->raster;
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t L = (size_t)s->num_rendered;
-  if (keys && L)
-    NEUMA_CUDA(ctx, cudaMemcpyAsync(keys, s->keys_b, L * sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
+  if (int r = absorb_count(ctx, true)) return r;
+  const size_t L = (size_t)(s->num_rendered > 0 ? s->num_rendered : 0);
+  const int tiles = s->tiles_x * s->tiles_y;
+  if (keys && L) {
+    export_keys_kernel<<<tiles, 256, 0, st>>>(tiles, s->ranges, s->keys, keys);
+    NEUMA_LAUNCH_CHECK(ctx, "export_keys_kernel");
+  }
   if (gaussian_ids && L)
-    NEUMA_CUDA(ctx, cudaMemcpyAsync(gaussian_ids, s->vals_b, L * sizeof(uint32_t),
+    NEUMA_CUDA(ctx, cudaMemcpyAsync(gaussian_ids, s->plist, L * sizeof(uint32_t),
                                     cudaMemcpyDeviceToDevice, st));
   if (tile_ranges)
-    NEUMA_CUDA(ctx, cudaMemcpyAsync(tile_ranges, s->ranges,
-                                    (size_t)s->tiles_x * s->tiles_y * sizeof(uint2),
+    NEUMA_CUDA(ctx, cudaMemcpyAsync(tile_ranges, s->ranges, (size_t)tiles * sizeof(uint2),
                                     cudaMemcpyDeviceToDevice, st));
   NEUMA_CUDA(ctx, cudaStreamSynchronize(st));
   return 0;

@@ -15,26 +15,33 @@ struct RasterState {
   float4* conic_o = nullptr;
   float* rgb = nullptr;
   unsigned char* clamped = nullptr;
-  uint32_t* tiles_touched = nullptr;
-  uint32_t* offsets = nullptr;
   float4* dconic = nullptr;  // backward: dL/d(A,B,C) of the conic, .w = dL/dopacity
   float* dcolor = nullptr;   // backward: dL/drgb [K,3]
-  // per instance
+  // per (Gaussian, tile) instance.  Binning is a two-level bucket sort, no global sort: count the
+  // instances of every tile, scan the counts, scatter every instance into its tile's bucket, then
+  // ONE CTA per tile sorts its bucket by (depth bits << 32 | Gaussian id) in shared memory -- the
+  // same total order as upstream's stable radix sort of (tile << 32 | depth) keys.
   size_t capD = 0;
-  uint64_t *keys_a = nullptr, *keys_b = nullptr;
-  uint32_t *vals_a = nullptr, *vals_b = nullptr;
+  uint64_t* keys = nullptr;   // [capD] depth bits << 32 | Gaussian id, bucketed by tile, sorted in place
+  uint32_t* plist = nullptr;  // [capD] Gaussian ids in blend order
   // per tile / pixel
   int capT = 0;
-  uint2* ranges = nullptr;
+  uint32_t* tile_count = nullptr;   // [tiles]
+  uint32_t* tile_start = nullptr;   // [tiles + 1] exclusive scan of the counts
+  uint32_t* tile_cursor = nullptr;  // [tiles]
+  uint2* ranges = nullptr;          // [tiles] (start, end) of the tile's instances; (0, 0) if none
   int capPix = 0;
   float* final_T = nullptr;
   uint32_t* n_contrib = nullptr;
-  // cub temp
-  void* temp = nullptr;
-  size_t temp_bytes = 0;
+  // instance count of the last forward: on the device ([0] = count, [1] = 1 if it exceeded capD)
+  // and, copied asynchronously after every forward, in pinned host memory
+  int32_t* d_num = nullptr;
+  int32_t* h_num = nullptr;
+  cudaEvent_t num_ready = nullptr;  // recorded after the async copy into h_num
+  bool num_pending = false;
   // last forward
-  int num_rendered = 0, K = 0, tiles_x = 0, tiles_y = 0, W = 0, Himg = 0;
-  int* num_rendered_pinned = nullptr;
+  int num_rendered = -1;            // -1: not read back yet (neuma_raster_num_rendered synchronises)
+  int K = 0, tiles_x = 0, tiles_y = 0, W = 0, Himg = 0;
 };
 
 
@@ -182,4 +189,4 @@ __device__ __forceinline__ void tile_rect(const Cam& cam, float px, float py, in
 void neuma_launch_preprocess(const Cam& cam, int K, int M, const float* means, const float* shs,
                              const float* colors_precomp, const float* opac, const float* cov6,
                              int* radii, RasterState* s, cudaStream_t st);
-void neuma_launch_duplicate(const Cam& cam, int K, const int* radii, RasterState* s, cudaStream_t st);
+void neuma_launch_bucket_scatter(const Cam& cam, int K, const int* radii, RasterState* s, cudaStream_t st);

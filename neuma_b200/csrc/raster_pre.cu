@@ -1,8 +1,8 @@
-// Per-Gaussian preprocess + instance duplication of the rasterizer forward.
+// Per-Gaussian preprocess + instance bucketing of the rasterizer forward.
 // Compiled with -fmad=false: every fp32 operation below rounds separately, in the
 // order written, exactly like oracle/raster_oracle.py::bin_np (numpy fp32), so the
-// depth bits, radii, tile rectangles -- and hence the sorted (tile << 32 | depth)
-// instance keys -- are bit-exact against the oracle.
+// depth bits, radii, tile rectangles -- and hence the per-tile blend order, equal to
+// upstream's sorted (tile << 32 | depth) instance keys -- are bit-exact against the oracle.
 #include "raster_common.cuh"
 
 namespace {
@@ -14,11 +14,10 @@ preprocess_kernel(Cam cam, int K, int M, const float* __restrict__ means,
                   const float* __restrict__ opac, const float* __restrict__ cov6,
                   int* __restrict__ radii, float* __restrict__ depths, float2* __restrict__ xy,
                   float4* __restrict__ conic_o, float* __restrict__ rgb,
-                  unsigned char* __restrict__ clamped, uint32_t* __restrict__ tiles_touched) {
+                  unsigned char* __restrict__ clamped, uint32_t* __restrict__ tile_count) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= K) return;
   radii[i] = 0;
-  tiles_touched[i] = 0;
   const float p[3] = {means[3 * i], means[3 * i + 1], means[3 * i + 2]};
   float pv[3];
   xform43(cam.view, p, pv);
@@ -66,26 +65,30 @@ preprocess_kernel(Cam cam, int K, int M, const float* __restrict__ means,
   radii[i] = radius;
   xy[i] = make_float2(px, py);
   conic_o[i] = make_float4(cv.c * di, -cv.b * di, cv.a * di, opac[i]);
-  tiles_touched[i] = (uint32_t)((x1 - x0) * (y1 - y0));
+  // first level of the bucket sort: how many instances every tile gets
+  for (int y = y0; y < y1; ++y)
+    for (int x = x0; x < x1; ++x) atomicAdd(&tile_count[y * cam.tiles_x + x], 1u);
 }
 
+// second level: every instance goes into its tile's bucket (any order inside the bucket; the
+// per-tile sort fixes it).  Instances beyond the capacity are dropped and flagged.
 __global__ void __launch_bounds__(256)
-duplicate_kernel(Cam cam, int K, const float2* __restrict__ xy, const float* __restrict__ depths,
-                 const uint32_t* __restrict__ offsets, const int* __restrict__ radii,
-                 uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+bucket_scatter_kernel(Cam cam, int K, const float2* __restrict__ xy, const float* __restrict__ depths,
+                      const int* __restrict__ radii, const uint32_t* __restrict__ tile_start,
+                      uint32_t* __restrict__ tile_cursor, uint64_t* __restrict__ keys, uint32_t cap,
+                      int32_t* __restrict__ d_num) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= K) return;
   if (radii[i] <= 0) return;
-  uint32_t off = (i == 0) ? 0 : offsets[i - 1];
   int x0, y0, x1, y1;
   tile_rect(cam, xy[i].x, xy[i].y, radii[i], x0, y0, x1, y1);
-  const uint32_t dbits = __float_as_uint(depths[i]);
+  const uint64_t key = ((uint64_t)__float_as_uint(depths[i]) << 32) | (uint32_t)i;
   for (int y = y0; y < y1; ++y)
     for (int x = x0; x < x1; ++x) {
-      const uint64_t key = ((uint64_t)(y * cam.tiles_x + x) << 32) | dbits;
-      keys[off] = key;
-      vals[off] = (uint32_t)i;
-      ++off;
+      const int t = y * cam.tiles_x + x;
+      const uint32_t pos = tile_start[t] + atomicAdd(&tile_cursor[t], 1u);
+      if (pos < cap) keys[pos] = key;
+      else d_num[1] = 1;
     }
 }
 
@@ -96,10 +99,10 @@ void neuma_launch_preprocess(const Cam& cam, int K, int M, const float* means, c
                              int* radii, RasterState* s, cudaStream_t st) {
   preprocess_kernel<<<(K + 255) / 256, 256, 0, st>>>(cam, K, M, means, shs, colors_precomp, opac,
                                                      cov6, radii, s->depths, s->xy, s->conic_o,
-                                                     s->rgb, s->clamped, s->tiles_touched);
+                                                     s->rgb, s->clamped, s->tile_count);
 }
 
-void neuma_launch_duplicate(const Cam& cam, int K, const int* radii, RasterState* s, cudaStream_t st) {
-  duplicate_kernel<<<(K + 255) / 256, 256, 0, st>>>(cam, K, s->xy, s->depths, s->offsets, radii,
-                                                    s->keys_a, s->vals_a);
+void neuma_launch_bucket_scatter(const Cam& cam, int K, const int* radii, RasterState* s, cudaStream_t st) {
+  bucket_scatter_kernel<<<(K + 255) / 256, 256, 0, st>>>(cam, K, s->xy, s->depths, radii, s->tile_start,
+                                                         s->tile_cursor, s->keys, (uint32_t)s->capD, s->d_num);
 }
