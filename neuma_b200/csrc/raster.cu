@@ -90,9 +90,10 @@ tile_scan_kernel(int tiles, const uint32_t* __restrict__ count, uint32_t* __rest
 // ONE CTA per tile: sort the tile's bucket by (depth bits << 32 | Gaussian id) ascending -- depth
 // order with ties broken by Gaussian index, i.e. exactly what a stable sort of the duplication
 // order by (tile << 32 | depth) gives -- and emit the blend-order id list and the tile's range.
-// Buckets up to SORT_SMEM keys are sorted in shared memory, larger ones in place in global memory;
-// both by the same all-ascending bitonic network, which needs no padding for arbitrary n.
-constexpr int SORT_THREADS = 256, SORT_SMEM = 4096;
+// Buckets up to SORT_SMEM keys are sorted here in static shared memory, larger ones by
+// tile_sort_big_kernel; both by the same all-ascending bitonic network, which needs no padding
+// for arbitrary n.
+constexpr int SORT_THREADS = 256, SORT_SMEM = 2048;
 __device__ __forceinline__ void bitonic_all_ascending(uint64_t* k, int n) {
   int P = 1;
   while (P < n) P <<= 1;
@@ -128,17 +129,40 @@ tile_sort_kernel(int tiles, const uint32_t* __restrict__ tile_start, uint64_t* _
   if (threadIdx.x == 0) ranges[t] = n > 0 ? make_uint2(s0, s1) : make_uint2(0u, 0u);
   if (n <= 0) return;
   uint64_t* g = keys + s0;
-  if (n <= SORT_SMEM) {
-    for (int i = threadIdx.x; i < n; i += blockDim.x) sk[i] = g[i];
+  if (n > SORT_SMEM) return;        // tile_sort_big_kernel's
+  for (int i = threadIdx.x; i < n; i += blockDim.x) sk[i] = g[i];
+  __syncthreads();
+  bitonic_all_ascending(sk, n);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const uint64_t k = sk[i];
+    g[i] = k;
+    plist[s0 + i] = (uint32_t)k;
+  }
+}
+
+// tiles whose bucket does not fit tile_sort_kernel's static shared memory: 1024 threads and up to
+// SORT_BIG keys in dynamic shared memory (beyond that, in place in global memory).  Launched over
+// all tiles; the small ones were done by tile_sort_kernel and exit at once.
+constexpr int SORT_BIG_THREADS = 1024, SORT_BIG = 16384;
+__global__ void __launch_bounds__(SORT_BIG_THREADS)
+tile_sort_big_kernel(int tiles, const uint32_t* __restrict__ tile_start, uint64_t* __restrict__ keys,
+                     uint32_t* __restrict__ plist, uint32_t cap) {
+  extern __shared__ __align__(16) uint64_t sbig[];
+  const int t = blockIdx.x;
+  const uint32_t s0 = min(tile_start[t], cap), s1 = min(tile_start[t + 1], cap);
+  const int n = (int)(s1 - s0);
+  if (n <= SORT_SMEM) return;
+  uint64_t* g = keys + s0;
+  if (n <= SORT_BIG) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) sbig[i] = g[i];
     __syncthreads();
-    bitonic_all_ascending(sk, n);
+    bitonic_all_ascending(sbig, n);
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      const uint64_t k = sk[i];
+      const uint64_t k = sbig[i];
       g[i] = k;
       plist[s0 + i] = (uint32_t)k;
     }
   } else {
-    __syncthreads();
     bitonic_all_ascending(g, n);
     for (int i = threadIdx.x; i < n; i += blockDim.x) plist[s0 + i] = (uint32_t)g[i];
   }
@@ -506,6 +530,8 @@ int ensure_state(neuma_ctx* ctx, int K, int tiles, int pix) {
     NEUMA_CUDA(ctx, cudaMallocHost(&ctx->raster->h_num, 2 * sizeof(int32_t)));
     NEUMA_CUDA(ctx, cudaMalloc(&ctx->raster->d_num, 2 * sizeof(int32_t)));
     NEUMA_CUDA(ctx, cudaMemset(ctx->raster->d_num, 0, 2 * sizeof(int32_t)));
+    NEUMA_CUDA(ctx, cudaFuncSetAttribute(tile_sort_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(SORT_BIG * sizeof(uint64_t))));
     NEUMA_CUDA(ctx, cudaEventCreateWithFlags(&ctx->raster->num_ready, cudaEventDisableTiming));
   }
   RasterState* s = ctx->raster;
@@ -569,6 +595,7 @@ static int absorb_count(neuma_ctx* ctx, bool wait) {
              "raster: a previous forward produced %d tile instances, more than the buffers hold (%zu): that "
              "image is incomplete; the capacity has been raised, run the forward again", s->h_num[0], s->capD);
     s->h_num[1] = 0;
+    cudaMemset(s->d_num + 1, 0, sizeof(int32_t));   // rare path: the sticky device flag is cleared here
     return 6;
   }
   return 0;
@@ -611,7 +638,13 @@ int neuma_raster_fwd(neuma_ctx* ctx, const neuma_raster_settings* set, int K, in
       if (int r = ensure_instances(ctx, want)) return r;   // stay 2x above what the scene produces
     }
   }
-  const bool first = !capturing && s->num_rendered < 0 && !s->num_pending;
+  // a fresh ctx, or a different scene / image than the previous forward: calibrate (one synchronising
+  // read-back of the count); a steady stream of frames of one scene never synchronises
+  const bool changed = s->K != K || s->W != cam.W || s->Himg != cam.H;
+  const bool first = !capturing && ((s->num_rendered < 0 && !s->num_pending) || changed);
+  if (first && changed && !capturing) {
+    if (int r = ensure_instances(ctx, (size_t)K * 16 + (size_t)tiles * 4 + 65536)) return r;
+  }
   s->K = K; s->tiles_x = cam.tiles_x; s->tiles_y = cam.tiles_y; s->W = cam.W; s->Himg = cam.H;
   NEUMA_CUDA(ctx, cudaMemsetAsync(s->tile_count, 0, (size_t)tiles * sizeof(uint32_t), st));
   if (K > 0) {
@@ -627,6 +660,9 @@ int neuma_raster_fwd(neuma_ctx* ctx, const neuma_raster_settings* set, int K, in
   tile_sort_kernel<<<tiles, SORT_THREADS, 0, st>>>(tiles, s->tile_start, s->keys, s->plist, s->ranges,
                                                    (uint32_t)s->capD);
   NEUMA_LAUNCH_CHECK(ctx, "tile_sort_kernel");
+  tile_sort_big_kernel<<<tiles, SORT_BIG_THREADS, SORT_BIG * sizeof(uint64_t), st>>>(
+      tiles, s->tile_start, s->keys, s->plist, (uint32_t)s->capD);
+  NEUMA_LAUNCH_CHECK(ctx, "tile_sort_big_kernel");
   render_fwd_kernel<<<dim3(cam.tiles_x, cam.tiles_y), dim3(BX, BY), 0, st>>>(
       cam, s->ranges, s->plist, s->xy, s->rgb, s->conic_o, s->final_T, s->n_contrib, image);
   NEUMA_LAUNCH_CHECK(ctx, "render_fwd_kernel");
