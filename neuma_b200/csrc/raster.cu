@@ -84,6 +84,7 @@ tile_scan_kernel(int tiles, const uint32_t* __restrict__ count, uint32_t* __rest
   if (tid == 0) {
     start[tiles] = carry_s;
     d_num[0] = (int32_t)carry_s;   // d_num[1], the overflow flag, is sticky: only the host clears it
+    d_num[2] = 0;                  // length of the big-tile list (tile_sort_kernel appends)
   }
 }
 
@@ -121,7 +122,8 @@ __device__ __forceinline__ void bitonic_all_ascending(uint64_t* k, int n) {
 }
 __global__ void __launch_bounds__(SORT_THREADS)
 tile_sort_kernel(int tiles, const uint32_t* __restrict__ tile_start, uint64_t* __restrict__ keys,
-                 uint32_t* __restrict__ plist, uint2* __restrict__ ranges, uint32_t cap) {
+                 uint32_t* __restrict__ plist, uint2* __restrict__ ranges, uint32_t cap,
+                 int32_t* __restrict__ d_num, uint32_t* __restrict__ big_list) {
   __shared__ uint64_t sk[SORT_SMEM];
   const int t = blockIdx.x;
   const uint32_t s0 = min(tile_start[t], cap), s1 = min(tile_start[t + 1], cap);
@@ -129,7 +131,10 @@ tile_sort_kernel(int tiles, const uint32_t* __restrict__ tile_start, uint64_t* _
   if (threadIdx.x == 0) ranges[t] = n > 0 ? make_uint2(s0, s1) : make_uint2(0u, 0u);
   if (n <= 0) return;
   uint64_t* g = keys + s0;
-  if (n > SORT_SMEM) return;        // tile_sort_big_kernel's
+  if (n > SORT_SMEM) {              // tile_sort_big_kernel's: queue the tile
+    if (threadIdx.x == 0) big_list[atomicAdd(&d_num[2], 1)] = (uint32_t)t;
+    return;
+  }
   for (int i = threadIdx.x; i < n; i += blockDim.x) sk[i] = g[i];
   __syncthreads();
   bitonic_all_ascending(sk, n);
@@ -140,19 +145,22 @@ tile_sort_kernel(int tiles, const uint32_t* __restrict__ tile_start, uint64_t* _
   }
 }
 
-// tiles whose bucket does not fit tile_sort_kernel's static shared memory: 1024 threads and up to
-// SORT_BIG keys in dynamic shared memory (beyond that, in place in global memory).  Launched over
-// all tiles; the small ones were done by tile_sort_kernel and exit at once.
+// tiles whose bucket does not fit tile_sort_kernel's static shared memory (queued in big_list):
+// 1024 threads and up to SORT_BIG keys in dynamic shared memory (beyond that, in place in global
+// memory).  A fixed grid of one CTA per SM walks the queue.
 constexpr int SORT_BIG_THREADS = 1024, SORT_BIG = 16384;
 __global__ void __launch_bounds__(SORT_BIG_THREADS)
-tile_sort_big_kernel(int tiles, const uint32_t* __restrict__ tile_start, uint64_t* __restrict__ keys,
-                     uint32_t* __restrict__ plist, uint32_t cap) {
+tile_sort_big_kernel(const uint32_t* __restrict__ tile_start, uint64_t* __restrict__ keys,
+                     uint32_t* __restrict__ plist, uint32_t cap, const int32_t* __restrict__ d_num,
+                     const uint32_t* __restrict__ big_list) {
   extern __shared__ __align__(16) uint64_t sbig[];
-  const int t = blockIdx.x;
+  const int nbig = d_num[2];
+  for (int q = blockIdx.x; q < nbig; q += gridDim.x) {
+  const int t = (int)big_list[q];
   const uint32_t s0 = min(tile_start[t], cap), s1 = min(tile_start[t + 1], cap);
   const int n = (int)(s1 - s0);
-  if (n <= SORT_SMEM) return;
   uint64_t* g = keys + s0;
+  __syncthreads();                  // the previous tile's keys have left shared memory
   if (n <= SORT_BIG) {
     for (int i = threadIdx.x; i < n; i += blockDim.x) sbig[i] = g[i];
     __syncthreads();
@@ -165,6 +173,7 @@ tile_sort_big_kernel(int tiles, const uint32_t* __restrict__ tile_start, uint64_
   } else {
     bitonic_all_ascending(g, n);
     for (int i = threadIdx.x; i < n; i += blockDim.x) plist[s0 + i] = (uint32_t)g[i];
+  }
   }
 }
 
@@ -528,8 +537,8 @@ int ensure_state(neuma_ctx* ctx, int K, int tiles, int pix) {
   if (!ctx->raster) {
     ctx->raster = new RasterState();
     NEUMA_CUDA(ctx, cudaMallocHost(&ctx->raster->h_num, 2 * sizeof(int32_t)));
-    NEUMA_CUDA(ctx, cudaMalloc(&ctx->raster->d_num, 2 * sizeof(int32_t)));
-    NEUMA_CUDA(ctx, cudaMemset(ctx->raster->d_num, 0, 2 * sizeof(int32_t)));
+    NEUMA_CUDA(ctx, cudaMalloc(&ctx->raster->d_num, 4 * sizeof(int32_t)));
+    NEUMA_CUDA(ctx, cudaMemset(ctx->raster->d_num, 0, 4 * sizeof(int32_t)));
     NEUMA_CUDA(ctx, cudaFuncSetAttribute(tile_sort_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)(SORT_BIG * sizeof(uint64_t))));
     NEUMA_CUDA(ctx, cudaEventCreateWithFlags(&ctx->raster->num_ready, cudaEventDisableTiming));
@@ -658,10 +667,12 @@ int neuma_raster_fwd(neuma_ctx* ctx, const neuma_raster_settings* set, int K, in
     NEUMA_LAUNCH_CHECK(ctx, "bucket_scatter_kernel");
   }
   tile_sort_kernel<<<tiles, SORT_THREADS, 0, st>>>(tiles, s->tile_start, s->keys, s->plist, s->ranges,
-                                                   (uint32_t)s->capD);
+                                                   (uint32_t)s->capD, s->d_num, s->tile_cursor);
   NEUMA_LAUNCH_CHECK(ctx, "tile_sort_kernel");
-  tile_sort_big_kernel<<<tiles, SORT_BIG_THREADS, SORT_BIG * sizeof(uint64_t), st>>>(
-      tiles, s->tile_start, s->keys, s->plist, (uint32_t)s->capD);
+  // (the scatter is done with its cursors: the array doubles as the queue of tiles too big for the
+  // kernel above)
+  tile_sort_big_kernel<<<ctx->num_sms, SORT_BIG_THREADS, SORT_BIG * sizeof(uint64_t), st>>>(
+      s->tile_start, s->keys, s->plist, (uint32_t)s->capD, s->d_num, s->tile_cursor);
   NEUMA_LAUNCH_CHECK(ctx, "tile_sort_big_kernel");
   render_fwd_kernel<<<dim3(cam.tiles_x, cam.tiles_y), dim3(BX, BY), 0, st>>>(
       cam, s->ranges, s->plist, s->xy, s->rgb, s->conic_o, s->final_T, s->n_contrib, image);
