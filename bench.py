@@ -392,11 +392,98 @@ def run_gpu(args):
     }
     if slab is not None:
         line["slab"] = slab
+    if not args.no_dropin:
+        line["dropin"] = dropin_measure(wl, dev, (x0, v0, C0, F0))
+        line["dropin_frames_per_s"] = line["dropin"]["frames_per_s"]
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_sample(wl, x0.cpu(), v0.cpu(), C0.cpu(), F0.cpu())
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------- drop-in (Level-1) path
+def dropin_measure(wl, dev, state0, steps: int = 5, warmup: int = 2) -> dict:
+    """The SAME frame through the reference-shaped classes with autograd, exactly as finetune.py's hot
+    loop calls them after the import swap of INTEGRATION.md (elasticity -> MPMCacheDiffSim ->
+    plasticity per substep, compute_bindings_*, diff_rasterization, l2_loss, loss.backward()): what a
+    user gets WITHOUT adopting FusedFrame."""
+    import types
+    from neuma_b200.sim import MPMModelBuilder, MPMCacheDiffSim, MPMStaticsInitializer, MPMInitData
+    from neuma_b200.material import InvariantFullMetaElasticity, InvariantFullMetaPlasticity
+    from neuma_b200.glue import compute_bindings_xyz, compute_bindings_F, diff_rasterization, l2_loss
+    spec, p, g, S = wl["spec"], wl["p"], wl["g"], wl["S"]
+    z = np.load(GOLD)
+    sim_cfg = dict(num_grids=spec["G"], dt=spec["dt"], bound=1, gravity=[0.0, -9.8, 0.0], bc="noslip", eps=6e-7)
+    model = MPMModelBuilder().parse_cfg(sim_cfg).finalize(dev, requires_grad=True)
+    sim = MPMCacheDiffSim(model, S)
+    init = MPMInitData(rho=1000.0, clip_bound=0.1, span=(0, S), num_particles=spec["n"], vol=float(p["vol"][0]),
+                       pos=p["x"].numpy())
+    si = MPMStaticsInitializer(model)
+    si.add_group(init)
+    statics = si.finalize()
+    mcfg = dict(layer_widths=[64, 64], norm=None, nonlinearity="gelu", no_bias=True, normalize_input=True,
+                alpha=float(z["alpha"]))
+    mods = []
+    for cls, tag in ((InvariantFullMetaElasticity, "elastic"), (InvariantFullMetaPlasticity, "plastic")):
+        m = cls(mcfg).to(dev)
+        m.init_lora_layers(r=16, lora_alpha=16)
+        m.load_state_dict({k[len(f"param_{tag}."):]: torch.from_numpy(z[k]).float() for k in z.files
+                           if k.startswith(f"param_{tag}.")})
+        m.to(dev)
+        m.freeze_all_except_lora()
+        mods.append(m)
+    elasticity, plasticity = mods
+
+    class G_:                                   # the accessors diff_rasterization uses (gaussian_model.py:95-118)
+        active_sh_degree = 3
+        get_xyz = g["xyz"].to(dev)
+        get_opacity = g["opac"].to(dev)
+        get_features = g["shs"].to(dev)
+        _cov = g["cov6"].to(dev)
+
+        def get_covariance(self, scaling_modifier=1):
+            return self._cov
+    gaussians = G_()
+    cam_ = wl["cam"]
+    cam = types.SimpleNamespace(FoVx=cam_.FoVx, FoVy=cam_.FoVy, image_height=IMAGE, image_width=IMAGE,
+                                world_view_transform=cam_.world_view_transform.to(dev),
+                                full_proj_transform=cam_.full_proj_transform.to(dev),
+                                camera_center=cam_.camera_center.to(dev))
+    bg = torch.ones(3, device=dev)
+    B = torch.sparse_csr_tensor(g["rowptr"].long(), g["col"].long(), g["w"], (g["K"], spec["n"])).to_sparse_coo().to(dev)
+    gt = wl["gt"].to(dev)
+    x0, v0, C0, F0 = state0
+
+    def frame():
+        for m in mods:
+            m.zero_grad(set_to_none=True)
+        x, v, C, F = x0, v0, C0, F0
+        de_x_prev = p["x"].to(dev)
+        for it in range(S):
+            stress = elasticity(F)
+            x, v, C, F = sim(statics, it, x, v, C, F, stress)
+            F = plasticity(F)
+        means3D = compute_bindings_xyz(x, de_x_prev, gaussians.get_xyz, B)
+        deform_grad = compute_bindings_F(F, B)
+        render = diff_rasterization(means3D, deform_grad, gaussians, cam, bg)
+        loss = l2_loss(render, gt)
+        loss.backward()
+        return loss
+    for _ in range(warmup):
+        frame()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        loss = frame()
+    b.record()
+    b.synchronize()
+    ms = a.elapsed_time(b) / steps
+    model.check(sim.curr_states)
+    return {"frames_per_s": 1000.0 / ms, "ms_per_frame": ms, "loss": float(loss), "steps": steps,
+            "api": "neuma_b200.sim.MPMCacheDiffSim + material.InvariantFullMeta* (LoRA r16, autograd) + glue."
+                   "diff_rasterization: the reference's finetune.py loop with the import swap only"}
 
 
 # --------------------------------------------------------------------------- Z-slab mode
@@ -612,6 +699,7 @@ def main():
                     help="parity-test configs of BASELINE.json for the record; the headline is jellyduck-100k-128")
     ap.add_argument("--no-fuse", action="store_true",
                     help="A/B: P2G / adjoint scatter as their own kernels instead of inside the constitutive epilogues")
+    ap.add_argument("--no-dropin", action="store_true", help="skip the drop-in (autograd classes) measurement")
     ap.add_argument("--no-slab", action="store_true", help="skip the Z-slab (config 5) section of the line")
     ap.add_argument("--slab-steps", type=int, default=5, help="timed frames of the Z-slab section")
     ap.add_argument("--halo", default="fused", choices=["fused", "peer", "nccl"],

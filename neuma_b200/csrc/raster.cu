@@ -96,21 +96,18 @@ tile_scan_kernel(int tiles, const uint32_t* __restrict__ count, uint32_t* __rest
 // for arbitrary n.
 constexpr int SORT_THREADS = 256, SORT_SMEM = 2048;
 __device__ __forceinline__ void bitonic_all_ascending(uint64_t* k, int n) {
-  int P = 1;
-  while (P < n) P <<= 1;
-  for (int size = 2; size <= P; size <<= 1) {
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      for (int t = threadIdx.x; t < (P >> 1); t += blockDim.x) {
+  int lp = 0;
+  while ((1 << lp) < n) ++lp;             // P = 2^lp >= n
+  const int half = (1 << lp) >> 1;
+  for (int lsize = 1; lsize <= lp; ++lsize) {
+    for (int ls = lsize - 1; ls >= 0; --ls) {   // stride = 2^ls (shifts, not divisions, in the pair math)
+      const int stride = 1 << ls, mask = stride - 1;
+      const bool mirror = ls == lsize - 1;
+      for (int t = threadIdx.x; t < half; t += blockDim.x) {
         // pair (i, j), i < j: first step of a merge mirrors (j = i ^ (size - 1)), the rest are j = i ^ stride
-        int i, j;
-        if (stride == (size >> 1)) {
-          const int blk = t / stride, off = t - blk * stride;
-          i = blk * size + off;
-          j = blk * size + size - 1 - off;
-        } else {
-          i = ((t / stride) * stride << 1) + (t % stride);
-          j = i + stride;
-        }
+        const int base = (t >> ls) << (ls + 1), off = t & mask;
+        const int i = base + off;
+        const int j = mirror ? base + (stride << 1) - 1 - off : i + stride;
         if (j < n) {  // elements >= n are virtual +inf: never exchanged
           const uint64_t a = k[i], b = k[j];
           if (a > b) { k[i] = b; k[j] = a; }

@@ -105,13 +105,27 @@ class _ConstitutiveFunction(torch.autograd.Function):
         ctx.kind, ctx.alpha = kind, alpha
         return out
 
+    _partials: dict = {}        # per device: the per-CTA weight-gradient partial sums (zeroed by the reduce)
+
     @staticmethod
     def backward(ctx, gout: Tensor):
         Fd, W0, W1, W2 = ctx.saved_tensors
         want_w = any(ctx.needs_input_grad[3:6])
-        gF, g0, g1, g2 = ops.constitutive_bwd(ctx.kind, Fd, W0, W1, W2, ctx.alpha, gout.contiguous(),
-                                              want_wgrad=want_w)
-        return None, None, (gF if ctx.needs_input_grad[2] else None), g0, g1, g2
+        if not want_w:
+            gF, g0, g1, g2 = ops.constitutive_bwd(ctx.kind, Fd, W0, W1, W2, ctx.alpha, gout.contiguous(),
+                                                  want_wgrad=False)
+            return None, None, (gF if ctx.needs_input_grad[2] else None), None, None, None
+        # weight gradients through the per-CTA partial sums + one reduce (no same-address atomics:
+        # 25 % of the kernel otherwise), as FusedFrame does
+        part = _ConstitutiveFunction._partials.get(Fd.device)
+        if part is None:
+            part = _ConstitutiveFunction._partials[Fd.device] = ops.constitutive_partials(Fd)
+        staged = ops.constitutive_stage(W0, W1, W2)
+        gF = torch.empty_like(Fd)
+        ops.constitutive_bwd_partials(ctx.kind, Fd, staged, ctx.alpha, gout.contiguous(), gF, part)
+        gW = [torch.zeros_like(w) for w in (W0, W1, W2)]
+        ops.constitutive_reduce_partials(part, *gW)
+        return None, None, (gF if ctx.needs_input_grad[2] else None), gW[0], gW[1], gW[2]
 
 
 class _InvariantFullMeta(nn.Module):

@@ -20,7 +20,8 @@ class MPMSimFunction(autograd.Function):
     def forward(ctx, model: MPMModel, statics: MPMStatics, state_curr: MPMState, state_next: MPMState,
                 x: Tensor, v: Tensor, C: Tensor, F: Tensor, stress: Tensor):
         state_curr.from_torch(x=x, v=v, C=C, F=F, stress=stress)
-        model.forward(statics, state_curr, state_next, None)
+        # the differentiable path keeps the substep's grid for the backward (no P2G recompute)
+        model.forward(statics, state_curr, state_next, None, save_grid=True)
         x_next, v_next, C_next, F_next, _ = state_next.to_torch()
         ctx.model = model
         ctx.statics = statics

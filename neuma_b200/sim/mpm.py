@@ -181,10 +181,59 @@ class MPMModel(object):
         statics.init(shape=shape, device=self.device)
         return statics
 
-    def forward(self, statics: MPMStatics, state_curr: MPMState, state_next: MPMState, tape=None) -> None:
+    def forward(self, statics: MPMStatics, state_curr: MPMState, state_next: MPMState, tape=None,
+                save_grid: bool = False) -> None:
+        """save_grid (the differentiable path, MPMSimFunction): the substep runs on the ROLLOUT kernels --
+        its (v, m) grid is kept in a compact, box-sized slot owned by `state_curr`, so that backward()
+        reads it instead of re-running P2G + grid_op (the reference recomputes them, mpm.py:312-315),
+        clears touch the occupied box only, and the node box of the NEXT substep comes out of G2P."""
         pc, pn = state_curr.particle, state_next.particle
-        ops.mpm_substep_fwd(self._cconst(), pc.x, pc.v, pc.C, pc.F, pc.stress, statics.vol, statics.rho,
-                            statics.clip_bound, statics.enabled, out=(pn.x, pn.v, pn.C, pn.F))
+        if not save_grid or state_curr is state_next:
+            ops.mpm_substep_fwd(self._cconst(), pc.x, pc.v, pc.C, pc.F, pc.stress, statics.vol, statics.rho,
+                                statics.clip_bound, statics.enabled, out=(pn.x, pn.v, pn.C, pn.F))
+            state_curr.grid = None
+            return
+        dev = pc.x.device
+        if getattr(state_curr, "box", None) is None:
+            state_curr.box = torch.zeros(2, 8, dtype=torch.int32, device=dev)
+        box = state_curr.box
+        # the node box of x: handed over by the previous substep's G2P if x is its output, untouched
+        hint = getattr(self, "_box_hint", None)
+        if hint is not None and hint[0] == pc.x.data_ptr() and hint[1] == pc.x._version:
+            box[0].copy_(hint[2])
+        else:
+            ops.mpm_box_from_x(self._cconst(), pc.x, statics.enabled, box[0])
+        c = self._cconst_compact(box[0])
+        if getattr(state_curr, "grid", None) is None or state_curr.grid.shape[0] != c.cap_nodes:
+            state_curr.grid = torch.empty(c.cap_nodes, 4, dtype=torch.float32, device=dev)
+        ops.mpm_rollout_fwd(c, pc.x, pc.v, pc.C, pc.F, pc.stress, statics.vol, statics.rho, statics.clip_bound,
+                            statics.enabled, (pn.x, pn.v, pn.C, pn.F), state_curr.grid, None, box[0], box[1])
+        self._box_hint = (pn.x.data_ptr(), pn.x._version, box[1])
+
+    def _cconst_compact(self, box0: Tensor):
+        """the C constant with compact grid slots; their capacity is fixed from the first box seen
+        (one host read), widened by 6 nodes per side like FusedFrame"""
+        cc = getattr(self, "_cc_compact", None)
+        if cc is None:
+            b = box0.cpu().tolist()
+            G, m = self.constant.num_grids, 6
+            if any(h < l for l, h in zip(b[:3], b[3:6])):
+                cap = 4096
+            else:
+                ext = [min(h + m, G - 1) - max(l - m, 0) + 1 for l, h in zip(b[:3], b[3:6])]
+                ext[0] = min(G + 7, ((ext[0] + 7) // 8 + 1) * 8)
+                cap = int(ext[0] * ext[1] * ext[2])
+            c = self.constant
+            cc = self._cc_compact = ops.mpm_const(c.num_grids, c.dt, c.bound, tuple(float(g) for g in c.gravity),
+                                                  c.eps, self.bc, cap_nodes=cap)
+            self._adj = torch.empty(cap, 4, dtype=torch.float32, device=box0.device)
+        return cc
+
+    def check(self, states) -> None:
+        """Raises if a substep's node box outgrew the compact grid slots (that substep was skipped)."""
+        for st in states:
+            if st is not None and getattr(st, "box", None) is not None and int(st.box[0, 6]) != 0:
+                raise ops.NeumaError("MPMModel: the particles' node box outgrew the compact grid slot")
 
     def backward(self, statics: MPMStatics, state_curr: MPMState, state_next: MPMState, tape=None,
                  need: Sequence[bool] = (True,) * 5) -> None:
@@ -195,8 +244,17 @@ class MPMModel(object):
         gv2 = g["v"] if g["v"] is not None else zeros(pn.v)
         gC2 = g["C"] if g["C"] is not None else zeros(pn.C)
         gF2 = g["F"] if g["F"] is not None else zeros(pn.F)
-        outs = ops.mpm_substep_bwd(self._cconst(), pc.x, pc.v, pc.C, pc.F, pc.stress, statics.vol, statics.rho,
-                                   statics.clip_bound, statics.enabled, pn.v, gx2, gv2, gC2, gF2, need=need)
+        if getattr(state_curr, "grid", None) is not None:
+            # saved-grid path: clear the adjoint scatter target over the box, scatter, node pass, gather
+            c = self._cc_compact
+            outs = [torch.empty_like(t) if nd else None for t, nd in zip((pc.x, pc.v, pc.C, pc.F, pc.stress), need)]
+            ops.mpm_box_clear(c, state_curr.box[0], self._adj, None, None)
+            ops.mpm_rollout_bwd(c, pc.x, pc.v, pc.C, pc.F, pc.stress, statics.vol, statics.rho, statics.clip_bound,
+                                statics.enabled, pn.v, pn.C, gx2.contiguous(), gv2.contiguous(), gC2.contiguous(),
+                                gF2.contiguous(), state_curr.grid, self._adj, state_curr.box[0], *outs)
+        else:
+            outs = ops.mpm_substep_bwd(self._cconst(), pc.x, pc.v, pc.C, pc.F, pc.stress, statics.vol, statics.rho,
+                                       statics.clip_bound, statics.enabled, pn.v, gx2, gv2, gC2, gF2, need=need)
         pc.grad = dict(zip(("x", "v", "C", "F", "stress"), outs))
 
 
