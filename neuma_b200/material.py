@@ -68,7 +68,8 @@ class LinearLoRA(nn.Linear):
 
     def effective_weight(self) -> Tensor:
         if self.r > 0 and not self.merged:
-            return self.weight + (self.lora_B @ self.lora_A) * self.scaling
+            # W + scaling * B A (loralib.py:219-222 folded into the weight), ONE differentiable op
+            return torch.addmm(self.weight, self.lora_B, self.lora_A, alpha=self.scaling)
         return self.weight
 
     def forward(self, x: Tensor) -> Tensor:  # only used outside the fused path
