@@ -783,8 +783,17 @@ int neuma_raster_num_rendered(neuma_ctx* ctx, void* stream, int* out_host) {
   (void)stream;
   *out_host = 0;
   if (!ctx->raster) return 0;
+  RasterState* s = ctx->raster;
+  if (!s->num_pending) {
+    // no read-back in flight (the last forward was replayed from a CUDA graph, which cannot carry
+    // one): fetch the device-side count and the sticky overflow flag now
+    NEUMA_CUDA(ctx, cudaStreamSynchronize((cudaStream_t)stream));
+    NEUMA_CUDA(ctx, cudaMemcpy(s->h_num, s->d_num, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    NEUMA_CUDA(ctx, cudaEventRecord(s->num_ready, (cudaStream_t)stream));
+    s->num_pending = true;
+  }
   if (int r = absorb_count(ctx, true)) return r;       // the one place that waits for the count
-  *out_host = ctx->raster->num_rendered > 0 ? ctx->raster->num_rendered : 0;
+  *out_host = s->num_rendered > 0 ? s->num_rendered : 0;
   return 0;
 }
 

@@ -254,6 +254,15 @@ def raster_bwd(s: RasterSettingsC, means3D, shs, colors_precomp, opacities, cov6
     return g3, g2, gcov, gop, gcol
 
 
+def raster_check(like: torch.Tensor) -> int:
+    """Waits for the last forward's instance count and raises if a forward (eager or replayed from a
+    CUDA graph) produced more tile instances than the buffers hold.  Returns the count."""
+    ctx = _ctx(like)
+    n = C.c_int(0)
+    ctx.call("neuma_raster_num_rendered", _stream(like), C.byref(n))
+    return n.value
+
+
 def raster_binning(like: torch.Tensor, tiles: int):
     """Sorted instance keys / Gaussian ids / tile ranges of the last forward."""
     ctx = _ctx(like)

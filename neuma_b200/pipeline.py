@@ -404,9 +404,62 @@ class FusedFrame:
 
     def frame_fwd_bwd(self, gt: torch.Tensor, de_x_prev, k_prev, g_state_next=None, want_g0: bool = True,
                       gt_ready: Optional[torch.cuda.Event] = None):
-        """frame_forward + frame_backward.  Returns (loss, dL/d(state at frame start))."""
+        """frame_forward + frame_backward.  Returns (loss, dL/d(state at frame start)).
+        With CUDA graphs the WHOLE frame is two graph launches: [S substeps, particles -> Gaussians,
+        rasterizer forward] and [pixel loss, rasterizer backward, transpose binding, S-substep reverse
+        pass] -- the rasterizer has no host round trip, so it captures like everything else; the
+        ground-truth image is waited for (gt_ready) between the two."""
+        if self.use_graphs and self.frames == 1 and g_state_next is None and len(self.views) == 1:
+            return self._frame_graphed(gt, de_x_prev, k_prev, want_g0, gt_ready)
         loss, _ = self.frame_forward(gt, de_x_prev, k_prev, gt_ready)
         return loss, self.frame_backward(g_state_next, want_g0)
+
+    def _frame_a(self) -> None:
+        self._sim_forward(0)
+        means3D, cov = self.gaussians_at(self._s_de, self._s_k, 0)
+        image, radii = self._raster(self.views[0], means3D, cov)
+        self._fa = (means3D, cov, radii, image)
+
+    def _frame_b(self) -> None:
+        means3D, cov, radii, image = self._fa
+        loss, dimg = self._pixel_loss(image, self._s_gt, 1.0)
+        for dst in self.g[0]:
+            dst.zero_()
+        g3 = self._raster_bwd(self.views[0], means3D, cov, radii, dimg)
+        b = self.bind
+        ops.gaussians_to_particles(b.rowptr, b.col, b.w, self.inv if self.sort else None, g3, self._size_h,
+                                   self.g[0][0])
+        self._sim_backward(0)
+        self._s_loss = loss
+
+    def _frame_graphed(self, gt, de_x_prev, k_prev, want_g0, gt_ready):
+        if getattr(self, "_fg", None) is None:
+            self._s_gt, self._s_de, self._s_k = torch.empty_like(gt), torch.empty_like(de_x_prev), torch.empty_like(k_prev)
+            self._s_gt.copy_(gt)
+            self._s_de.copy_(de_x_prev)
+            self._s_k.copy_(k_prev)
+            keep = [t.clone() for t in self.gWe + self.gWp + [self.gWe_part, self.gWp_part]]
+            self._frame_a()                       # eager warm-up: sizes the library's workspaces
+            self._frame_b()
+            torch.cuda.synchronize(self.dev)
+            ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(ga):
+                self._frame_a()
+            with torch.cuda.graph(gb, pool=ga.pool()):
+                self._frame_b()
+            for dst, src in zip(self.gWe + self.gWp + [self.gWe_part, self.gWp_part], keep):
+                dst.copy_(src)
+            self._fg = (ga, gb)
+        self._s_de.copy_(de_x_prev)
+        self._s_k.copy_(k_prev)
+        self._fg[0].replay()
+        if gt_ready is not None:
+            torch.cuda.current_stream(self.dev).wait_event(gt_ready)
+        self._s_gt.copy_(gt)
+        self._fg[1].replay()
+        self._render_saved = self._fa[:3] + (0,)
+        g0 = [self._to_caller(t) for t in self.g[0]] if want_g0 else None
+        return self._s_loss, g0
 
     # ------------------------------------------------------------------ the whole rollout of an epoch
     def rollout_fwd_bwd(self, gts, weights=None, de_x_prev=None, k_prev=None, want_g0: bool = True):
