@@ -1037,17 +1037,18 @@ svd3_bwd_kernel(int n, const float* __restrict__ U, const float* __restrict__ si
 }
 
 // gW += sum over the CTA slots of the partial buffer; the slots are zeroed for the next frame.
-// Block = 32 consecutive elements x 8 slot lanes (independent loads in flight), smem tree at the end.
-__global__ void __launch_bounds__(256)
+// Block = 32 consecutive elements x 32 slot lanes: every thread sums <= 5 slots (independent loads
+// in flight), shared-memory tree at the end (the round-1 shape, 8 slot lanes, took 52 us for 3.3 MB).
+__global__ void __launch_bounds__(1024)
 reduce_partials_kernel(int slots, float* __restrict__ part, float* __restrict__ gW0,
                        float* __restrict__ gW1, float* __restrict__ gW2) {
-  __shared__ float red[8][32];
+  __shared__ float red[32][33];
   const int lane = threadIdx.x & 31, sl = threadIdx.x >> 5;
   const int e = blockIdx.x * 32 + lane;
   float acc = 0.f;
   if (e < GW_FLOATS) {
-#pragma unroll 4
-    for (int sidx = sl; sidx < slots; sidx += 8) {
+#pragma unroll 5
+    for (int sidx = sl; sidx < slots; sidx += 32) {
       float* q = part + (size_t)sidx * GW_FLOATS + e;
       acc += *q;
       *q = 0.f;
@@ -1057,7 +1058,7 @@ reduce_partials_kernel(int slots, float* __restrict__ part, float* __restrict__ 
   __syncthreads();
   if (sl == 0 && e < GW_FLOATS) {
 #pragma unroll
-    for (int i = 1; i < 8; ++i) acc += red[i][lane];
+    for (int i = 1; i < 32; ++i) acc += red[i][lane];
     if (e < GW_OFF0) gW1[e] += acc;
     else if (e < GW_OFF2) gW0[e - GW_OFF0] += acc;
     else gW2[e - GW_OFF2] += acc;
@@ -1265,7 +1266,7 @@ int neuma_constitutive_reduce_partials(neuma_ctx* ctx, int hidden, float* gWpart
   if (int r = check_args(ctx, 0, hidden)) return r;
   if (!gWpart || !gW0 || !gW1 || !gW2)
     return neuma_fail_msg(ctx, "neuma_constitutive_reduce_partials: NULL argument");
-  reduce_partials_kernel<<<(GW_FLOATS + 31) / 32, 256, 0, (cudaStream_t)stream>>>(ctx->num_sms, gWpart,
+  reduce_partials_kernel<<<(GW_FLOATS + 31) / 32, 1024, 0, (cudaStream_t)stream>>>(ctx->num_sms, gWpart,
                                                                                  gW0, gW1, gW2);
   NEUMA_LAUNCH_CHECK(ctx, "reduce_partials_kernel");
   return 0;
