@@ -187,23 +187,41 @@ __device__ __forceinline__ void p2g_particle(const neuma_mpm_const& c, const Gri
 #pragma unroll
   for (int i = 0; i < 9; ++i) A[i] = k * stress9[i] + p_mass * C[9 * p + i];
   const float pv[3] = {p_mass * v[3 * p], p_mass * v[3 * p + 1], p_mass * v[3 * p + 2]};
+  // mv_n += w (m v + affine dpos_n), dpos_n = (o_n - f) dx with integer offsets o_n: the bracket is
+  // Z_n = Z0 + As o_n (As = dx affine, Z0 = m v - As f), built up along the unrolled loops by adding
+  // matrix columns -- 3 adds per visit instead of a 3x3 matrix-vector product
+  float As[9], Z0[3];
 #pragma unroll
-  for (int i = 0; i < 3; ++i)
+  for (int a = 0; a < 3; ++a) {
+    float af = 0.f;
 #pragma unroll
-    for (int j = 0; j < 3; ++j)
+    for (int b = 0; b < 3; ++b) {
+      As[3 * a + b] = c.dx * A[3 * a + b];
+      af += As[3 * a + b] * s.f[b];
+    }
+    Z0[a] = pv[a] - af;
+  }
 #pragma unroll
-      for (int kk = 0; kk < 3; ++kk) {
+  for (int kk = 0; kk < 3; ++kk) {
+    float Zz[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) Zz[a] = Z0[a] + (float)kk * As[3 * a + 2];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      float Zy[3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) Zy[a] = Zz[a] + (float)j * As[3 * a + 1];
+      const float wjk = s.w[1][j] * s.w[2][kk];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
         const int ix = s.b[0] + i, iy = s.b[1] + j, iz = s.b[2] + kk;
         if (!node_in_range(gm, ix, iy, iz)) continue;
-        const float d0 = ((float)i - s.f[0]) * c.dx;
-        const float d1 = ((float)j - s.f[1]) * c.dx;
-        const float d2 = ((float)kk - s.f[2]) * c.dx;
-        const float w = s.w[0][i] * s.w[1][j] * s.w[2][kk];
-        const float m0 = w * (pv[0] + (A[0] * d0 + A[1] * d1 + A[2] * d2));
-        const float m1 = w * (pv[1] + (A[3] * d0 + A[4] * d1 + A[5] * d2));
-        const float m2 = w * (pv[2] + (A[6] * d0 + A[7] * d1 + A[8] * d2));
-        red_add_f4(grid + node_index(gm, ix, iy, iz), m0, m1, m2, w * p_mass);
+        const float w = s.w[0][i] * wjk;
+        red_add_f4(grid + node_index(gm, ix, iy, iz), w * (Zy[0] + (float)i * As[0]), w * (Zy[1] + (float)i * As[3]),
+                   w * (Zy[2] + (float)i * As[6]), w * p_mass);
       }
+    }
+  }
 }
 
 // ---- G2P: one particle (mpm.py:432-498).  LAZY: the grid holds (mv, m) and grid_op is
@@ -323,24 +341,39 @@ __device__ __forceinline__ void g2p_adjoint_scatter(const neuma_mpm_const& c, co
                                                     float4* __restrict__ gadj) {
   const Stencil s = make_stencil(x[3 * p], x[3 * p + 1], x[3 * p + 2], c.inv_dx);
   const float k4 = 4.0f * c.inv_dx * c.inv_dx;
+  // dL/dv_n += w (gvt + k4 gCt dpos_n) = w U_n,  U_n = U0 + Gs o_n  (integer offsets, see p2g_particle)
+  float Gs[9], U0[3];
 #pragma unroll
-  for (int kk = 0; kk < 3; ++kk)
+  for (int a = 0; a < 3; ++a) {
+    float cf = 0.f;
 #pragma unroll
-    for (int j = 0; j < 3; ++j)
+    for (int b = 0; b < 3; ++b) {
+      Gs[3 * a + b] = (k4 * c.dx) * g.gCt[3 * a + b];
+      cf += Gs[3 * a + b] * s.f[b];
+    }
+    U0[a] = g.gvt[a] - cf;
+  }
+#pragma unroll
+  for (int kk = 0; kk < 3; ++kk) {
+    float Uz[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) Uz[a] = U0[a] + (float)kk * Gs[3 * a + 2];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      float Uy[3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) Uy[a] = Uz[a] + (float)j * Gs[3 * a + 1];
+      const float wjk = s.w[1][j] * s.w[2][kk];
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
         const int ix = s.b[0] + i, iy = s.b[1] + j, iz = s.b[2] + kk;
         if (!node_in_range(gm, ix, iy, iz)) continue;
-        const float d[3] = {((float)i - s.f[0]) * c.dx, ((float)j - s.f[1]) * c.dx,
-                            ((float)kk - s.f[2]) * c.dx};
-        const float w = s.w[0][i] * s.w[1][j] * s.w[2][kk];
-        float o[3];
-#pragma unroll
-        for (int a = 0; a < 3; ++a)
-          o[a] = w * (g.gvt[a] + k4 * (g.gCt[3 * a] * d[0] + g.gCt[3 * a + 1] * d[1] +
-                                       g.gCt[3 * a + 2] * d[2]));
-        red_add_f4(gadj + node_index(gm, ix, iy, iz), o[0], o[1], o[2], 0.0f);
+        const float w = s.w[0][i] * wjk;
+        red_add_f4(gadj + node_index(gm, ix, iy, iz), w * (Uy[0] + (float)i * Gs[0]), w * (Uy[1] + (float)i * Gs[3]),
+                   w * (Uy[2] + (float)i * Gs[6]), 0.0f);
       }
+    }
+  }
 }
 
 // ---- backward pass 3, one particle: gather its 27 nodes and accumulate adj(G2P) (the terms
