@@ -395,6 +395,9 @@ def run_gpu(args):
     if not args.no_dropin:
         line["dropin"] = dropin_measure(wl, dev, (x0, v0, C0, F0))
         line["dropin_frames_per_s"] = line["dropin"]["frames_per_s"]
+        # + ONE extra line in the caller: `elasticity.cache_merged = plasticity.cache_merged = True`
+        line["dropin_cached_merge_frames_per_s"] = dropin_measure(wl, dev, (x0, v0, C0, F0),
+                                                                   cache_merged=True)["frames_per_s"]
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_sample(wl, x0.cpu(), v0.cpu(), C0.cpu(), F0.cpu())
     print(json.dumps(line))
@@ -403,7 +406,7 @@ def run_gpu(args):
 
 
 # --------------------------------------------------------------------------- drop-in (Level-1) path
-def dropin_measure(wl, dev, state0, steps: int = 5, warmup: int = 2) -> dict:
+def dropin_measure(wl, dev, state0, steps: int = 5, warmup: int = 2, cache_merged: bool = False) -> dict:
     """The SAME frame through the reference-shaped classes with autograd, exactly as finetune.py's hot
     loop calls them after the import swap of INTEGRATION.md (elasticity -> MPMCacheDiffSim ->
     plasticity per substep, compute_bindings_*, diff_rasterization, l2_loss, loss.backward()): what a
@@ -432,6 +435,7 @@ def dropin_measure(wl, dev, state0, steps: int = 5, warmup: int = 2) -> dict:
                            if k.startswith(f"param_{tag}.")})
         m.to(dev)
         m.freeze_all_except_lora()
+        m.cache_merged = cache_merged      # opt-in: one shared LoRA-merge node per rollout (material.py)
         mods.append(m)
     elasticity, plasticity = mods
 

@@ -150,6 +150,7 @@ class _InvariantFullMeta(nn.Module):
 
     # ---- LoRA management (meta.py:185-194, loralib.py:13-81)
     def init_lora_layers(self, r: int, lora_alpha: int = 1):
+        self._weff = None
         for block in list(self.layers) + [self.final_layer]:
             lin = block.fc
             if isinstance(lin, LinearLoRA):
@@ -172,8 +173,36 @@ class _InvariantFullMeta(nn.Module):
     # forward, as the reference does (loralib.py:216-224) -- three tiny matmuls.  (Round 1 cached
     # it per parameter version, which broke two forward+backward rounds without an optimizer step
     # and went stale under weight.data.copy_().)
+    # Opt-in (`module.cache_merged = True`): within ONE rollout the 2 x S forward calls see the same
+    # parameters, so the merged weights -- and their autograd node -- can be shared: autograd then sums
+    # dL/dW_eff over the calls and runs the LoRA un-merge once instead of 2 x S times (15 small launches
+    # per call otherwise).  The shared node is dropped as soon as a backward reaches it (tensor hook),
+    # so a second forward+backward round without an optimizer step rebuilds it; it is keyed on the
+    # parameters' versions.  NOT seen: writes through `.data` between two forwards of the same rollout
+    # (call invalidate_merged()); the reference re-merges on every forward, hence off by default.
+    cache_merged: bool = False
+
+    def invalidate_merged(self) -> None:
+        self._weff = None
+
     def effective_weights(self):
-        return [b.effective_weight() for b in list(self.layers) + [self.final_layer]]
+        blocks = list(self.layers) + [self.final_layer]
+        if not self.cache_merged:
+            return [b.effective_weight() for b in blocks]
+        key = tuple((p.data_ptr(), p._version, p.requires_grad) for p in self.parameters()) + \
+              (torch.is_grad_enabled(), tuple(getattr(b.fc, "merged", False) for b in blocks))
+        cached = getattr(self, "_weff", None)
+        if cached is None or cached[0] != key:
+            ws = [b.effective_weight() for b in blocks]
+
+            def _drop(grad, m=self):
+                m._weff = None
+                return None
+            for w in ws:
+                if w.requires_grad and not w.is_leaf:
+                    w.register_hook(_drop)
+            cached = self._weff = (key, ws)
+        return cached[1]
 
     def _kind(self) -> int:
         return self.KIND

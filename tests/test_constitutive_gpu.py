@@ -160,7 +160,8 @@ def test_staged_and_partials_paths_match_atomics_path(cuda_dev, n):
     assert float(part.abs().max()) == 0.0                  # slots are zeroed by the reduce
 
 
-def test_lora_two_rounds_without_optimizer_step(cuda_dev):
+@pytest.mark.parametrize("cached", [False, True])
+def test_lora_two_rounds_without_optimizer_step(cuda_dev, cached):
     """two forward+backward rounds with LoRA and no optimizer.step() in between (gradient
     accumulation, a repeated loss evaluation) must work, and weight.data.copy_() must be seen --
     the reference rebuilds the LoRA product on every forward (loralib.py:216-224)."""
@@ -170,9 +171,13 @@ def test_lora_two_rounds_without_optimizer_step(cuda_dev):
     m = InvariantFullMetaElasticity(cfg).to(cuda_dev)
     m.init_lora_layers(r=16, lora_alpha=16)
     m.freeze_all_except_lora()
+    m.cache_merged = cached            # opt-in shared merge node: must survive the same flows
     for blk in list(m.layers) + [m.final_layer]:
         torch.nn.init.normal_(blk.fc.lora_B, std=0.05)
     F = (torch.eye(3) + 0.05 * torch.randn(300, 3, 3)).to(cuda_dev)
+    (m(F).square().sum() + m(0.5 * F + 0.5 * torch.eye(3, device=cuda_dev)).square().sum()).backward()   # two uses, one backward
+    for p in m.parameters():
+        p.grad = None
     m(F).square().sum().backward()
     g1 = [p.grad.clone() for p in m.parameters() if p.requires_grad]
     m(F).square().sum().backward()                                   # accumulates: no "backward twice" error
@@ -181,4 +186,6 @@ def test_lora_two_rounds_without_optimizer_step(cuda_dev):
     y0 = m(F).detach().clone()
     with torch.no_grad():
         m.layers[0].fc.weight.data.copy_(0.5 * m.layers[0].fc.weight.data)   # does not bump _version
+    if cached:
+        m.invalidate_merged()          # the documented limitation of the opt-in cache
     assert (m(F).detach() - y0).abs().max() > 1e-6
