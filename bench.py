@@ -485,7 +485,7 @@ def dropin_measure(wl, dev, state0, steps: int = 5, warmup: int = 2, cache_merge
     b.synchronize()
     ms = a.elapsed_time(b) / steps
     model.check(sim.curr_states)
-    return {"frames_per_s": 1000.0 / ms, "ms_per_frame": ms, "loss": float(loss), "steps": steps,
+    return {"frames_per_s": 1000.0 / ms, "ms_per_frame": ms, "loss": float(loss.detach()), "steps": steps,
             "api": "neuma_b200.sim.MPMCacheDiffSim + material.InvariantFullMeta* (LoRA r16, autograd) + glue."
                    "diff_rasterization: the reference's finetune.py loop with the import swap only"}
 

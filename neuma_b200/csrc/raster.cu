@@ -255,6 +255,7 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+template <bool NEED_OP>
 __global__ void __launch_bounds__(BLOCK)
 render_bwd_kernel(Cam cam, const uint2* __restrict__ ranges, const uint32_t* __restrict__ plist,
                   const float2* __restrict__ xy, const float* __restrict__ rgb,
@@ -348,21 +349,37 @@ render_bwd_kernel(Cam cam, const uint2* __restrict__ ranges, const uint32_t* __r
           }
         }
       }
-      // one atomic per warp per Gaussian instead of one per pixel
+      // one set of atomics per warp per Gaussian instead of one per pixel.  The eight sums NeuMA needs
+      // (dL/dmean2D.xy, dL/dconic.abc, dL/drgb) are reduced TOGETHER by a transposing butterfly: every
+      // step halves the values a lane carries (4 + 2 + 1 shuffles), two more finish the single survivor --
+      // 9 shuffles instead of 8 x 5 -- and leave value k summed in the lanes with bits (4,3,2) = k, so
+      // eight lanes issue one scalar atomic each, in parallel.  dL/dopacity is only reduced on request.
       if (__any_sync(0xffffffffu, active)) {
-        g_mx = warp_sum(g_mx); g_my = warp_sum(g_my);
-        g_ca = warp_sum(g_ca); g_cb = warp_sum(g_cb); g_cc = warp_sum(g_cc);
-        g_op = warp_sum(g_op);
-        g_col[0] = warp_sum(g_col[0]); g_col[1] = warp_sum(g_col[1]); g_col[2] = warp_sum(g_col[2]);
-        if (lane == 0) {
-          const uint32_t id = s_id[j];
-          atomicAdd(dmean2d + 3 * id, g_mx);
-          atomicAdd(dmean2d + 3 * id + 1, g_my);
-          red_add_f4(dconic + id, g_ca, g_cb, g_cc, g_op);
-          atomicAdd(dcolor + 3 * id, g_col[0]);
-          atomicAdd(dcolor + 3 * id + 1, g_col[1]);
-          atomicAdd(dcolor + 3 * id + 2, g_col[2]);
+        const float v[8] = {g_mx, g_my, g_ca, g_cb, g_cc, g_col[0], g_col[1], g_col[2]};
+        const bool h1 = lane & 16, h2 = lane & 8, h3 = lane & 4;
+        float w4[4], w2[2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float send = h1 ? v[i] : v[i + 4], keep = h1 ? v[i + 4] : v[i];
+          w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
         }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const float send = h2 ? w4[i] : w4[i + 2], keep = h2 ? w4[i + 2] : w4[i];
+          w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+        float t = (h3 ? w2[1] : w2[0]) + __shfl_xor_sync(0xffffffffu, h3 ? w2[0] : w2[1], 4);
+        t += __shfl_xor_sync(0xffffffffu, t, 2);
+        t += __shfl_xor_sync(0xffffffffu, t, 1);
+        if (NEED_OP) g_op = warp_sum(g_op);
+        const uint32_t id = s_id[j];
+        if ((lane & 3) == 0) {
+          const int k = lane >> 2;   // which of the eight sums this lane holds
+          float* dst = k < 2 ? dmean2d + 3 * id + k
+                             : (k < 5 ? reinterpret_cast<float*>(dconic + id) + (k - 2) : dcolor + 3 * id + (k - 5));
+          atomicAdd(dst, t);
+        }
+        if (NEED_OP && lane == 1) atomicAdd(reinterpret_cast<float*>(dconic + id) + 3, g_op);
       }
     }
   }
@@ -734,9 +751,12 @@ int neuma_raster_bwd(neuma_ctx* ctx, const neuma_raster_settings* set, int K, in
   NEUMA_CUDA(ctx, cudaMemsetAsync(s->dconic, 0, (size_t)K * sizeof(float4), st));
   NEUMA_CUDA(ctx, cudaMemsetAsync(s->dcolor, 0, (size_t)K * 3 * sizeof(float), st));
   if (L > 0) {
-    render_bwd_kernel<<<dim3(cam.tiles_x, cam.tiles_y), dim3(BX, BY), 0, st>>>(
-        cam, ranges, plist, xy, rgb, conic_o, final_T, n_contrib, dL_dimage, dL_dmeans2D, s->dconic,
-        s->dcolor);
+    if (dL_dopacity)
+      render_bwd_kernel<true><<<dim3(cam.tiles_x, cam.tiles_y), dim3(BX, BY), 0, st>>>(
+          cam, ranges, plist, xy, rgb, conic_o, final_T, n_contrib, dL_dimage, dL_dmeans2D, s->dconic, s->dcolor);
+    else
+      render_bwd_kernel<false><<<dim3(cam.tiles_x, cam.tiles_y), dim3(BX, BY), 0, st>>>(
+          cam, ranges, plist, xy, rgb, conic_o, final_T, n_contrib, dL_dimage, dL_dmeans2D, s->dconic, s->dcolor);
     NEUMA_LAUNCH_CHECK(ctx, "render_bwd_kernel");
   }
   preprocess_bwd_kernel<<<(K + 255) / 256, 256, 0, st>>>(
