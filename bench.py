@@ -164,7 +164,7 @@ def run_gpu(args):
     x0, v0, C0, F0 = [t.clone() for t in pre.sim_forward()]
     del pre
     eng = FusedFrame(n, cc, statics, We, Wp, wl["w"]["alpha"], S, dev, bind=bind, gaussians=gs, settings=settings,
-                     fuse=not args.no_fuse)
+                     fuse=args.fuse)
     eng.load_state(x0, v0, C0, F0)
     k_prev = g["xyz"].to(dev)
     de_x_prev = d["x"].clone()
@@ -173,7 +173,7 @@ def run_gpu(args):
 
     # launches per frame: count one eager (un-graphed) frame with the library's own counter
     eager = FusedFrame(n, cc, statics, We, Wp, wl["w"]["alpha"], S, dev, bind=bind, gaussians=gs,
-                       settings=settings, use_graphs=False, fuse=not args.no_fuse)
+                       settings=settings, use_graphs=False, fuse=args.fuse)
     eager.load_state(x0, v0, C0, F0)
     l0 = ctx.launches
     eager.frame_fwd_bwd(gt, de_x_prev, k_prev)
@@ -702,7 +702,10 @@ def main():
     ap.add_argument("--workload", default=WORKLOAD, choices=["bouncyball-50k-64", "jellyduck-100k-128", "claycat-200k-128"],
                     help="parity-test configs of BASELINE.json for the record; the headline is jellyduck-100k-128")
     ap.add_argument("--no-fuse", action="store_true",
-                    help="A/B: P2G / adjoint scatter as their own kernels instead of inside the constitutive epilogues")
+                    help="A/B: every MPM stage its own kernel (same as --fuse none)")
+    ap.add_argument("--fuse", default="full", choices=["full", "epilogue", "none"],
+                    help="A/B: full = 3 kernels per substep each way (default); epilogue = only P2G / the adjoint "
+                         "scatter ride in the constitutive kernels; none = every stage its own kernel")
     ap.add_argument("--no-dropin", action="store_true", help="skip the drop-in (autograd classes) measurement")
     ap.add_argument("--no-slab", action="store_true", help="skip the Z-slab (config 5) section of the line")
     ap.add_argument("--slab-steps", type=int, default=5, help="timed frames of the Z-slab section")
@@ -712,6 +715,7 @@ def main():
     ap.add_argument("--slab", action="store_true",
                     help="BASELINE config 5: 1M particles / 256^3 MPM fwd+bwd, Z-slab sharded over the ranks")
     args = ap.parse_args()
+    args.fuse = False if (args.no_fuse or args.fuse == "none") else args.fuse
     WORKLOAD = args.workload
     if WORKLOAD.startswith("claycat"):       # plasticine_0300 weights
         GOLD = os.path.join(ROOT, "tests", "golden", "material_plasticine.npz")

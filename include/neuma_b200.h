@@ -190,8 +190,14 @@ int neuma_mpm_p2g_to(neuma_ctx* ctx, const neuma_mpm_const* c, int n, const floa
                      float* grid, void* stream);
 /* grid_op_* (mpm.py:373-429) over the box, in place: (mv, m) -> (v, m); components zeroed
  * by the wall BC are stored as -0.0f.  adj_to_clear (may be NULL) is zeroed over the box. */
-int neuma_mpm_grid_op_box(neuma_ctx* ctx, const neuma_mpm_const* c, const int32_t* box, float* grid,
+int neuma_mpm_grid_op_box(neuma_ctx* ctx, const neuma_mpm_const* c, int32_t* box, float* grid,
                           float* adj_to_clear, void* stream);
+/* the same, and prepares the NEXT substep's slot so that no clear kernel sits between this substep's
+ * G2P and the next P2G: next_grid (may be NULL) is zeroed over this box dilated by one node (the
+ * next box lies inside unless a particle crossed more than one cell in the substep -- the fused
+ * neuma_constitutive_fwd_g2p raises box_next[6] then), box_reset (may be NULL) is set to "empty". */
+int neuma_mpm_grid_op_next(neuma_ctx* ctx, const neuma_mpm_const* c, int32_t* box, float* grid, float* adj_to_clear,
+                           float* next_grid, int32_t* box_reset, void* stream);
 /* g2p (mpm.py:432-498) from a (v, m) grid; box_next (may be NULL; must hold the empty box
  * or a partial reduction) receives the box of the nodes the NEW positions touch */
 int neuma_mpm_g2p_from(neuma_ctx* ctx, const neuma_mpm_const* c, int n, const float* x,
@@ -231,6 +237,10 @@ int neuma_mpm_bwd_node_gather(neuma_ctx* ctx, const neuma_mpm_const* c, int n, c
                               const float* gx2, const float* gv2, const float* gC2, const float* gF2,
                               const float* grid_v, float* adj, const int32_t* box, float* gx,
                               float* gv, float* gC, float* gF, float* gstress, void* stream);
+/* the node pass alone (adjoint of grid_op over the box, in place on adj); the gather that follows it is
+ * either neuma_mpm_bwd_node_gather's second kernel or neuma_constitutive_bwd_gather */
+int neuma_mpm_bwd_node(neuma_ctx* ctx, const neuma_mpm_const* c, const float* grid_v, float* adj, const int32_t* box,
+                       void* stream);
 /* dst += src over `nodes` packed float4 nodes: the receiving side of the Z-slab halo exchange
  * (a slab's overlap planes are one contiguous block in the plane-major layout) */
 int neuma_mpm_planes_add(neuma_ctx* ctx, float* dst, const float* src, size_t nodes, void* stream);
@@ -323,7 +333,14 @@ int neuma_constitutive_reduce_partials(neuma_ctx* ctx, int hidden, float* gWpart
  *   neuma_constitutive_bwd_scatter plasticity backward + the adjoint scatter of g2p into `adj`
  *                                  (= neuma_constitutive_bwd_partials(kind 1) followed by
  *                                  neuma_mpm_bwd_scatter with gF2 = the gFtrial just computed).
- * c / box / grid / adj as in the rollout entry points (c->sel_mode applies to the MPM part). */
+ *   neuma_constitutive_fwd_g2p     g2p (mpm.py:432-498) + plasticity of every particle: the thread gathers
+ *                                  x', v', C', F_trial (all written, as neuma_mpm_g2p_from does, box_next
+ *                                  included) and maps F_trial to F_out = F[s+1] -- finetune.py:363-364;
+ *   neuma_constitutive_bwd_gather  the adjoint gather of the substep (neuma_mpm_bwd_gather_v) + the
+ *                                  elasticity backward that consumes its dL/dstress: writes gx, gv, gC,
+ *                                  gstress and the complete gF (MPM part + elasticity part).
+ * c / box / grid / adj as in the rollout entry points (c->sel_mode applies to the MPM part; the g2p /
+ * gather fusions need sel_mode 0). */
 int neuma_constitutive_fwd_p2g(neuma_ctx* ctx, int kind, int n, int hidden, const float* F, const void* staged,
                                float* stress, const neuma_mpm_const* c, const float* x, const float* v,
                                const float* C, const float* vol, const float* rho, const int32_t* enabled,
@@ -334,6 +351,17 @@ int neuma_constitutive_bwd_scatter(neuma_ctx* ctx, int n, int hidden, const floa
                                    const float* clip_bound, const int32_t* enabled, const float* v2,
                                    const float* gx2, const float* gv2, const float* gC2, const int32_t* box,
                                    float* adj, void* stream);
+int neuma_constitutive_fwd_g2p(neuma_ctx* ctx, int n, int hidden, const void* staged, float alpha, float* F_out,
+                               const neuma_mpm_const* c, const float* x, const float* F, const float* clip_bound,
+                               const int32_t* enabled, const int32_t* box, const float* grid, float* x2, float* v2,
+                               float* C2, float* Ftrial, int32_t* box_next, void* stream);
+int neuma_constitutive_bwd_gather(neuma_ctx* ctx, int kind, int n, int hidden, const void* staged, float* gWpart,
+                                  const neuma_mpm_const* c, const float* x, const float* v, const float* C,
+                                  const float* F, const float* stress, const float* vol, const float* rho,
+                                  const float* clip_bound, const int32_t* enabled, const float* v2, const float* C2,
+                                  const float* gx2, const float* gv2, const float* gC2, const float* gF2,
+                                  const int32_t* box, const float* grid, const float* adj, float* gx, float* gv,
+                                  float* gC, float* gF, float* gstress, void* stream);
 
 /* ---- particle -> Gaussian binding: modules/tune/utils.py:424-472 ------- */
 /* out[K,ncol] = B in[Np,ncol] (transpose=0) or out[Np,ncol] = B^T in[K,ncol]

@@ -11,7 +11,8 @@ import os
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libneuma_b200.so")
+# NEUMA_B200_LIB: another build of the same library (A/B tooling: tools/gather_variants.sh)
+LIB_PATH = os.environ.get("NEUMA_B200_LIB") or os.path.join(_HERE, "libneuma_b200.so")
 
 
 class MPMConstC(C.Structure):
@@ -79,6 +80,8 @@ SIGNATURES = {
     "neuma_mpm_box_clear": [_P, _CP, _P, _P, _P, _P, _P],
     "neuma_mpm_p2g_to": [_P, _CP, _I] + [_P] * 10,
     "neuma_mpm_grid_op_box": [_P, _CP, _P, _P, _P, _P],
+    "neuma_mpm_bwd_node": [_P, _CP, _P, _P, _P, _P],
+    "neuma_mpm_grid_op_next": [_P, _CP, _P, _P, _P, _P, _P, _P],
     "neuma_mpm_g2p_from": [_P, _CP, _I] + [_P] * 12,
     "neuma_mpm_rollout_fwd": [_P, _CP, _I] + [_P] * 18,
     "neuma_mpm_rollout_bwd": [_P, _CP, _I] + [_P] * 24,
@@ -103,6 +106,8 @@ SIGNATURES = {
     "neuma_constitutive_bwd_partials": [_P, _I, _I, _I, _P, _P, _F, _P, _P, _I, _P, _P],
     "neuma_constitutive_fwd_p2g": [_P, _I, _I, _I, _P, _P, _P, _CP] + [_P] * 9,
     "neuma_constitutive_bwd_scatter": [_P, _I, _I, _P, _P, _F, _P, _P, _P, _CP] + [_P] * 11,
+    "neuma_constitutive_fwd_g2p": [_P, _I, _I, _P, _F, _P, _CP] + [_P] * 12,
+    "neuma_constitutive_bwd_gather": [_P, _I, _I, _I, _P, _P, _CP] + [_P] * 24,
     "neuma_constitutive_reduce_partials": [_P, _I, _P, _P, _P, _P, _P],
     "neuma_bind_spmm": [_P, _I, _I, _P, _P, _P, _I, _P, _P, _I, _P],
     "neuma_particles_to_gaussians": [_P, _I] + [_P] * 15,

@@ -31,6 +31,7 @@ struct neuma_ctx {
   size_t wstage_bytes;
   RasterState* raster;
   int attrs_set;  // cudaFuncSetAttribute (opt-in shared memory) is per DEVICE: tracked per ctx
+  int rollout_attrs_set;
 };
 
 static inline int neuma_fail(neuma_ctx* ctx, const char* what, cudaError_t e) {

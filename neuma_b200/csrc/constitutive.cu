@@ -457,11 +457,69 @@ struct FusedScatter {
   float4* adj;
 };
 
+// forward, plasticity: G2P of the particle (mpm.py:432-498) right before its return mapping -- the
+// thread gathers its 27 nodes, writes x', v', C', F_trial (the backward needs them) and goes on
+// with F_trial; the gather's memory latency hides under the other pipelines' arithmetic.
+// grid == NULL: not fused.
+struct FusedG2P {
+  neuma_mpm_const c;
+  const float *x, *F, *clip;
+  const int32_t *enabled, *box;
+  const float4* grid;
+  float *x2, *v2, *C2, *F2;
+  int32_t* box_next;
+};
+// backward, elasticity: the adjoint gather of the MPM substep (mpm_rollout.cu::bwd_gather_v_kernel)
+// right before the elasticity backward that consumes its dL/dstress; grid == NULL: not fused.
+struct FusedGather {
+  neuma_mpm_const c;
+  const float *x, *v, *C, *F, *stress, *vol, *rho, *clip, *v2, *C2, *gx2, *gv2, *gC2, *gF2;
+  const int32_t *enabled, *box;
+  const float4 *grid, *adj;
+  float *gx, *gv, *gC, *gstress;
+};
+
+// node box of the next substep + Z-slab drift counter, from inside a tile pipeline (warp reductions
+// and global atomics; the stand-alone G2P kernel reduces through shared memory first)
+__device__ __forceinline__ void box_accumulate_warp(const neuma_mpm_const& c, bool active, const float px[3],
+                                                    const int32_t* __restrict__ box_cur, int32_t* __restrict__ box) {
+  int lo[3] = {INT_MAX, INT_MAX, INT_MAX}, hi[3] = {INT_MIN, INT_MIN, INT_MIN};
+  if (active) {
+    const int mn[3] = {0, 0, c.z_off}, mx[3] = {c.num_grids - 1, c.num_grids - 1, c.z_off + c.nz - 1};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const int b = base_node(px[a], c.inv_dx);
+      lo[a] = max(b, mn[a]);
+      hi[a] = min(b + 2, mx[a]);
+    }
+    const int bz = base_node(px[2], c.inv_dx);
+    const bool below = bz < c.z_off;
+    const bool above = bz + 2 > c.z_off + c.nz - 1 && c.z_off + c.nz < c.num_grids;
+    if (below || above) atomicAdd(&box[7], 1);
+    // neuma_mpm_grid_op_next cleared the next slot over THIS box dilated by one node
+    if (box_cur) {
+      bool out = false;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) out |= lo[a] < box_cur[a] - 1 || hi[a] > box_cur[3 + a] + 1;
+      if (out) box[6] = 1;
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const int l = __reduce_min_sync(0xffffffffu, lo[a]);
+    const int h = __reduce_max_sync(0xffffffffu, hi[a]);
+    if ((threadIdx.x & 31) == 0 && l <= h) {
+      atomicMin(&box[a], l);
+      atomicMax(&box[3 + a], h);
+    }
+  }
+}
+
 // ------------------------------------------------------------------ forward
 template <int RT>
 __global__ void __launch_bounds__(fwd_threads<RT>(), 1)
 constitutive_fwd_kernel(int kind, int n, const float* __restrict__ F, const uint8_t* __restrict__ staged,
-                        float alpha, float* __restrict__ out, const FusedP2G fp) {
+                        float alpha, float* __restrict__ out, const FusedP2G fp, const FusedG2P fg) {
   constexpr int NS = NS_FWD, NPIPE = NPIPE_FWD, PW = 4 * RT;  // PW = warps per pipeline
   using W = WImg<NS>;
   using P = PipeFwd<NS>;
@@ -528,8 +586,21 @@ constitutive_fwd_kernel(int kind, int n, const float* __restrict__ F, const uint
       const int pi = tile * TP + r;
       Mat3 kF, kR;
       if (owner) {
+        Mat3 Fin;
+        bool have_F = false;
+        if (fg.grid) {   // fused G2P: F (= F_trial of this substep) is produced here, not read
+          const bool act = pi < n && fg.enabled[pi] != 0;
+          float nx3[3] = {0.f, 0.f, 0.f};
+          if (act) {
+            g2p_particle<false>(fg.c, grid_map(fg.c, fg.box), pi, fg.x, fg.F, fg.clip, fg.grid, fg.x2, fg.v2, fg.C2,
+                                fg.F2, nx3, Fin.m);
+            have_F = true;
+          }
+          if (fg.box_next) box_accumulate_warp(fg.c, act, nx3, fg.box, fg.box_next);
+        }
+        if (!have_F) Fin = load_F_or_identity(F, pi, n);
         Kinematics k;
-        kinematics(load_F_or_identity(F, pi, n), kind != 2, k);
+        kinematics(Fin, kind != 2, k);
         kF = k.F;
         kR = k.R;
         float f[KF];
@@ -539,7 +610,7 @@ constitutive_fwd_kernel(int kind, int n, const float* __restrict__ F, const uint
         store_chunk<NS>(pm + P::OFF_FEAT, SMALL_SPLIT, 1, r, f + 8);
       }
       ps.publish_async();                                            // -> h1 = feat W0^T
-      if (owner) prefetch_row(F, pi + chains * TP, n);
+      if (owner && !fg.grid) prefetch_row(F, pi + chains * TP, n);
       ps.wait_done();
       gelu_phase<NS, false, RT>(tacc, pm + P::OFF_BIGA, r, half);
       ps.publish_async();                                            // -> h2 = a1 W1^T
@@ -581,7 +652,7 @@ __global__ void __launch_bounds__(bwd_threads<RT>(), 1)
 constitutive_bwd_kernel(int kind, int n, const float* __restrict__ F, const uint8_t* __restrict__ staged,
                         float alpha, const float* __restrict__ gout, float* __restrict__ gF,
                         float* __restrict__ gW0, float* __restrict__ gW1, float* __restrict__ gW2,
-                        float* __restrict__ gWpart, int accumulate_gF, const FusedScatter fs) {
+                        float* __restrict__ gWpart, int accumulate_gF, const FusedScatter fs, const FusedGather fa) {
   constexpr int NS = NS_BWD, NPIPE = NPIPE_BWD, PW = 4 * RT;  // PW = warps per pipeline
   using W = WImg<NS>;
   using P = PipeBwd<NS>;
@@ -682,6 +753,16 @@ constitutive_bwd_kernel(int kind, int n, const float* __restrict__ F, const uint
     for (int tile = p * gridDim.x + blockIdx.x; tile < tiles; tile += chains, first = false) {
       const int pi = tile * TP + r;
       const bool live = pi < n;
+      if (owner && fa.grid && live) {
+        // fused adjoint gather: writes dL/dx, dL/dv, dL/dC, the MPM part of dL/dF (into gF, which this
+        // kernel then accumulates onto) and dL/dstress (= this kernel's gout, read back below)
+        if (fa.enabled[pi] == 0)
+          zero_particle_grads(pi, fa.gx, fa.gv, fa.gC, gF, fa.gstress);
+        else
+          bwd_gather_particle<false, true>(fa.c, grid_map(fa.c, fa.box), pi, fa.x, fa.v, fa.C, fa.F, fa.stress, fa.vol,
+                                           fa.rho, fa.clip, fa.v2, fa.C2, fa.gx2, fa.gv2, fa.gC2, fa.gF2, fa.grid,
+                                           fa.adj, fa.gx, fa.gv, fa.gC, gF, fa.gstress);
+      }
       Kinematics k;
       if (owner) kinematics(load_F_or_identity(F, pi, n), kind != 2, k);
       PHASE(0);
@@ -712,7 +793,7 @@ constitutive_bwd_kernel(int kind, int n, const float* __restrict__ F, const uint
         umma::commit(dbar);
       }
       if (owner) {
-        prefetch_row(gout, pi, n);
+        if (!fa.grid) prefetch_row(gout, pi, n);
         prefetch_row(F, pi + chains * TP, n);
       }
       PHASE(1);
@@ -763,7 +844,13 @@ constitutive_bwd_kernel(int kind, int n, const float* __restrict__ F, const uint
           }
           const Mat3 X = head_to_sym(o);
           const Mat3 Pm = mat3_mul(kR, X);
-          const Mat3 G = mat3_load(gout + (size_t)pi * 9);
+          Mat3 G;
+          if (fa.grid) {  // written by this thread's fused gather above: read it back through L2
+#pragma unroll
+            for (int i = 0; i < 9; ++i) G.m[i] = __ldcg(fa.gstress + (size_t)pi * 9 + i);
+          } else {
+            G = mat3_load(gout + (size_t)pi * 9);
+          }
           Mat3 gP;  // out = P F^T (elastic)  |  out = F + alpha P (plastic)
           if (kind == 1) {
 #pragma unroll
@@ -1098,29 +1185,29 @@ int set_attrs(neuma_ctx* ctx) {
 
 // one place that picks the instantiation
 int launch_fwd(neuma_ctx* ctx, int kind, int n, const float* F, const void* staged, float alpha, float* out,
-               const FusedP2G& fp, cudaStream_t st) {
+               const FusedP2G& fp, const FusedG2P& fg, cudaStream_t st) {
   const int tiles = (n + TP - 1) / TP;
   const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
   if (row_threads() == 2)
     NEUMA_CUDA(ctx, neuma_launch(constitutive_fwd_kernel<2>, dim3(grid), dim3(fwd_threads<2>()), FWD_SMEM, st, kind, n,
-                                 F, (const uint8_t*)staged, alpha, out, fp));
+                                 F, (const uint8_t*)staged, alpha, out, fp, fg));
   else
     NEUMA_CUDA(ctx, neuma_launch(constitutive_fwd_kernel<1>, dim3(grid), dim3(fwd_threads<1>()), FWD_SMEM, st, kind, n,
-                                 F, (const uint8_t*)staged, alpha, out, fp));
+                                 F, (const uint8_t*)staged, alpha, out, fp, fg));
   NEUMA_LAUNCH_CHECK(ctx, "constitutive_fwd_kernel");
   return 0;
 }
 
 int launch_bwd(neuma_ctx* ctx, bool wgrad, int kind, int n, const float* F, const void* staged, float alpha,
                const float* gout, float* gF, float* gW0, float* gW1, float* gW2, float* gWpart, int accumulate_gF,
-               const FusedScatter& fs, cudaStream_t st) {
+               const FusedScatter& fs, const FusedGather& fa, cudaStream_t st) {
   const int tiles = (n + TP - 1) / TP;
   const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
   const uint8_t* sg = (const uint8_t*)staged;
 #define NEUMA_BWD(WG, RTV)                                                                                       \
   NEUMA_CUDA(ctx, neuma_launch(constitutive_bwd_kernel<WG, RTV>, dim3(grid), dim3(bwd_threads<RTV>()),            \
                                bwd_smem<RTV>(), st, kind, n, F, sg, alpha, gout, gF, gW0, gW1, gW2, gWpart,       \
-                               accumulate_gF, fs))
+                               accumulate_gF, fs, fa))
   if (row_threads() == 2) {
     if (wgrad) NEUMA_BWD(true, 2); else NEUMA_BWD(false, 2);
   } else {
@@ -1194,7 +1281,9 @@ int neuma_constitutive_fwd_staged(neuma_ctx* ctx, int kind, int n, int hidden, c
   if (int r = set_attrs(ctx)) return r;
   FusedP2G none;
   memset(&none, 0, sizeof(none));
-  return launch_fwd(ctx, kind, n, F, staged, alpha, out, none, (cudaStream_t)stream);
+  FusedG2P nog;
+  memset(&nog, 0, sizeof(nog));
+  return launch_fwd(ctx, kind, n, F, staged, alpha, out, none, nog, (cudaStream_t)stream);
 }
 
 int neuma_constitutive_fwd_p2g(neuma_ctx* ctx, int kind, int n, int hidden, const float* F, const void* staged,
@@ -1210,7 +1299,26 @@ int neuma_constitutive_fwd_p2g(neuma_ctx* ctx, int kind, int n, int hidden, cons
   if (n <= 0) return 0;
   if (int r = set_attrs(ctx)) return r;
   FusedP2G fp{*c, x, v, C, vol, rho, enabled, box, (float4*)grid};
-  return launch_fwd(ctx, kind, n, F, staged, 0.0f, stress, fp, (cudaStream_t)stream);
+  FusedG2P nog;
+  memset(&nog, 0, sizeof(nog));
+  return launch_fwd(ctx, kind, n, F, staged, 0.0f, stress, fp, nog, (cudaStream_t)stream);
+}
+
+int neuma_constitutive_fwd_g2p(neuma_ctx* ctx, int n, int hidden, const void* staged, float alpha, float* F_out,
+                               const neuma_mpm_const* c, const float* x, const float* F, const float* clip_bound,
+                               const int32_t* enabled, const int32_t* box, const float* grid, float* x2, float* v2,
+                               float* C2, float* Ftrial, int32_t* box_next, void* stream) {
+  if (int r = check_args(ctx, 1, hidden)) return r;
+  if (!c || !x || !F || !clip_bound || !enabled || !grid || !x2 || !v2 || !C2 || !Ftrial || !F_out)
+    return neuma_fail_msg(ctx, "neuma_constitutive_fwd_g2p: NULL argument");
+  if (c->sel_mode != 0) return neuma_fail_msg(ctx, "neuma_constitutive_fwd_g2p: sel_mode must be 0");
+  if (c->compact && !box) return neuma_fail_msg(ctx, "neuma_constitutive_fwd_g2p: a compact grid needs the box");
+  if (n <= 0) return 0;
+  if (int r = set_attrs(ctx)) return r;
+  FusedP2G nop;
+  memset(&nop, 0, sizeof(nop));
+  FusedG2P fg{*c, x, F, clip_bound, enabled, box, (const float4*)grid, x2, v2, C2, Ftrial, box_next};
+  return launch_fwd(ctx, 1, n, Ftrial, staged, alpha, F_out, nop, fg, (cudaStream_t)stream);
 }
 
 int neuma_constitutive_bwd_staged(neuma_ctx* ctx, int kind, int n, int hidden, const float* F,
@@ -1224,7 +1332,9 @@ int neuma_constitutive_bwd_staged(neuma_ctx* ctx, int kind, int n, int hidden, c
     return neuma_fail_msg(ctx, "neuma_constitutive_bwd: pass all of gW0,gW1,gW2 or none");
   FusedScatter none;
   memset(&none, 0, sizeof(none));
-  return launch_bwd(ctx, wgrad, kind, n, F, staged, alpha, gout, gF, gW0, gW1, gW2, nullptr, 0, none,
+  FusedGather noa;
+  memset(&noa, 0, sizeof(noa));
+  return launch_bwd(ctx, wgrad, kind, n, F, staged, alpha, gout, gF, gW0, gW1, gW2, nullptr, 0, none, noa,
                     (cudaStream_t)stream);
 }
 
@@ -1239,8 +1349,10 @@ int neuma_constitutive_bwd_partials(neuma_ctx* ctx, int kind, int n, int hidden,
   if (int r = set_attrs(ctx)) return r;
   FusedScatter none;
   memset(&none, 0, sizeof(none));
+  FusedGather noa;
+  memset(&noa, 0, sizeof(noa));
   return launch_bwd(ctx, true, kind, n, F, staged, alpha, gout, gF, nullptr, nullptr, nullptr, gWpart,
-                    accumulate_gF, none, (cudaStream_t)stream);
+                    accumulate_gF, none, noa, (cudaStream_t)stream);
 }
 
 int neuma_constitutive_bwd_scatter(neuma_ctx* ctx, int n, int hidden, const float* Ftrial, const void* staged,
@@ -1257,8 +1369,34 @@ int neuma_constitutive_bwd_scatter(neuma_ctx* ctx, int n, int hidden, const floa
   if (n <= 0) return 0;
   if (int r = set_attrs(ctx)) return r;
   FusedScatter fs{*c, x, F, clip_bound, v2, gx2, gv2, gC2, enabled, box, (float4*)adj};
+  FusedGather noa;
+  memset(&noa, 0, sizeof(noa));
   return launch_bwd(ctx, true, 1, n, Ftrial, staged, alpha, gout, gFtrial, nullptr, nullptr, nullptr, gWpart, 0,
-                    fs, (cudaStream_t)stream);
+                    fs, noa, (cudaStream_t)stream);
+}
+
+int neuma_constitutive_bwd_gather(neuma_ctx* ctx, int kind, int n, int hidden, const void* staged, float* gWpart,
+                                  const neuma_mpm_const* c, const float* x, const float* v, const float* C,
+                                  const float* F, const float* stress, const float* vol, const float* rho,
+                                  const float* clip_bound, const int32_t* enabled, const float* v2, const float* C2,
+                                  const float* gx2, const float* gv2, const float* gC2, const float* gF2,
+                                  const int32_t* box, const float* grid, const float* adj, float* gx, float* gv,
+                                  float* gC, float* gF, float* gstress, void* stream) {
+  if (int r = check_args(ctx, kind, hidden)) return r;
+  if (kind == 1) return neuma_fail_msg(ctx, "neuma_constitutive_bwd_gather: elasticity kinds only (0, 2)");
+  if (!gWpart || !c || !x || !v || !C || !F || !stress || !vol || !rho || !clip_bound || !enabled || !v2 || !C2 ||
+      !gx2 || !gv2 || !gC2 || !gF2 || !grid || !adj || !gx || !gv || !gC || !gF || !gstress)
+    return neuma_fail_msg(ctx, "neuma_constitutive_bwd_gather: NULL argument");
+  if (c->sel_mode != 0) return neuma_fail_msg(ctx, "neuma_constitutive_bwd_gather: sel_mode must be 0");
+  if (c->compact && !box) return neuma_fail_msg(ctx, "neuma_constitutive_bwd_gather: a compact grid needs the box");
+  if (n <= 0) return 0;
+  if (int r = set_attrs(ctx)) return r;
+  FusedScatter nos;
+  memset(&nos, 0, sizeof(nos));
+  FusedGather fa{*c, x, v, C, F, stress, vol, rho, clip_bound, v2, C2, gx2, gv2, gC2, gF2, enabled, box,
+                 (const float4*)grid, (const float4*)adj, gx, gv, gC, gstress};
+  return launch_bwd(ctx, true, kind, n, F, staged, 0.0f, gstress, gF, nullptr, nullptr, nullptr, gWpart, 1, nos, fa,
+                    (cudaStream_t)stream);
 }
 
 int neuma_constitutive_reduce_partials(neuma_ctx* ctx, int hidden, float* gWpart, float* gW0,

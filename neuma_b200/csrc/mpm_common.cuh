@@ -96,6 +96,73 @@ __device__ __forceinline__ bool node_in_range(const GridMap& m, int ix, int iy, 
 __device__ __forceinline__ size_t node_index(const GridMap& m, int ix, int iy, int iz) {
   return ((size_t)(iz - m.z0) * m.ny + (iy - m.y0)) * m.nx + (ix - m.x0);
 }
+// A valid index for ANY node: out-of-range coordinates are clamped to the nearest node of the map
+// (index 0 for an empty map).  The gathers load through it unconditionally and zero what they loaded
+// when !node_in_range -- a load behind a branch cannot be hoisted, and 27 of them in a row cost 27
+// serialized L2 round trips per warp (ncu: profiles/r03_gather_latency.txt).
+__device__ __forceinline__ size_t node_index_clamped(const GridMap& m, int ix, int iy, int iz) {
+  const int cx = min(max(ix - m.x0, 0), max(m.nx - 1, 0));
+  const int cy = min(max(iy - m.y0, 0), max(m.ny - 1, 0));
+  const int cz = min(max(iz - m.z0, 0), max(m.nz - 1, 0));
+  return ((size_t)cz * m.ny + cy) * m.nx + cx;
+}
+// A/B switch of the gathers' node loads (tools/gather_variants.sh; the default is what ships):
+//   0 = a load per visited node behind its range check, 1 = unconditional clamped loads,
+//   2 = 1 + the whole stencil prefetched to L1 first
+#ifndef NEUMA_GATHER_VARIANT
+#define NEUMA_GATHER_VARIANT 1
+#endif
+
+// The 27 node indices of a particle's stencil as 9 row bases + 3 x offsets (12 registers), each
+// clamped to the map, and the per-axis in-range bits.
+struct StencilIdx {
+  int row[9];    // [3 * kk + j]: index of (x0, b1 + j, b2 + kk), y / z clamped
+  int cx[3];     // clamped x offset of b0 + i
+  unsigned ok;   // bit i: x in range, bit 3 + j: y, bit 6 + kk: z
+  __device__ __forceinline__ bool in_range(int i, int j, int kk) const {
+    return ((ok >> i) & (ok >> (3 + j)) & (ok >> (6 + kk)) & 1u) != 0;
+  }
+  __device__ __forceinline__ int at(int i, int j, int kk) const { return row[3 * kk + j] + cx[i]; }
+};
+__device__ __forceinline__ StencilIdx make_stencil_idx(const GridMap& m, const int b[3]) {
+  StencilIdx si;
+  si.ok = 0;
+  int cy[3], cz[3];
+#pragma unroll
+  for (int t = 0; t < 3; ++t) {
+    const int rx = b[0] + t - m.x0, ry = b[1] + t - m.y0, rz = b[2] + t - m.z0;
+    si.ok |= ((unsigned)rx < (unsigned)m.nx ? 1u : 0u) << t;
+    si.ok |= ((unsigned)ry < (unsigned)m.ny ? 1u : 0u) << (3 + t);
+    si.ok |= ((unsigned)rz < (unsigned)m.nz ? 1u : 0u) << (6 + t);
+    si.cx[t] = min(max(rx, 0), max(m.nx - 1, 0));
+    cy[t] = min(max(ry, 0), max(m.ny - 1, 0));
+    cz[t] = min(max(rz, 0), max(m.nz - 1, 0));
+  }
+#pragma unroll
+  for (int kk = 0; kk < 3; ++kk)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) si.row[3 * kk + j] = (cz[kk] * m.ny + cy[j]) * m.nx;
+  return si;
+}
+// pull the 27 stencil nodes of a particle towards L1 in ONE round trip (a row's 3 nodes are 48
+// contiguous bytes: its two ends cover the one or two 128-byte lines it lies in).  The gathers are short
+// of registers and of warps (100 k particles are 21 warps per SM): the compiler issues their node loads
+// a few at a time and, without this, the warp pays a memory latency per group.
+__device__ __forceinline__ void prefetch_stencil(const StencilIdx& si, const float4* __restrict__ g0,
+                                                 const float4* __restrict__ g1) {
+#pragma unroll
+  for (int r = 0; r < 9; ++r) {
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(g0 + si.row[r] + si.cx[0]));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(g0 + si.row[r] + si.cx[2]));
+    if (g1) {
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(g1 + si.row[r] + si.cx[0]));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(g1 + si.row[r] + si.cx[2]));
+    }
+  }
+}
+__device__ __forceinline__ float4 select4(bool ok, const float4& q) {
+  return make_float4(ok ? q.x : 0.f, ok ? q.y : 0.f, ok ? q.z : 0.f, ok ? q.w : 0.f);
+}
 
 // ---- Z-slab overlap selection (neuma_mpm_const::sel_*): planes below sel_lo_end and from
 // sel_up_start on are shared with a neighbour rank.
@@ -225,28 +292,34 @@ __device__ __forceinline__ void p2g_particle(const neuma_mpm_const& c, const Gri
 }
 
 // ---- G2P: one particle (mpm.py:432-498).  LAZY: the grid holds (mv, m) and grid_op is
-// evaluated per gathered node; otherwise it holds v.  Writes x', v', C', F'; returns x' in nx3.
+// evaluated per gathered node; otherwise it holds v.  Writes x', v', C', F'; returns x' in nx3 and,
+// when Fret is given, F' in registers (the fused plasticity kernel goes on with it).
 template <bool LAZY>
 __device__ __forceinline__ void g2p_particle(const neuma_mpm_const& c, const GridMap& gm, int p,
                                              const float* __restrict__ x, const float* __restrict__ F,
                                              const float* __restrict__ clip,
                                              const float4* __restrict__ grid, float* __restrict__ x2,
                                              float* __restrict__ v2, float* __restrict__ C2,
-                                             float* __restrict__ F2, float nx3[3]) {
+                                             float* __restrict__ F2, float nx3[3], float* Fret = nullptr) {
   const float px[3] = {x[3 * p], x[3 * p + 1], x[3 * p + 2]};
   const Stencil s = make_stencil(px[0], px[1], px[2], c.inv_dx);
   float nv[3] = {0.f, 0.f, 0.f};
   float nC[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   const float k4 = 4.0f * c.inv_dx * c.inv_dx;
+  const StencilIdx si = make_stencil_idx(gm, s.b);
+  if (NEUMA_GATHER_VARIANT >= 2) prefetch_stencil(si, grid, nullptr);
 #pragma unroll
-  for (int kk = 0; kk < 3; ++kk)
+  for (int kk = 0; kk < 3; ++kk) {
 #pragma unroll
     for (int j = 0; j < 3; ++j)
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
         const int ix = s.b[0] + i, iy = s.b[1] + j, iz = s.b[2] + kk;
-        if (!node_in_range(gm, ix, iy, iz)) continue;
-        const float4 q = grid[node_index(gm, ix, iy, iz)];
+        const bool ok = si.in_range(i, j, kk);           // dropped visits contribute exact zeros
+#if NEUMA_GATHER_VARIANT == 0
+        if (!ok) continue;
+#endif
+        const float4 q = select4(ok, grid[si.at(i, j, kk)]);
         float gv[3];
         if (LAZY) {
           float pass[3], inv_m, vp[3];
@@ -256,7 +329,7 @@ __device__ __forceinline__ void g2p_particle(const neuma_mpm_const& c, const Gri
         }
         const float d[3] = {((float)i - s.f[0]) * c.dx, ((float)j - s.f[1]) * c.dx,
                             ((float)kk - s.f[2]) * c.dx};
-        const float w = s.w[0][i] * s.w[1][j] * s.w[2][kk];
+        const float w = ok ? s.w[0][i] * s.w[1][j] * s.w[2][kk] : 0.0f;
         const float w4 = k4 * w;
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
@@ -265,6 +338,7 @@ __device__ __forceinline__ void g2p_particle(const neuma_mpm_const& c, const Gri
           for (int b = 0; b < 3; ++b) nC[3 * a + b] += w4 * (gv[a] * d[b]);
         }
       }
+  }
   // F' = (I + dt C') F   (mpm.py:487)
   float Fo[9], Fn[9];
 #pragma unroll
@@ -292,6 +366,7 @@ __device__ __forceinline__ void g2p_particle(const neuma_mpm_const& c, const Gri
   for (int i = 0; i < 9; ++i) {
     C2[9 * p + i] = nC[i];
     F2[9 * p + i] = Fn[i];
+    if (Fret) Fret[i] = Fn[i];
   }
 }
 
@@ -392,9 +467,11 @@ __device__ __forceinline__ void bwd_gather_particle(
     const float* __restrict__ gF2, const float4* __restrict__ grid, const float4* __restrict__ gadj,
     float* __restrict__ gx, float* __restrict__ gv, float* __restrict__ gC, float* __restrict__ gF,
     float* __restrict__ gstress) {
+  const Stencil s = make_stencil(x[3 * p], x[3 * p + 1], x[3 * p + 2], c.inv_dx);
+  const StencilIdx si = make_stencil_idx(gm, s.b);
+  if (NEUMA_GATHER_VARIANT >= 2) prefetch_stencil(si, grid, gadj);
   const float p_vol = vol[p];
   const float p_mass = p_vol * rho[p];
-  const Stencil s = make_stencil(x[3 * p], x[3 * p + 1], x[3 * p + 2], c.inv_dx);
   const float ks = -c.dt * p_vol * 4.0f * c.inv_dx * c.inv_dx;
   const float k4 = 4.0f * c.inv_dx * c.inv_dx;
   float A[9];
@@ -449,10 +526,12 @@ __device__ __forceinline__ void bwd_gather_particle(
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
         const int ix = s.b[0] + i, iy = s.b[1] + j, iz = s.b[2] + kk;
-        if (!node_in_range(gm, ix, iy, iz)) continue;
-        const size_t ni = node_index(gm, ix, iy, iz);
-        const float4 q = grid[ni];
-        const float4 ga = gadj[ni];
+        const bool ok = si.in_range(i, j, kk);           // dropped visits contribute exact zeros
+#if NEUMA_GATHER_VARIANT == 0
+        if (!ok) continue;
+#endif
+        const float4 q = select4(ok, grid[si.at(i, j, kk)]);
+        const float4 ga = select4(ok, gadj[si.at(i, j, kk)]);
         float vn[3], gmv[3], gmn;
         if (LAZY) {
           float pass[3], inv_m, vp[3];
@@ -466,7 +545,7 @@ __device__ __forceinline__ void bwd_gather_particle(
           gmv[0] = ga.x; gmv[1] = ga.y; gmv[2] = ga.z;
           gmn = ga.w;
         }
-        const float w = s.w[0][i] * wjk;
+        const float w = ok ? s.w[0][i] * wjk : 0.0f;
         const float off[3] = {(float)i, (float)j, (float)kk};   // compile-time 0 / 1 / 2 after unrolling
         float gW = gmn * p_mass;
 #pragma unroll
@@ -482,6 +561,7 @@ __device__ __forceinline__ void bwd_gather_particle(
             if (need_C) Mv[3 * a + b] += off[b] * (w * vn[a]);
           }
         }
+        if (LAZY) gW = ok ? gW : 0.0f;   // (!LAZY: q = ga = 0 already makes it an exact zero)
         gw[0][i] += gW * wjk;
         gw[1][j] += gW * (s.w[0][i] * s.w[2][kk]);
         gw[2][kk] += gW * (s.w[0][i] * s.w[1][j]);
@@ -542,6 +622,39 @@ __device__ __forceinline__ void bwd_gather_particle(
         gF[9 * p + 3 * a + b] = finite_or_zero(acc);
       }
   }
+}
+
+// ---- coalesced row I/O.  The particle arrays are arrays of 3- or 9-float rows; a thread reading "its"
+// row makes every warp instruction touch 12 / 32 sectors (ncu on g2p_from_kernel: 18 sectors per load
+// request, 27 per store request -- the kernels were bound by L1 sector lookups, not by latency or
+// bandwidth).  A block copies the rows of its B consecutive particles between global and shared memory
+// with 128 contiguous bytes per warp instruction (4 sectors) and the per-particle code runs on the
+// shared copy (stride-K words with K odd: no bank conflicts).
+template <int K, int B>
+__device__ __forceinline__ void rows_load(float* __restrict__ sm, const float* __restrict__ g, int p0, int cnt) {
+  const float* __restrict__ src = g + (size_t)p0 * K;
+  const int nf = cnt * K;
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+    const int i = j * B + (int)threadIdx.x;
+    if (i < nf) sm[i] = src[i];
+  }
+}
+template <int K, int B>
+__device__ __forceinline__ void rows_store(float* __restrict__ g, const float* __restrict__ sm, int p0, int cnt) {
+  float* __restrict__ dst = g + (size_t)p0 * K;
+  const int nf = cnt * K;
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+    const int i = j * B + (int)threadIdx.x;
+    if (i < nf) dst[i] = sm[i];
+  }
+}
+// one thread's row (the fallback when only some particles of the block write)
+template <int K>
+__device__ __forceinline__ void row_store(float* __restrict__ g, const float* __restrict__ sm, int p, int t) {
+#pragma unroll
+  for (int j = 0; j < K; ++j) g[(size_t)p * K + j] = sm[t * K + j];
 }
 
 // disabled particles: the reference's kernels return early, no adjoint contribution

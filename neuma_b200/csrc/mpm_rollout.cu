@@ -217,12 +217,43 @@ p2g_tiled_kernel(neuma_mpm_const c, int n, const float* __restrict__ x, const fl
 
 // grid_op over the box, in place: (mv, m) -> (v, m); BC-zeroed components become -0.0f.
 // Optionally zeroes the same nodes of `adj` (the backward's scatter target).
+// next_grid != NULL: also prepares the NEXT substep's grid slot -- zeroes the window of this box
+// dilated by one node (the next box lies inside it unless a particle crosses more than a cell in one
+// substep, which the fused G2P flags in box_next[6]) -- and resets box_reset to "empty".  With that the
+// forward needs no separate clear kernel between G2P and the next P2G.
 __global__ void __launch_bounds__(256)
-grid_op_box_kernel(neuma_mpm_const c, const int32_t* __restrict__ box, float4* __restrict__ grid,
-                   float4* __restrict__ adj) {
+grid_op_box_kernel(neuma_mpm_const c, int32_t* __restrict__ box, float4* __restrict__ grid,
+                   float4* __restrict__ adj, float4* __restrict__ next_grid, int32_t* __restrict__ box_reset) {
   pdl_prologue();
+  if (box_reset && blockIdx.x == 0 && threadIdx.x < 8)
+    box_reset[threadIdx.x] = threadIdx.x < 3 ? INT_MAX : (threadIdx.x < 6 ? INT_MIN : 0);
+  if (c.compact && blockIdx.x == 0 && threadIdx.x == 0 && map_overflows(c, box_window(c, load_box(box))))
+    box[6] = 1;
   const BoxIter it = box_iter(c, box);
   const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (next_grid) {
+    Box d = load_box(box);
+    if (!box_empty(d)) {
+      const int mn[3] = {0, 0, c.z_off}, mx[3] = {c.num_grids - 1, c.num_grids - 1, c.z_off + c.nz - 1};
+#pragma unroll
+      for (int a = 0; a < 3; ++a) { d.lo[a] = max(d.lo[a] - 1, mn[a]); d.hi[a] = min(d.hi[a] + 1, mx[a]); }
+    }
+    const GridMap wd = box_window(c, d);
+    const GridMap md = c.compact ? wd : GridMap{0, 0, c.z_off, c.num_grids, c.num_grids, c.nz};
+    long long cnt = map_nodes(wd);
+    if (c.compact && cnt > (long long)c.cap_nodes) cnt = c.cap_nodes;   // the whole slot
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < cnt;
+         i += (long long)gridDim.x * blockDim.x) {
+      if (c.compact) {
+        next_grid[i] = z;
+      } else {
+        const int row = (int)(i / wd.nx);
+        const int ix = wd.x0 + (int)(i - (long long)row * wd.nx);
+        const int pl = row / wd.ny;
+        next_grid[node_index(md, ix, wd.y0 + (row - pl * wd.ny), wd.z0 + pl)] = z;
+      }
+    }
+  }
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < it.total;
        i += (long long)gridDim.x * blockDim.x) {
     int ix, iy, iz;
@@ -245,8 +276,11 @@ grid_op_box_kernel(neuma_mpm_const c, const int32_t* __restrict__ box, float4* _
 
 // g2p from a (v, m) grid (mpm.py:432-498); optionally folds the new positions into the
 // next substep's box.
+// 100 k particles are 21 warps per SM: (256, 3) keeps 24 warps resident so the kernel is ONE wave.
+// Row I/O goes through shared memory (rows_load / rows_store in mpm_common.cuh).
+constexpr int G2P_BLOCK = 256;
 template <bool WITH_BOX>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(G2P_BLOCK, 3)
 g2p_from_kernel(neuma_mpm_const c, int n, const float* __restrict__ x, const float* __restrict__ F,
                 const float* __restrict__ clip, const int* __restrict__ enabled,
                 const int32_t* __restrict__ box, const float4* __restrict__ grid,
@@ -254,12 +288,35 @@ g2p_from_kernel(neuma_mpm_const c, int n, const float* __restrict__ x, const flo
                 float* __restrict__ F2, int32_t* __restrict__ box_next) {
   pdl_prologue();
   __shared__ int sbox[6];
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool active = p < n && enabled[p] != 0 && particle_selected(c, x[3 * p + 2]);
+  constexpr int B = G2P_BLOCK;
+  __shared__ float sm[B * 36];                         // in: x 3, F 9; out: x' 3, v' 3, C' 9, F' 9
+  float* const sx = sm;
+  float* const sF = sx + 3 * B;
+  float* const ox = sF + 9 * B;
+  float* const ov = ox + 3 * B;
+  float* const oC = ov + 3 * B;
+  float* const oF = oC + 9 * B;
+  const int t = threadIdx.x, p0 = blockIdx.x * B, p = p0 + t, cnt = min(B, n - p0);
+  const GridMap gm = grid_map(c, box);
+  rows_load<3, B>(sx, x, p0, cnt);
+  rows_load<9, B>(sF, F, p0, cnt);
+  const int en = p < n ? enabled[p] : 0;
+  __syncthreads();
+  const bool active = p < n && en != 0 && particle_selected(c, sx[3 * t + 2]);
   float nx3[3] = {0.f, 0.f, 0.f};
-  if (active) {
-    const GridMap gm = grid_map(c, box);
-    g2p_particle<false>(c, gm, p, x, F, clip, grid, x2, v2, C2, F2, nx3);
+  if (active) g2p_particle<false>(c, gm, t, sx, sF, clip + p0, grid, ox, ov, oC, oF, nx3);
+  // rows of particles that do not take part keep what they hold: the block stores cooperatively only
+  // when every particle wrote its row
+  if (__syncthreads_and(active || p >= n)) {
+    rows_store<3, B>(x2, ox, p0, cnt);
+    rows_store<3, B>(v2, ov, p0, cnt);
+    rows_store<9, B>(C2, oC, p0, cnt);
+    rows_store<9, B>(F2, oF, p0, cnt);
+  } else if (active) {
+    row_store<3>(x2, ox, p, t);
+    row_store<3>(v2, ov, p, t);
+    row_store<9>(C2, oC, p, t);
+    row_store<9>(F2, oF, p, t);
   }
   if (WITH_BOX) box_accumulate(c, active, nx3[0], nx3[1], nx3[2], box_next, sbox);
 }
@@ -314,8 +371,11 @@ bwd_node_kernel(neuma_mpm_const c, const int32_t* __restrict__ box,
 
 // backward pass 3, per particle: gather v_node and (dL/dmv, dL/dm) of its 27 nodes and
 // accumulate adj(G2P) (the terms that need v_node) and adj(P2G).
+constexpr int GATHER_BLOCK = 128;
+constexpr int GATHER_SMEM_FLOATS = 69 + 33;           // staged inputs + outputs per particle
+constexpr int GATHER_SMEM = GATHER_SMEM_FLOATS * GATHER_BLOCK * 4;
 template <bool HAVE_C2>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(GATHER_BLOCK, 3)
 bwd_gather_v_kernel(neuma_mpm_const c, int n, const float* __restrict__ x,
                     const float* __restrict__ v, const float* __restrict__ C,
                     const float* __restrict__ F, const float* __restrict__ stress,
@@ -328,16 +388,41 @@ bwd_gather_v_kernel(neuma_mpm_const c, int n, const float* __restrict__ x,
                     const float4* __restrict__ gadj, float* __restrict__ gx, float* __restrict__ gv,
                     float* __restrict__ gC, float* __restrict__ gF, float* __restrict__ gstress) {
   pdl_prologue();
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n) return;
-  if (!particle_selected(c, x[3 * p + 2])) return;      // the other class's launch writes these rows
-  if (enabled[p] == 0) {
-    zero_particle_grads(p, gx, gv, gC, gF, gstress);
-    return;
-  }
+  constexpr int B = GATHER_BLOCK;
+  extern __shared__ float gsm[];                       // GATHER_SMEM_FLOATS per particle, see below
+  float* q = gsm;
+  auto take = [&](int k) { float* r = q; q += k * B; return r; };
+  float* const sx = take(3); float* const sv = take(3); float* const sC = take(9); float* const sF = take(9);
+  float* const ss = take(9); float* const sv2 = take(3); float* const sC2 = take(9); float* const sgx2 = take(3);
+  float* const sgv2 = take(3); float* const sgC2 = take(9); float* const sgF2 = take(9);
+  float* const ogx = take(3); float* const ogv = take(3); float* const ogC = take(9); float* const ogF = take(9);
+  float* const ogs = take(9);
+  const int t = threadIdx.x, p0 = blockIdx.x * B, p = p0 + t, cnt = min(B, n - p0);
   const GridMap gm = grid_map(c, box);
-  bwd_gather_particle<false, HAVE_C2>(c, gm, p, x, v, C, F, stress, vol, rho, clip, v2, C2, gx2, gv2, gC2,
-                                      gF2, grid, gadj, gx, gv, gC, gF, gstress);
+  rows_load<3, B>(sx, x, p0, cnt);   rows_load<3, B>(sv, v, p0, cnt);     rows_load<9, B>(sC, C, p0, cnt);
+  rows_load<9, B>(sF, F, p0, cnt);   rows_load<9, B>(ss, stress, p0, cnt); rows_load<3, B>(sv2, v2, p0, cnt);
+  if (HAVE_C2) rows_load<9, B>(sC2, C2, p0, cnt);
+  rows_load<3, B>(sgx2, gx2, p0, cnt); rows_load<3, B>(sgv2, gv2, p0, cnt); rows_load<9, B>(sgC2, gC2, p0, cnt);
+  rows_load<9, B>(sgF2, gF2, p0, cnt);
+  const int en = p < n ? enabled[p] : 0;
+  __syncthreads();
+  // rows of the other selection class belong to the other launch
+  const bool mine = p < n && particle_selected(c, sx[3 * t + 2]);
+  if (mine) {
+    if (en == 0)
+      zero_particle_grads(t, ogx, ogv, ogC, ogF, ogs);
+    else
+      bwd_gather_particle<false, HAVE_C2>(c, gm, t, sx, sv, sC, sF, ss, vol + p0, rho + p0, clip + p0, sv2,
+                                          HAVE_C2 ? sC2 : nullptr, sgx2, sgv2, sgC2, sgF2, grid, gadj, ogx, ogv, ogC,
+                                          ogF, ogs);
+  }
+  if (__syncthreads_and(mine || p >= n)) {
+    rows_store<3, B>(gx, ogx, p0, cnt); rows_store<3, B>(gv, ogv, p0, cnt); rows_store<9, B>(gC, ogC, p0, cnt);
+    rows_store<9, B>(gF, ogF, p0, cnt); rows_store<9, B>(gstress, ogs, p0, cnt);
+  } else if (mine) {
+    row_store<3>(gx, ogx, p, t); row_store<3>(gv, ogv, p, t); row_store<9>(gC, ogC, p, t);
+    row_store<9>(gF, ogF, p, t); row_store<9>(gstress, ogs, p, t);
+  }
 }
 
 // ------------------------------------------------------------------ cell order
@@ -588,6 +673,20 @@ inline int pblock(int dflt) {
   return v > 0 ? v : dflt;
 }
 
+// opt-in dynamic shared memory of the gather kernel (per device, tracked in the ctx)
+int set_rollout_attrs(neuma_ctx* ctx) {
+  if (ctx->rollout_attrs_set) return 0;
+  int cur = -1;
+  cudaGetDevice(&cur);
+  if (cur != ctx->device) NEUMA_CUDA(ctx, cudaSetDevice(ctx->device));
+  const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
+  NEUMA_CUDA(ctx, cudaFuncSetAttribute(bwd_gather_v_kernel<true>, attr, GATHER_SMEM));
+  NEUMA_CUDA(ctx, cudaFuncSetAttribute(bwd_gather_v_kernel<false>, attr, GATHER_SMEM));
+  ctx->rollout_attrs_set = 1;
+  if (cur >= 0 && cur != ctx->device) cudaSetDevice(cur);
+  return 0;
+}
+
 int check_slab(neuma_ctx* ctx, const neuma_mpm_const* c) {
   if (!ctx || !c) return 2;
   if (c->num_grids <= 0 || c->nz <= 0 || c->z_off < 0 || c->z_off + c->nz > c->num_grids + 4)
@@ -647,11 +746,18 @@ int neuma_mpm_p2g_to(neuma_ctx* ctx, const neuma_mpm_const* c, int n, const floa
   return 0;
 }
 
-int neuma_mpm_grid_op_box(neuma_ctx* ctx, const neuma_mpm_const* c, const int32_t* box, float* grid,
+int neuma_mpm_grid_op_box(neuma_ctx* ctx, const neuma_mpm_const* c, int32_t* box, float* grid,
                           float* adj_to_clear, void* stream) {
+  return neuma_mpm_grid_op_next(ctx, c, box, grid, adj_to_clear, nullptr, nullptr, stream);
+}
+
+int neuma_mpm_grid_op_next(neuma_ctx* ctx, const neuma_mpm_const* c, int32_t* box, float* grid, float* adj_to_clear,
+                           float* next_grid, int32_t* box_reset, void* stream) {
   if (int r = check_slab(ctx, c)) return r;
+  if (!box || !grid) return neuma_fail_msg(ctx, "neuma_mpm_grid_op: box and grid are required");
+  if (next_grid && c->sel_mode != 0) return neuma_fail_msg(ctx, "neuma_mpm_grid_op_next: sel_mode must be 0");
   NEUMA_CUDA(ctx, neuma_launch(grid_op_box_kernel, dim3(node_pass_blocks(ctx)), dim3(256), 0, (cudaStream_t)stream,
-                               *c, box, (float4*)grid, (float4*)adj_to_clear));
+                               *c, box, (float4*)grid, (float4*)adj_to_clear, (float4*)next_grid, box_reset));
   NEUMA_LAUNCH_CHECK(ctx, "grid_op_box_kernel");
   return 0;
 }
@@ -664,7 +770,7 @@ int neuma_mpm_g2p_from(neuma_ctx* ctx, const neuma_mpm_const* c, int n, const fl
   if (n <= 0) return 0;
   if (c->compact && !box) return neuma_fail_msg(ctx, "neuma_mpm_g2p_from: a compact grid needs its box");
   cudaStream_t st = (cudaStream_t)stream;
-  const int pb = pblock(256);
+  const int pb = G2P_BLOCK;
   NEUMA_CUDA(ctx, neuma_launch(box_next ? g2p_from_kernel<true> : g2p_from_kernel<false>, dim3((n + pb - 1) / pb),
                                dim3(pb), 0, st, *c, n, x, F, clip_bound, enabled, box, (const float4*)grid_v, x2, v2,
                                C2, F2, box_next));
@@ -703,6 +809,16 @@ int neuma_mpm_bwd_scatter(neuma_ctx* ctx, const neuma_mpm_const* c, int n, const
   return 0;
 }
 
+int neuma_mpm_bwd_node(neuma_ctx* ctx, const neuma_mpm_const* c, const float* grid_v, float* adj, const int32_t* box,
+                       void* stream) {
+  if (int r = check_slab(ctx, c)) return r;
+  if (!grid_v || !adj || !box) return neuma_fail_msg(ctx, "neuma_mpm_bwd_node: NULL argument");
+  NEUMA_CUDA(ctx, neuma_launch(bwd_node_kernel, dim3(node_pass_blocks(ctx)), dim3(256), 0, (cudaStream_t)stream, *c,
+                               box, (const float4*)grid_v, (float4*)adj));
+  NEUMA_LAUNCH_CHECK(ctx, "bwd_node_kernel");
+  return 0;
+}
+
 int neuma_mpm_bwd_node_gather(neuma_ctx* ctx, const neuma_mpm_const* c, int n, const float* x,
                               const float* v, const float* C, const float* F, const float* stress,
                               const float* vol, const float* rho, const float* clip_bound,
@@ -718,9 +834,10 @@ int neuma_mpm_bwd_node_gather(neuma_ctx* ctx, const neuma_mpm_const* c, int n, c
   NEUMA_CUDA(ctx, neuma_launch(bwd_node_kernel, dim3(node_pass_blocks(ctx)), dim3(256), 0, st, *c, box,
                                (const float4*)grid_v, (float4*)adj));
   NEUMA_LAUNCH_CHECK(ctx, "bwd_node_kernel");
-  const int pb = pblock(128) > 128 ? 128 : pblock(128);
+  const int pb = GATHER_BLOCK;
+  if (int r = set_rollout_attrs(ctx)) return r;
   NEUMA_CUDA(ctx, neuma_launch(C2 ? bwd_gather_v_kernel<true> : bwd_gather_v_kernel<false>, dim3((n + pb - 1) / pb),
-                               dim3(pb), 0, st, *c, n, x, v, C, F, stress, vol, rho, clip_bound, enabled, v2, C2, gx2,
+                               dim3(pb), GATHER_SMEM, st, *c, n, x, v, C, F, stress, vol, rho, clip_bound, enabled, v2, C2, gx2,
                                gv2, gC2, gF2, box, (const float4*)grid_v, (const float4*)adj, gx, gv, gC, gF, gstress));
   NEUMA_LAUNCH_CHECK(ctx, "bwd_gather_v_kernel");
   return 0;

@@ -314,8 +314,11 @@ def mpm_p2g_to(c: MPMConstC, x, v, Cm, stress, vol, rho, enabled, grid, box=None
                  ptr(vol), ptr(rho), ptr(enabled), ptr(box), ptr(grid), _stream(x))
 
 
-def mpm_grid_op_box(c: MPMConstC, box, grid, adj_to_clear=None) -> None:
-    _ctx(grid).call("neuma_mpm_grid_op_box", C.byref(c), ptr(box), ptr(grid), ptr(adj_to_clear), _stream(grid))
+def mpm_grid_op_box(c: MPMConstC, box, grid, adj_to_clear=None, next_grid=None, box_reset=None) -> None:
+    """grid_op over the box; next_grid / box_reset: also prepare the next substep's slot
+    (neuma_mpm_grid_op_next)."""
+    _ctx(grid).call("neuma_mpm_grid_op_next", C.byref(c), ptr(box), ptr(grid), ptr(adj_to_clear), ptr(next_grid),
+                    ptr(box_reset), _stream(grid))
 
 
 def mpm_g2p_from(c: MPMConstC, x, F, clip_bound, enabled, grid_v, out, box_next=None, box=None) -> None:
@@ -419,6 +422,26 @@ def constitutive_bwd_scatter(Ftrial, staged, alpha: float, gout, gFtrial, gWpart
                  _stream(F))
 
 
+def constitutive_fwd_g2p(staged, alpha: float, F_out, c: MPMConstC, x, F, clip_bound, enabled, grid_v, out,
+                         box_next=None, box=None, hidden: int = 64) -> None:
+    """G2P + plasticity in one kernel (neuma_constitutive_fwd_g2p): out = (x', v', C', F_trial) as
+    mpm_g2p_from writes them, F_out = plasticity(F_trial)."""
+    x2, v2, C2, Ft = out
+    _ctx(x).call("neuma_constitutive_fwd_g2p", x.shape[0], hidden, ptr(staged), C.c_float(alpha), ptr(F_out),
+                 C.byref(c), ptr(x), ptr(F), ptr(clip_bound), ptr(enabled), ptr(box), ptr(grid_v), ptr(x2), ptr(v2),
+                 ptr(C2), ptr(Ft), ptr(box_next), _stream(x))
+
+
+def constitutive_bwd_gather(kind: int, staged, gWpart, c: MPMConstC, x, v, Cm, F, stress, vol, rho, clip_bound,
+                            enabled, v2, C2, gx2, gv2, gC2, gF2, grid_v, adj, gx, gv, gC, gF, gstress, box=None,
+                            hidden: int = 64) -> None:
+    """adjoint gather of the substep + elasticity backward in one kernel (neuma_constitutive_bwd_gather)."""
+    _ctx(x).call("neuma_constitutive_bwd_gather", kind, x.shape[0], hidden, ptr(staged), ptr(gWpart), C.byref(c),
+                 ptr(x), ptr(v), ptr(Cm), ptr(F), ptr(stress), ptr(vol), ptr(rho), ptr(clip_bound), ptr(enabled),
+                 ptr(v2), ptr(C2), ptr(gx2), ptr(gv2), ptr(gC2), ptr(gF2), ptr(box), ptr(grid_v), ptr(adj), ptr(gx),
+                 ptr(gv), ptr(gC), ptr(gF), ptr(gstress), _stream(x))
+
+
 def constitutive_reduce_partials(gWpart, gW0, gW1, gW2, hidden: int = 64) -> None:
     """gW* += sum of the slots; the slots are zeroed."""
     _ctx(gWpart).call("neuma_constitutive_reduce_partials", hidden, ptr(gWpart), ptr(gW0), ptr(gW1), ptr(gW2),
@@ -435,6 +458,10 @@ def mpm_planes_add(dst: torch.Tensor, src: torch.Tensor) -> None:
 def mpm_bwd_scatter(c: MPMConstC, x, F, clip_bound, enabled, v2, gx2, gv2, gC2, gF2, adj, box=None) -> None:
     _ctx(x).call("neuma_mpm_bwd_scatter", C.byref(c), x.shape[0], ptr(x), ptr(F), ptr(clip_bound), ptr(enabled),
                  ptr(v2), ptr(gx2), ptr(gv2), ptr(gC2), ptr(gF2), ptr(box), ptr(adj), _stream(x))
+
+
+def mpm_bwd_node(c: MPMConstC, grid_v, adj, box) -> None:
+    _ctx(adj).call("neuma_mpm_bwd_node", C.byref(c), ptr(grid_v), ptr(adj), ptr(box), _stream(adj))
 
 
 def mpm_bwd_node_gather(c: MPMConstC, x, v, Cm, F, stress, vol, rho, clip_bound, enabled, v2, C2, gx2, gv2, gC2,

@@ -39,7 +39,7 @@ class FusedFrame:
                  alpha: float, substeps: int, device, bind=None, gaussians=None,
                  settings: Optional[RasterSettingsC] = None, center=None, size=None,
                  elastic_kind: int = ops.KIND_ELASTIC, use_graphs: bool = True, sort: bool = True,
-                 compact: bool = True, grid_margin: int = 6, cap_nodes: Optional[int] = None, fuse: bool = True,
+                 compact: bool = True, grid_margin: int = 6, cap_nodes: Optional[int] = None, fuse=True,
                  frames: int = 1, views: Optional[Sequence[RasterSettingsC]] = None, loss: str = "l2",
                  force_mask_data: bool = False):
         """frames: rendered frames this engine rolls out before ONE backward over all of them
@@ -51,7 +51,11 @@ class FusedFrame:
         compact: saved grids hold the node bounding box only; their capacity is fixed at the first
         load_state() from that state's box widened by `grid_margin` nodes on every side (room for
         the cloud to move / deform over the frames this engine will see), or given as cap_nodes.
-        A later box that does not fit is reported by check() -- nothing is written out of bounds."""
+        A later box that does not fit is reported by check() -- nothing is written out of bounds.
+        fuse: True | "full" = three kernels per forward substep ([elasticity + P2G] [grid_op] [G2P +
+        plasticity]) and three per backward substep ([plasticity bwd + adjoint scatter] [node pass]
+        [adjoint gather + elasticity bwd]); "epilogue" = only the scatters ride in the constitutive kernels
+        (five / six launches per substep); False = every stage its own kernel."""
         self.n, self.S, self.dev = int(n), int(substeps), device
         self.frames = int(frames)
         self.T = self.S * self.frames                   # substeps resident for one backward
@@ -64,7 +68,9 @@ class FusedFrame:
         # statics in the engine's (cell-sorted) particle order; refreshed by load_state()
         self.vol, self.rho, self.clip, self.enabled = [t.clone() for t in self._statics_in]
         self.sort = bool(sort)
-        self.fuse = bool(fuse)       # P2G / adjoint scatter inside the constitutive kernels' epilogues
+        if fuse not in (True, False, "full", "epilogue"):
+            raise ValueError("fuse must be True, False, 'full' or 'epilogue'")
+        self.fuse = "full" if fuse is True else fuse     # which MPM stages ride inside the constitutive kernels
         self.perm = torch.arange(n, device=device, dtype=torch.int32)   # sorted slot -> caller index
         self.inv = self.perm.clone()                                    # caller index -> sorted slot
         self.We = [w.detach().clone().contiguous() for w in We]     # engine-owned static buffers (set_weights)
@@ -117,8 +123,9 @@ class FusedFrame:
             self.c = self.c.variant(compact=1, cap_nodes=int(nodes))
         self.cap_nodes = int(nodes)
         self.grid = torch.empty(self.T, nodes, 4, **f)
-        # ONE adjoint scatter target, cleared (over the substep's box) inside the backward itself
+        # adjoint scatter target(s), cleared (over the substep's box) inside the backward itself
         self.adj = torch.empty(nodes, 4, **f)
+        self.adj2 = torch.empty(nodes, 4, **f) if self.fuse == "full" else None
 
     def _cap_from_box(self, box_host) -> int:
         lo, hi = box_host[:3], box_host[3:6]
@@ -138,15 +145,30 @@ class FusedFrame:
     def check(self) -> None:
         """Raises if a substep's node box did not fit the compact grid slots (that substep was
         skipped on the device).  Synchronises."""
-        if self.compact and self.grid is not None and bool(self.box[:, 6].any().item()):
+        if self.grid is not None and bool(self.box[:, 6].any().item()):
             raise NeumaError("FusedFrame: the particles' node box outgrew the compact grid slots "
-                                 f"(cap_nodes={self.cap_nodes}); build the engine with a larger grid_margin / cap_nodes")
+                                 f"(cap_nodes={self.cap_nodes}; build the engine with a larger grid_margin / cap_nodes)"
+                                 " or a particle crossed more than one cell in a substep (use fuse='epilogue')")
 
     # ------------------------------------------------------------------ sim
     def _sim_forward(self, frame: int = 0) -> None:
         c = self.c
         main = torch.cuda.current_stream(self.dev)
         s0, s1 = frame * self.S, (frame + 1) * self.S
+        if self.fuse == "full":
+            # three kernels per substep: [elasticity + P2G] [grid_op + prepare the next slot]
+            # [G2P + plasticity] (csrc/constitutive.cu FusedP2G / FusedG2P, mpm_rollout.cu grid_op_box_kernel)
+            ops.mpm_box_clear(c, self.box[s0], self.grid[s0], None, None)
+            for s in range(s0, s1):
+                ops.constitutive_fwd_p2g(self.kind_e, self.F[s], self.We_st, self.stress[s], c, self.x[s], self.v[s],
+                                         self.C[s], self.vol, self.rho, self.enabled, self.grid[s], box=self.box[s])
+                ops.mpm_grid_op_box(c, self.box[s], self.grid[s], None,
+                                    next_grid=self.grid[s + 1] if s + 1 < s1 else None, box_reset=self.box[s + 1])
+                ops.constitutive_fwd_g2p(self.Wp_st, self.alpha, self.F[s + 1], c, self.x[s], self.F[s], self.clip,
+                                         self.enabled, self.grid[s],
+                                         (self.x[s + 1], self.v[s + 1], self.C[s + 1], self.Ftrial[s]),
+                                         box_next=self.box[s + 1], box=self.box[s])
+            return
         ops.mpm_box_clear(c, self.box[s0], self.grid[s0], None, self.box[s0 + 1])
         for s in range(s0, s1):
             if self.fuse:
@@ -179,24 +201,43 @@ class FusedFrame:
         main = torch.cuda.current_stream(self.dev)
         s0, s1 = frame * self.S, (frame + 1) * self.S
         cur, nxt = 0, 1
-        # the ONE adjoint scatter target is cleared over a substep's box inside the backward itself
-        ops.mpm_box_clear(c, self.box[s1 - 1], self.adj, None, None)
+        full = self.fuse == "full"
+        # the adjoint scatter target is cleared over a substep's box inside the backward itself
+        # (full fusion: two targets in turn, so that the clear for substep s - 1 runs beside substep s)
+        adjs = (self.adj, self.adj2) if full else (self.adj, self.adj)
+        ops.mpm_box_clear(c, self.box[s1 - 1], adjs[(s1 - 1) & 1], None, None)
         for s in reversed(range(s0, s1)):
             gx2, gv2, gC2, gF_next = self.g[cur]
             gx, gv, gC, gF = self.g[nxt]
+            adj = adjs[s & 1]
+            if full and s > s0:
+                self._side.wait_stream(main)
+                with torch.cuda.stream(self._side):
+                    ops.mpm_box_clear(c, self.box[s - 1], adjs[(s - 1) & 1], None, None)
             # plasticity: F[s+1] = P(Ftrial[s]); then adj(G2P) scatters dL/dv_node into adj
             if self.fuse:
                 ops.constitutive_bwd_scatter(self.Ftrial[s], self.Wp_st, self.alpha, gF_next, self.gFtrial,
                                              self.gWp_part, c, self.x[s], self.F[s], self.clip, self.enabled,
-                                             self.v[s + 1], gx2, gv2, gC2, self.adj, box=self.box[s])
+                                             self.v[s + 1], gx2, gv2, gC2, adj, box=self.box[s])
             else:
                 ops.constitutive_bwd_partials(ops.KIND_PLASTIC, self.Ftrial[s], self.Wp_st, self.alpha, gF_next,
                                               self.gFtrial, self.gWp_part)
                 ops.mpm_bwd_scatter(c, self.x[s], self.F[s], self.clip, self.enabled, self.v[s + 1], gx2, gv2, gC2,
-                                    self.gFtrial, self.adj, box=self.box[s])
+                                    self.gFtrial, adj, box=self.box[s])
+            if full:
+                # [node pass] [adjoint gather + elasticity backward]
+                ops.mpm_bwd_node(c, self.grid[s], adj, self.box[s])
+                ops.constitutive_bwd_gather(self.kind_e, self.We_st, self.gWe_part, c, self.x[s], self.v[s], self.C[s],
+                                            self.F[s], self.stress[s], self.vol, self.rho, self.clip, self.enabled,
+                                            self.v[s + 1], self.C[s + 1], gx2, gv2, gC2, self.gFtrial, self.grid[s],
+                                            adj, gx, gv, gC, gF, self.gstress, box=self.box[s])
+                if s > s0:
+                    main.wait_stream(self._side)
+                cur, nxt = nxt, cur
+                continue
             ops.mpm_bwd_node_gather(c, self.x[s], self.v[s], self.C[s], self.F[s], self.stress[s], self.vol,
                                     self.rho, self.clip, self.enabled, self.v[s + 1], self.C[s + 1], gx2, gv2, gC2,
-                                    self.gFtrial, self.grid[s], self.adj, self.box[s], gx, gv, gC, gF, self.gstress)
+                                    self.gFtrial, self.grid[s], adj, self.box[s], gx, gv, gC, gF, self.gstress)
             if s > s0:
                 # adj was last read by the gather above: clear it for substep s - 1 next to the
                 # elasticity backward

@@ -57,6 +57,59 @@ def test_graph_replay_equals_eager_from_the_first_frame(cuda_dev):
             assert rel_err(a, b) < 1e-4, key
 
 
+@pytest.mark.parametrize("compact", [True, False])
+def test_fuse_modes_agree(cuda_dev, compact):
+    """fuse = "full" (3 kernels per substep each way: G2P inside the plasticity kernel, the adjoint gather
+    inside the elasticity backward, the next slot prepared by grid_op) and "epilogue" against the un-fused
+    launch sequence: same per-particle code, so forward state and loss agree to fp32 atomics order."""
+    from neuma_b200.pipeline import FusedFrame
+    spec, cc, d, W, alpha, settings, bind, gs, F0, gt, kxyz = _setup(cuda_dev, n=4000)
+    runs = {}
+    for fuse in (False, "epilogue", "full"):
+        eng = FusedFrame(spec["n"], cc, (d["vol"], d["rho"], d["clip"], d["enabled"]), W["elastic"], W["plastic"],
+                         alpha, 4, cuda_dev, bind=bind, gaussians=gs, settings=settings, use_graphs=False, fuse=fuse,
+                         compact=compact)
+        eng.load_state(d["x"], d["v"], d["C"], F0)
+        eng.zero_weight_grads()
+        loss, g0 = eng.frame_fwd_bwd(gt, d["x"].clone(), kxyz)
+        eng.check()
+        runs[fuse] = (loss.clone(), [t.clone() for t in eng.final_state()], [t.clone() for t in g0],
+                      [t.clone() for t in eng.gWe + eng.gWp], eng.box.clone())
+    ref = runs[False]
+    for fuse in ("epilogue", "full"):
+        loss, st, g0, gW, box = runs[fuse]
+        assert torch.equal(box[:, :6], ref[4][:, :6]), fuse            # node boxes of every substep
+        assert abs(float(loss) - float(ref[0])) <= 1e-6 * abs(float(ref[0])), fuse
+        for a, b in zip(st, ref[1]):
+            assert rel_err(a, b) < 5e-5, fuse
+        for a, b in zip(g0, ref[2]):
+            assert rel_err(a, b) < 1e-4, fuse
+        for a, b in zip(gW, ref[3]):
+            assert rel_err(a, b) < 1e-4, fuse
+
+
+def test_full_fusion_flags_a_particle_crossing_more_than_a_cell(cuda_dev):
+    """fuse="full" clears the next grid slot over the current box dilated by ONE node; a particle that
+    leaves that region in one substep must raise check() instead of scattering into stale nodes."""
+    from neuma_b200._lib import NeumaError
+    from neuma_b200.pipeline import FusedFrame
+    spec, cc, d, W, alpha, settings, bind, gs, F0, gt, kxyz = _setup(cuda_dev, n=1000)
+    v = d["v"].clone()
+    v[:, 0] = 3.0 / (spec["G"] * 1e-3)                # three cells per substep along +x
+    eng = FusedFrame(spec["n"], cc, (d["vol"], d["rho"], d["clip"], d["enabled"]), W["elastic"], W["plastic"], alpha, 2,
+                     cuda_dev, bind=bind, gaussians=gs, settings=settings, use_graphs=False, grid_margin=12)
+    eng.load_state(d["x"], v, d["C"], F0)
+    eng.sim_forward()
+    with pytest.raises(NeumaError):
+        eng.check()
+    ok = FusedFrame(spec["n"], cc, (d["vol"], d["rho"], d["clip"], d["enabled"]), W["elastic"], W["plastic"], alpha, 2,
+                    cuda_dev, bind=bind, gaussians=gs, settings=settings, use_graphs=False, grid_margin=12,
+                    fuse="epilogue")
+    ok.load_state(d["x"], v, d["C"], F0)
+    ok.sim_forward()
+    ok.check()
+
+
 def test_set_weights_restages(cuda_dev):
     from neuma_b200.pipeline import FusedFrame
     spec, cc, d, W, alpha, settings, bind, gs, F0, gt, kxyz = _setup(cuda_dev, n=1000)
