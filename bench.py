@@ -703,9 +703,10 @@ def main():
                     help="parity-test configs of BASELINE.json for the record; the headline is jellyduck-100k-128")
     ap.add_argument("--no-fuse", action="store_true",
                     help="A/B: every MPM stage its own kernel (same as --fuse none)")
-    ap.add_argument("--fuse", default="full", choices=["full", "epilogue", "none"],
-                    help="A/B: full = 3 kernels per substep each way (default); epilogue = only P2G / the adjoint "
-                         "scatter ride in the constitutive kernels; none = every stage its own kernel")
+    ap.add_argument("--fuse", default="best", choices=["best", "full", "epilogue", "none"],
+                    help="A/B: epilogue = P2G / the adjoint scatter ride in the constitutive kernels; full = also G2P "
+                         "and the adjoint gather (3 kernels per substep each way); best (default) = epilogue forward, "
+                         "full backward; none = every stage its own kernel")
     ap.add_argument("--no-dropin", action="store_true", help="skip the drop-in (autograd classes) measurement")
     ap.add_argument("--no-slab", action="store_true", help="skip the Z-slab (config 5) section of the line")
     ap.add_argument("--slab-steps", type=int, default=5, help="timed frames of the Z-slab section")
@@ -715,7 +716,7 @@ def main():
     ap.add_argument("--slab", action="store_true",
                     help="BASELINE config 5: 1M particles / 256^3 MPM fwd+bwd, Z-slab sharded over the ranks")
     args = ap.parse_args()
-    args.fuse = False if (args.no_fuse or args.fuse == "none") else args.fuse
+    args.fuse = False if (args.no_fuse or args.fuse == "none") else (True if args.fuse == "best" else args.fuse)
     WORKLOAD = args.workload
     if WORKLOAD.startswith("claycat"):       # plasticine_0300 weights
         GOLD = os.path.join(ROOT, "tests", "golden", "material_plasticine.npz")

@@ -128,19 +128,31 @@ box_clear_kernel(neuma_mpm_const c, int32_t* __restrict__ box, float4* __restric
   }
 }
 
-__global__ void __launch_bounds__(256)
+constexpr int SCATTER_BLOCK = 256;   // p2g_to_kernel / bwd_scatter_adj_kernel: rows staged in shared memory
+__global__ void __launch_bounds__(SCATTER_BLOCK)
 p2g_to_kernel(neuma_mpm_const c, int n, const float* __restrict__ x, const float* __restrict__ v,
               const float* __restrict__ C, const float* __restrict__ stress,
               const float* __restrict__ vol, const float* __restrict__ rho,
               const int* __restrict__ enabled, const int32_t* __restrict__ box,
               float4* __restrict__ grid) {
   pdl_prologue();
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n) return;
-  if (enabled[p] == 0 || !particle_selected(c, x[3 * p + 2])) return;
-  check_interior_class(c, x[3 * p + 2], box);
+  constexpr int B = SCATTER_BLOCK;
+  __shared__ float sm[B * 24];                         // x 3, v 3, C 9, stress 9
+  float* const sx = sm;
+  float* const sv = sx + 3 * B;
+  float* const sC = sv + 3 * B;
+  float* const ss = sC + 9 * B;
+  const int t = threadIdx.x, p0 = blockIdx.x * B, p = p0 + t, cnt = min(B, n - p0);
   const GridMap gm = grid_map(c, box);
-  p2g_particle(c, gm, p, x, v, C, stress + 9 * (size_t)p, vol[p], rho[p], grid);
+  rows_load<3, B>(sx, x, p0, cnt);
+  rows_load<3, B>(sv, v, p0, cnt);
+  rows_load<9, B>(sC, C, p0, cnt);
+  rows_load<9, B>(ss, stress, p0, cnt);
+  const int en = p < n ? enabled[p] : 0;
+  __syncthreads();
+  if (p >= n || en == 0 || !particle_selected(c, sx[3 * t + 2])) return;
+  check_interior_class(c, sx[3 * t + 2], box);
+  p2g_particle(c, gm, t, sx, sv, sC, ss + 9 * t, vol[p], rho[p], grid);
 }
 
 // ---- the north_star's P2G shape, kept as a MEASURED ALTERNATIVE (NEUMA_P2G=tiled; tools/p2g_ab.py,
@@ -322,7 +334,7 @@ g2p_from_kernel(neuma_mpm_const c, int n, const float* __restrict__ x, const flo
 }
 
 // backward pass 1: scatter adj(G2P)'s dL/dv_node into adj (xyz; w unused)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(SCATTER_BLOCK)
 bwd_scatter_adj_kernel(neuma_mpm_const c, int n, const float* __restrict__ x,
                        const float* __restrict__ F, const float* __restrict__ clip,
                        const int* __restrict__ enabled, const float* __restrict__ v2,
@@ -330,13 +342,23 @@ bwd_scatter_adj_kernel(neuma_mpm_const c, int n, const float* __restrict__ x,
                        const float* __restrict__ gC2, const float* __restrict__ gF2,
                        const int32_t* __restrict__ box, float4* __restrict__ gadj) {
   pdl_prologue();
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n) return;
-  if (enabled[p] == 0 || !particle_selected(c, x[3 * p + 2])) return;
-  check_interior_class(c, x[3 * p + 2], box);
+  constexpr int B = SCATTER_BLOCK;
+  __shared__ float sm[B * 39];                         // x 3, F 9, v' 3, gx' 3, gv' 3, gC' 9, gF' 9
+  float* q = sm;
+  auto take = [&](int k) { float* r = q; q += k * B; return r; };
+  float* const sx = take(3); float* const sF = take(9); float* const sv2 = take(3); float* const sgx2 = take(3);
+  float* const sgv2 = take(3); float* const sgC2 = take(9); float* const sgF2 = take(9);
+  const int t = threadIdx.x, p0 = blockIdx.x * B, p = p0 + t, cnt = min(B, n - p0);
   const GridMap gm = grid_map(c, box);
-  const G2PAdj g = g2p_adjoint_inputs(c, p, x, F, clip, v2, gx2, gv2, gC2, gF2 + 9 * (size_t)p);
-  g2p_adjoint_scatter(c, gm, p, x, g, gadj);
+  rows_load<3, B>(sx, x, p0, cnt);     rows_load<9, B>(sF, F, p0, cnt);       rows_load<3, B>(sv2, v2, p0, cnt);
+  rows_load<3, B>(sgx2, gx2, p0, cnt); rows_load<3, B>(sgv2, gv2, p0, cnt);   rows_load<9, B>(sgC2, gC2, p0, cnt);
+  rows_load<9, B>(sgF2, gF2, p0, cnt);
+  const int en = p < n ? enabled[p] : 0;
+  __syncthreads();
+  if (p >= n || en == 0 || !particle_selected(c, sx[3 * t + 2])) return;
+  check_interior_class(c, sx[3 * t + 2], box);
+  const G2PAdj g = g2p_adjoint_inputs(c, t, sx, sF, clip + p0, sv2, sgx2, sgv2, sgC2, sgF2 + 9 * t);
+  g2p_adjoint_scatter(c, gm, t, sx, g, gadj);
 }
 
 // backward pass 2, per node of the box: adj(grid_op).  (v, m) and dL/dv -> (dL/dmv, dL/dm),
@@ -409,19 +431,28 @@ bwd_gather_v_kernel(neuma_mpm_const c, int n, const float* __restrict__ x,
   // rows of the other selection class belong to the other launch
   const bool mine = p < n && particle_selected(c, sx[3 * t + 2]);
   if (mine) {
+    // any of the five outputs may be NULL (not wanted by the caller)
     if (en == 0)
-      zero_particle_grads(t, ogx, ogv, ogC, ogF, ogs);
+      zero_particle_grads(t, gx ? ogx : nullptr, gv ? ogv : nullptr, gC ? ogC : nullptr, gF ? ogF : nullptr,
+                          gstress ? ogs : nullptr);
     else
       bwd_gather_particle<false, HAVE_C2>(c, gm, t, sx, sv, sC, sF, ss, vol + p0, rho + p0, clip + p0, sv2,
-                                          HAVE_C2 ? sC2 : nullptr, sgx2, sgv2, sgC2, sgF2, grid, gadj, ogx, ogv, ogC,
-                                          ogF, ogs);
+                                          HAVE_C2 ? sC2 : nullptr, sgx2, sgv2, sgC2, sgF2, grid, gadj,
+                                          gx ? ogx : nullptr, gv ? ogv : nullptr, gC ? ogC : nullptr,
+                                          gF ? ogF : nullptr, gstress ? ogs : nullptr);
   }
   if (__syncthreads_and(mine || p >= n)) {
-    rows_store<3, B>(gx, ogx, p0, cnt); rows_store<3, B>(gv, ogv, p0, cnt); rows_store<9, B>(gC, ogC, p0, cnt);
-    rows_store<9, B>(gF, ogF, p0, cnt); rows_store<9, B>(gstress, ogs, p0, cnt);
+    if (gx) rows_store<3, B>(gx, ogx, p0, cnt);
+    if (gv) rows_store<3, B>(gv, ogv, p0, cnt);
+    if (gC) rows_store<9, B>(gC, ogC, p0, cnt);
+    if (gF) rows_store<9, B>(gF, ogF, p0, cnt);
+    if (gstress) rows_store<9, B>(gstress, ogs, p0, cnt);
   } else if (mine) {
-    row_store<3>(gx, ogx, p, t); row_store<3>(gv, ogv, p, t); row_store<9>(gC, ogC, p, t);
-    row_store<9>(gF, ogF, p, t); row_store<9>(gstress, ogs, p, t);
+    if (gx) row_store<3>(gx, ogx, p, t);
+    if (gv) row_store<3>(gv, ogv, p, t);
+    if (gC) row_store<9>(gC, ogC, p, t);
+    if (gF) row_store<9>(gF, ogF, p, t);
+    if (gstress) row_store<9>(gstress, ogs, p, t);
   }
 }
 
@@ -663,16 +694,6 @@ constexpr int NEUMA_HALO_BLOCKS = 64;
 
 inline int node_pass_blocks(neuma_ctx* ctx) { return ctx->num_sms * 8; }
 
-// threads per block of the per-particle kernels (NEUMA_MPM_BLOCK overrides; tuned in profiles/)
-inline int pblock(int dflt) {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("NEUMA_MPM_BLOCK");
-    v = e ? atoi(e) : 0;
-  }
-  return v > 0 ? v : dflt;
-}
-
 // opt-in dynamic shared memory of the gather kernel (per device, tracked in the ctx)
 int set_rollout_attrs(neuma_ctx* ctx) {
   if (ctx->rollout_attrs_set) return 0;
@@ -739,7 +760,7 @@ int neuma_mpm_p2g_to(neuma_ctx* ctx, const neuma_mpm_const* c, int n, const floa
     NEUMA_LAUNCH_CHECK(ctx, "p2g_tiled_kernel");
     return 0;
   }
-  const int pb = pblock(256);
+  const int pb = SCATTER_BLOCK;
   NEUMA_CUDA(ctx, neuma_launch(p2g_to_kernel, dim3((n + pb - 1) / pb), dim3(pb), 0, (cudaStream_t)stream, *c, n, x,
                                v, C, stress, vol, rho, enabled, box, (float4*)grid));
   NEUMA_LAUNCH_CHECK(ctx, "p2g_to_kernel");
@@ -802,7 +823,7 @@ int neuma_mpm_bwd_scatter(neuma_ctx* ctx, const neuma_mpm_const* c, int n, const
     return neuma_fail_msg(ctx, "neuma_mpm_bwd_scatter: a compact grid / sel_mode 3 needs the box");
   if (!v2 || !gx2 || !gv2 || !gC2 || !gF2 || !adj)
     return neuma_fail_msg(ctx, "neuma_mpm_bwd_scatter: NULL argument");
-  const int pb = pblock(256);
+  const int pb = SCATTER_BLOCK;
   NEUMA_CUDA(ctx, neuma_launch(bwd_scatter_adj_kernel, dim3((n + pb - 1) / pb), dim3(pb), 0, (cudaStream_t)stream,
                                *c, n, x, F, clip_bound, enabled, v2, gx2, gv2, gC2, gF2, box, (float4*)adj));
   NEUMA_LAUNCH_CHECK(ctx, "bwd_scatter_adj_kernel");

@@ -52,10 +52,11 @@ class FusedFrame:
         load_state() from that state's box widened by `grid_margin` nodes on every side (room for
         the cloud to move / deform over the frames this engine will see), or given as cap_nodes.
         A later box that does not fit is reported by check() -- nothing is written out of bounds.
-        fuse: True | "full" = three kernels per forward substep ([elasticity + P2G] [grid_op] [G2P +
-        plasticity]) and three per backward substep ([plasticity bwd + adjoint scatter] [node pass]
-        [adjoint gather + elasticity bwd]); "epilogue" = only the scatters ride in the constitutive kernels
-        (five / six launches per substep); False = every stage its own kernel."""
+        fuse: which MPM stages ride inside the constitutive kernels.  "epilogue" = the two scatters (P2G after
+        elasticity, the adjoint scatter after the plasticity backward); "full" = also G2P in front of
+        plasticity and the adjoint gather in front of the elasticity backward (three kernels per substep
+        each way); True (default) = the measured best of both, "epilogue" forward and "full" backward
+        (profiles/r03_fuse_modes.txt); False = every stage its own kernel."""
         self.n, self.S, self.dev = int(n), int(substeps), device
         self.frames = int(frames)
         self.T = self.S * self.frames                   # substeps resident for one backward
@@ -70,7 +71,9 @@ class FusedFrame:
         self.sort = bool(sort)
         if fuse not in (True, False, "full", "epilogue"):
             raise ValueError("fuse must be True, False, 'full' or 'epilogue'")
-        self.fuse = "full" if fuse is True else fuse     # which MPM stages ride inside the constitutive kernels
+        self.fuse = fuse                                 # which MPM stages ride inside the constitutive kernels
+        self.fuse_fwd = {True: "epilogue", False: False}.get(fuse, fuse)
+        self.fuse_bwd = {True: "full", False: False}.get(fuse, fuse)
         self.perm = torch.arange(n, device=device, dtype=torch.int32)   # sorted slot -> caller index
         self.inv = self.perm.clone()                                    # caller index -> sorted slot
         self.We = [w.detach().clone().contiguous() for w in We]     # engine-owned static buffers (set_weights)
@@ -125,7 +128,7 @@ class FusedFrame:
         self.grid = torch.empty(self.T, nodes, 4, **f)
         # adjoint scatter target(s), cleared (over the substep's box) inside the backward itself
         self.adj = torch.empty(nodes, 4, **f)
-        self.adj2 = torch.empty(nodes, 4, **f) if self.fuse == "full" else None
+        self.adj2 = torch.empty(nodes, 4, **f) if self.fuse_bwd == "full" else None
 
     def _cap_from_box(self, box_host) -> int:
         lo, hi = box_host[:3], box_host[3:6]
@@ -155,7 +158,7 @@ class FusedFrame:
         c = self.c
         main = torch.cuda.current_stream(self.dev)
         s0, s1 = frame * self.S, (frame + 1) * self.S
-        if self.fuse == "full":
+        if self.fuse_fwd == "full":
             # three kernels per substep: [elasticity + P2G] [grid_op + prepare the next slot]
             # [G2P + plasticity] (csrc/constitutive.cu FusedP2G / FusedG2P, mpm_rollout.cu grid_op_box_kernel)
             ops.mpm_box_clear(c, self.box[s0], self.grid[s0], None, None)
@@ -171,7 +174,7 @@ class FusedFrame:
             return
         ops.mpm_box_clear(c, self.box[s0], self.grid[s0], None, self.box[s0 + 1])
         for s in range(s0, s1):
-            if self.fuse:
+            if self.fuse_fwd:
                 # elasticity + P2G in ONE kernel: the particle is scattered by the thread that just
                 # computed its stress (csrc/constitutive.cu, FusedP2G)
                 ops.constitutive_fwd_p2g(self.kind_e, self.F[s], self.We_st, self.stress[s], c, self.x[s], self.v[s],
@@ -201,7 +204,7 @@ class FusedFrame:
         main = torch.cuda.current_stream(self.dev)
         s0, s1 = frame * self.S, (frame + 1) * self.S
         cur, nxt = 0, 1
-        full = self.fuse == "full"
+        full = self.fuse_bwd == "full"
         # the adjoint scatter target is cleared over a substep's box inside the backward itself
         # (full fusion: two targets in turn, so that the clear for substep s - 1 runs beside substep s)
         adjs = (self.adj, self.adj2) if full else (self.adj, self.adj)
@@ -215,7 +218,7 @@ class FusedFrame:
                 with torch.cuda.stream(self._side):
                     ops.mpm_box_clear(c, self.box[s - 1], adjs[(s - 1) & 1], None, None)
             # plasticity: F[s+1] = P(Ftrial[s]); then adj(G2P) scatters dL/dv_node into adj
-            if self.fuse:
+            if self.fuse_bwd:
                 ops.constitutive_bwd_scatter(self.Ftrial[s], self.Wp_st, self.alpha, gF_next, self.gFtrial,
                                              self.gWp_part, c, self.x[s], self.F[s], self.clip, self.enabled,
                                              self.v[s + 1], gx2, gv2, gC2, adj, box=self.box[s])

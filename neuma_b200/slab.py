@@ -355,7 +355,8 @@ class SlabRollout:
         self.x[0], self.v[0], self.C[0], self.F[0] = loc[:4]
         self.vol, self.rho, self.clip, self.enabled = loc[4:]
         self.grid = torch.zeros(S, nz, G, G, 4, **f)
-        self.adj = torch.zeros(nz, G, G, 4, **f)           # ONE adjoint scatter target, cleared in the backward
+        self.adj = torch.zeros(nz, G, G, 4, **f)           # adjoint scatter target(s), cleared in the backward
+        self.adj2 = torch.zeros(nz, G, G, 4, **f) if (self.fuse and self.overlap == "none") else None
         self.box = torch.zeros(S + 1, 8, device=dev, dtype=torch.int32)
         self.g = [[torch.zeros(n, 3, **f), torch.zeros(n, 3, **f), torch.zeros(n, 3, 3, **f),
                    torch.zeros(n, 3, 3, **f)] for _ in range(2)]
@@ -529,11 +530,39 @@ class SlabRollout:
         legacy = self.overlap in ("scatter", "full")
         cur, nxt = 0, 1
 
-        def clear(s):      # the ONE adjoint scatter target, cleared over a substep's box inside the backward
-            ops.mpm_box_clear(c, self.box[s], self.adj, None, None)
+        def clear(s, adj=None):      # the adjoint scatter target, cleared over a substep's box inside the backward
+            adj = self.adj if adj is None else adj
+            ops.mpm_box_clear(c, self.box[s], adj, None, None)
             if self.world > 1 and not windowed:
-                for vw in self._overlap_views(self.adj):
+                for vw in self._overlap_views(adj):
                     vw.zero_()
+        if self.fuse and self.overlap == "none":
+            # three kernels + the exchange per substep: [plasticity bwd + adjoint scatter] [exchange] [node pass]
+            # [adjoint gather + elasticity bwd]; two scatter targets in turn, so that the clear for substep
+            # s - 1 runs beside substep s (as FusedFrame._sim_backward, fuse_bwd = "full")
+            adjs = (self.adj, self.adj2)
+            clear(self.S - 1, adjs[(self.S - 1) & 1])
+            for s in reversed(range(self.S)):
+                gx2, gv2, gC2, gF_next = self.g[cur]
+                gxo, gvo, gCo, gFo = self.g[nxt]
+                adj = adjs[s & 1]
+                if s > 0:
+                    self._side.wait_stream(main)
+                    with torch.cuda.stream(self._side):
+                        clear(s - 1, adjs[(s - 1) & 1])
+                ops.constitutive_bwd_scatter(self.Ftrial[s], self.Wp_st, self.alpha, gF_next, self.gFtrial,
+                                             self.gWp_part, c, self.x[s], self.F[s], self.clip, self.enabled,
+                                             self.v[s + 1], gx2, gv2, gC2, adj, box=self.box[s])
+                self._exchange(adj, self.box[s])
+                ops.mpm_bwd_node(c, self.grid[s], adj, self.box[s])
+                ops.constitutive_bwd_gather(self.kind_e, self.We_st, self.gWe_part, c, self.x[s], self.v[s], self.C[s],
+                                            self.F[s], self.stress[s], self.vol, self.rho, self.clip, self.enabled,
+                                            self.v[s + 1], self.C[s + 1], gx2, gv2, gC2, self.gFtrial, self.grid[s],
+                                            adj, gxo, gvo, gCo, gFo, self.gstress, box=self.box[s])
+                if s > 0:
+                    main.wait_stream(self._side)
+                cur, nxt = nxt, cur
+            return
         clear(self.S - 1)
         for s in reversed(range(self.S)):
             gx2, gv2, gC2, gF_next = self.g[cur]
