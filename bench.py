@@ -691,7 +691,7 @@ def run_reference(args):
 
 
 def main():
-    global WORKLOAD, GOLD
+    global WORKLOAD, GOLD, SLAB_WORKLOAD
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -710,6 +710,8 @@ def main():
     ap.add_argument("--no-dropin", action="store_true", help="skip the drop-in (autograd classes) measurement")
     ap.add_argument("--no-slab", action="store_true", help="skip the Z-slab (config 5) section of the line")
     ap.add_argument("--slab-steps", type=int, default=5, help="timed frames of the Z-slab section")
+    ap.add_argument("--slab-workload", default=SLAB_WORKLOAD, choices=["block-1m-256", "block-250k-256"],
+                    help="block-250k-256: development proxy (2 GPUs carry an 8-GPU rank's load each)")
     ap.add_argument("--halo", default="fused", choices=["fused", "peer", "nccl"],
                     help="Z-slab halo exchange: one fused windowed kernel (default), round-1 push/add kernel pairs, "
                          "or NCCL send/recv (eager)")
@@ -718,6 +720,7 @@ def main():
     args = ap.parse_args()
     args.fuse = False if (args.no_fuse or args.fuse == "none") else (True if args.fuse == "best" else args.fuse)
     WORKLOAD = args.workload
+    SLAB_WORKLOAD = args.slab_workload
     if WORKLOAD.startswith("claycat"):       # plasticine_0300 weights
         GOLD = os.path.join(ROOT, "tests", "golden", "material_plasticine.npz")
     if args.impl == "reference":

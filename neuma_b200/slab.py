@@ -263,7 +263,7 @@ class SlabRollout:
     def __init__(self, G: int, dt: float, We, Wp, alpha: float, substeps: int, device, group=None,
                  bound: int = 1, gravity=(0.0, -9.8, 0.0), eps: float = 6e-7, bc: str = "noslip",
                  halo_k: int = 1, elastic_kind: int = 0, halo: str = "fused", use_graphs: Optional[bool] = None,
-                 overlap="none", standalone: bool = False, fuse: bool = True):
+                 overlap="split", standalone: bool = False, fuse: bool = True):
         from . import ops
         self.ops = ops
         self.G, self.dt, self.S, self.dev, self.group = int(G), float(dt), int(substeps), device, group
@@ -303,8 +303,10 @@ class SlabRollout:
         #              the exchange on a side stream under elasticity + P2G of the interior range
         #              (backward: plasticity backward + adjoint scatter likewise).  An interior-range
         #              particle that touches a shared plane after all is counted on the device.
-        # Measured on 2 and 8 B200s (profiles/r02k_slab_scaling.txt): none of the three hides the ~25-30 us
-        # an exchange costs -- the split launches cost what the overlap saves -- so "none" is the default.
+        # Measured (profiles/r02k_slab_scaling.txt, r03_slab_split.txt): "scatter" / "full" cost in extra launches
+        # what they hide; "split" pays once its split points sit on whole tile ROUNDS of the persistent
+        # constitutive kernels (distribute(): split_fwd / split_bwd) -- 1M particles on 2 GPUs 21.2 -> 20.4 ms
+        # per frame against a no-exchange floor of 20.2 -- and is the default.
         overlap = {True: "split", False: "none", None: "none"}.get(overlap, overlap)
         if overlap not in ("none", "scatter", "full", "split"):
             raise ValueError("overlap must be 'none', 'split', 'scatter' or 'full'")
@@ -344,6 +346,13 @@ class SlabRollout:
         order = torch.cat([bnd.nonzero(as_tuple=True)[0], (~bnd).nonzero(as_tuple=True)[0]])
         perm = perm[order].contiguous()
         self.nb = int(bnd.sum().item())
+        # overlap="split" launches [0, split) first and [split, n) under the exchange.  The constitutive kernels
+        # are persistent (one CTA per SM, 3 forward / 2 backward tile pipelines of 128 particles): a split
+        # point on a whole number of tile ROUNDS costs no extra round, any other point costs one
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        n_loc = int(loc[0].shape[0]) if loc[0].dim() else 0
+        self.split_fwd = min(n_loc, -(-self.nb // (sms * 3 * 128)) * (sms * 3 * 128))
+        self.split_bwd = min(n_loc, -(-self.nb // (sms * 2 * 128)) * (sms * 2 * 128))
         loc = [ops.gather_rows(t, perm) if t.shape[0] else t for t in loc]
         self.ids = mine.to(dev)[perm.long()]
         n = self.n = int(loc[0].shape[0])
@@ -356,7 +365,7 @@ class SlabRollout:
         self.vol, self.rho, self.clip, self.enabled = loc[4:]
         self.grid = torch.zeros(S, nz, G, G, 4, **f)
         self.adj = torch.zeros(nz, G, G, 4, **f)           # adjoint scatter target(s), cleared in the backward
-        self.adj2 = torch.zeros(nz, G, G, 4, **f) if (self.fuse and self.overlap == "none") else None
+        self.adj2 = torch.zeros(nz, G, G, 4, **f) if (self.fuse and self.overlap in ("none", "split")) else None
         self.box = torch.zeros(S + 1, 8, device=dev, dtype=torch.int32)
         self.g = [[torch.zeros(n, 3, **f), torch.zeros(n, 3, **f), torch.zeros(n, 3, 3, **f),
                    torch.zeros(n, 3, 3, **f)] for _ in range(2)]
@@ -468,11 +477,11 @@ class SlabRollout:
                     main.wait_stream(self._side)
                     self._mpm_fwd(c, s)
             elif self.overlap == "split":
-                self._elastic_p2g(c, s, 0, self.nb)                 # boundary range: elasticity + P2G
+                self._elastic_p2g(c, s, 0, self.split_fwd)          # boundary range: elasticity + P2G
                 self._side.wait_stream(main)
                 with torch.cuda.stream(self._side):
                     self._exchange(self.grid[s], self.box[s])       # the ONE exchange of the substep ...
-                self._elastic_p2g(self.c_chk, s, self.nb, self.n)   # ... under the interior range's kernel
+                self._elastic_p2g(self.c_chk, s, self.split_fwd, self.n)   # ... under the interior range's kernel
                 main.wait_stream(self._side)
                 self._mpm_fwd(c, s)
             else:
@@ -506,22 +515,23 @@ class SlabRollout:
                 o += t.numel()
         return self.g[self.S % 2]
 
-    def _plastic_bwd_scatter(self, c, s: int, lo: int, hi: int, gx2, gv2, gC2, gF_next) -> None:
+    def _plastic_bwd_scatter(self, c, s: int, lo: int, hi: int, gx2, gv2, gC2, gF_next, adj=None) -> None:
         """plasticity backward (+ adjoint scatter of G2P, fused or as a second kernel) of [lo, hi)"""
         ops = self.ops
         if hi <= lo:
             return
+        adj = self.adj if adj is None else adj
         sl = slice(lo, hi)
         if self.fuse:
             ops.constitutive_bwd_scatter(self.Ftrial[s][sl], self.Wp_st, self.alpha, gF_next[sl], self.gFtrial[sl],
                                          self.gWp_part, c, self.x[s][sl], self.F[s][sl], self.clip[sl],
-                                         self.enabled[sl], self.v[s + 1][sl], gx2[sl], gv2[sl], gC2[sl], self.adj,
+                                         self.enabled[sl], self.v[s + 1][sl], gx2[sl], gv2[sl], gC2[sl], adj,
                                          box=self.box[s])
         else:
             ops.constitutive_bwd_partials(ops.KIND_PLASTIC, self.Ftrial[s][sl], self.Wp_st, self.alpha, gF_next[sl],
                                           self.gFtrial[sl], self.gWp_part)
             ops.mpm_bwd_scatter(c, self.x[s][sl], self.F[s][sl], self.clip[sl], self.enabled[sl], self.v[s + 1][sl],
-                                gx2[sl], gv2[sl], gC2[sl], self.gFtrial[sl], self.adj, box=self.box[s])
+                                gx2[sl], gv2[sl], gC2[sl], self.gFtrial[sl], adj, box=self.box[s])
 
     def _backward_body(self) -> None:
         ops, c = self.ops, self.c
@@ -536,30 +546,38 @@ class SlabRollout:
             if self.world > 1 and not windowed:
                 for vw in self._overlap_views(adj):
                     vw.zero_()
-        if self.fuse and self.overlap == "none":
-            # three kernels + the exchange per substep: [plasticity bwd + adjoint scatter] [exchange] [node pass]
-            # [adjoint gather + elasticity bwd]; two scatter targets in turn, so that the clear for substep
-            # s - 1 runs beside substep s (as FusedFrame._sim_backward, fuse_bwd = "full")
+        if self.fuse and self.overlap in ("none", "split"):
+            # [plasticity bwd + adjoint scatter] [exchange] [node pass] [adjoint gather + elasticity bwd]; two
+            # scatter targets in turn, so that the clear for substep s - 1 runs beside substep s (as
+            # FusedFrame._sim_backward, fuse_bwd = "full").  split: the exchange (and that clear) run on the side
+            # stream under the interior range's plasticity kernel.
             adjs = (self.adj, self.adj2)
+            split = self.overlap == "split"
             clear(self.S - 1, adjs[(self.S - 1) & 1])
             for s in reversed(range(self.S)):
                 gx2, gv2, gC2, gF_next = self.g[cur]
                 gxo, gvo, gCo, gFo = self.g[nxt]
                 adj = adjs[s & 1]
-                if s > 0:
+                if s > 0:            # the other target's clear: beside the first kernel of this substep
                     self._side.wait_stream(main)
                     with torch.cuda.stream(self._side):
                         clear(s - 1, adjs[(s - 1) & 1])
-                ops.constitutive_bwd_scatter(self.Ftrial[s], self.Wp_st, self.alpha, gF_next, self.gFtrial,
-                                             self.gWp_part, c, self.x[s], self.F[s], self.clip, self.enabled,
-                                             self.v[s + 1], gx2, gv2, gC2, adj, box=self.box[s])
-                self._exchange(adj, self.box[s])
+                if split:
+                    self._plastic_bwd_scatter(c, s, 0, self.split_bwd, gx2, gv2, gC2, gF_next, adj)
+                    self._side.wait_stream(main)
+                    with torch.cuda.stream(self._side):
+                        self._exchange(adj, self.box[s])
+                    self._plastic_bwd_scatter(self.c_chk, s, self.split_bwd, self.n, gx2, gv2, gC2, gF_next, adj)
+                    main.wait_stream(self._side)
+                else:
+                    self._plastic_bwd_scatter(c, s, 0, self.n, gx2, gv2, gC2, gF_next, adj)
+                    self._exchange(adj, self.box[s])
                 ops.mpm_bwd_node(c, self.grid[s], adj, self.box[s])
                 ops.constitutive_bwd_gather(self.kind_e, self.We_st, self.gWe_part, c, self.x[s], self.v[s], self.C[s],
                                             self.F[s], self.stress[s], self.vol, self.rho, self.clip, self.enabled,
                                             self.v[s + 1], self.C[s + 1], gx2, gv2, gC2, self.gFtrial, self.grid[s],
                                             adj, gxo, gvo, gCo, gFo, self.gstress, box=self.box[s])
-                if s > 0:
+                if s > 0 and not split:
                     main.wait_stream(self._side)
                 cur, nxt = nxt, cur
             return
@@ -593,11 +611,11 @@ class SlabRollout:
                     main.wait_stream(self._side)
                     node_gather(c)
             elif self.overlap == "split":
-                self._plastic_bwd_scatter(c, s, 0, self.nb, gx2, gv2, gC2, gF_next)
+                self._plastic_bwd_scatter(c, s, 0, self.split_bwd, gx2, gv2, gC2, gF_next)
                 self._side.wait_stream(main)
                 with torch.cuda.stream(self._side):
                     self._exchange(self.adj, self.box[s])           # the ONE exchange of the backward substep
-                self._plastic_bwd_scatter(self.c_chk, s, self.nb, self.n, gx2, gv2, gC2, gF_next)
+                self._plastic_bwd_scatter(self.c_chk, s, self.split_bwd, self.n, gx2, gv2, gC2, gF_next)
                 main.wait_stream(self._side)
                 node_gather(c)
             else:

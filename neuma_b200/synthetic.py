@@ -24,6 +24,9 @@ WORKLOADS = {
     "jellyduck-100k-128": dict(n=100_000, G=128, box=((0.3, 0.7),) * 3, K=50_000, image=800, dt=2.5e-4),
     "claycat-200k-128": dict(n=200_000, G=128, box=((0.25, 0.75),) * 3, K=100_000, image=800, dt=2.5e-4),
     "block-1m-256": dict(n=1_000_000, G=256, box=((0.2, 0.8), (0.2, 0.8), (0.1, 0.9)), K=0, image=0, dt=1.25e-4),
+    # a quarter of block-1m-256 along z at the same density: on 2 GPUs each rank carries what a rank of the
+    # 8-GPU run carries (125 k particles) -- the development proxy for the 8-GPU slab behaviour
+    "block-250k-256": dict(n=250_000, G=256, box=((0.2, 0.8), (0.2, 0.8), (0.4, 0.6)), K=0, image=0, dt=1.25e-4),
 }
 
 
