@@ -579,6 +579,9 @@ def slab_measure(dev, world: int, rank: int, substeps: int, steps: int, warmup: 
                 sim.overlap, sim._graphs = mode, {}
                 by_mode[mode] = time_ms(sim, g, True)
         out["ms_per_frame_by_overlap"] = by_mode
+        if "split" in by_mode:   # what the split LAUNCHES cost by themselves (no exchange kernel at all)
+            sim.overlap, sim.skip_exchange, sim._graphs = "split", True, {}
+            out["ms_per_frame_split_no_exchange"] = time_ms(sim, g, True)
         sim.overlap, sim.skip_exchange, sim._graphs = "none", True, {}
         ms0 = time_ms(sim, g, True)
         out["ms_per_frame_no_exchange"] = ms0
