@@ -164,7 +164,7 @@ def run_gpu(args):
     x0, v0, C0, F0 = [t.clone() for t in pre.sim_forward()]
     del pre
     eng = FusedFrame(n, cc, statics, We, Wp, wl["w"]["alpha"], S, dev, bind=bind, gaussians=gs, settings=settings,
-                     fuse=args.fuse)
+                     fuse=args.fuse, save_svd=args.save_svd)
     eng.load_state(x0, v0, C0, F0)
     k_prev = g["xyz"].to(dev)
     de_x_prev = d["x"].clone()
@@ -173,7 +173,7 @@ def run_gpu(args):
 
     # launches per frame: count one eager (un-graphed) frame with the library's own counter
     eager = FusedFrame(n, cc, statics, We, Wp, wl["w"]["alpha"], S, dev, bind=bind, gaussians=gs,
-                       settings=settings, use_graphs=False, fuse=args.fuse)
+                       settings=settings, use_graphs=False, fuse=args.fuse, save_svd=args.save_svd)
     eager.load_state(x0, v0, C0, F0)
     l0 = ctx.launches
     eager.frame_fwd_bwd(gt, de_x_prev, k_prev)
@@ -710,6 +710,8 @@ def main():
                     help="A/B: epilogue = P2G / the adjoint scatter ride in the constitutive kernels; full = also G2P "
                          "and the adjoint gather (3 kernels per substep each way); best (default) = epilogue forward, "
                          "full backward; none = every stage its own kernel")
+    ap.add_argument("--save-svd", action="store_true",
+                    help="A/B: the forward constitutive kernels save V, the backward ones skip the Jacobi iteration")
     ap.add_argument("--no-dropin", action="store_true", help="skip the drop-in (autograd classes) measurement")
     ap.add_argument("--no-slab", action="store_true", help="skip the Z-slab (config 5) section of the line")
     ap.add_argument("--slab-steps", type=int, default=5, help="timed frames of the Z-slab section")

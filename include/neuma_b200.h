@@ -351,6 +351,12 @@ int neuma_constitutive_bwd_scatter(neuma_ctx* ctx, int n, int hidden, const floa
                                    const float* clip_bound, const int32_t* enabled, const float* v2,
                                    const float* gx2, const float* gv2, const float* gC2, const int32_t* box,
                                    float* adj, void* stream);
+/* Rollouts evaluate the backward of a net on exactly the rows its forward saw (finetune.py:360-414): the
+ * forward can hand the right singular vectors V of every input row (9 floats per particle) to the backward,
+ * which then skips the Jacobi iteration of the 3x3 SVD (warp/svd.py:59-96 recomputes U, sigma, V^T from the
+ * saved tensors as well).  Applies to the NEXT constitutive launch on this ctx only, whichever entry point:
+ * a forward kernel writes v_out[n][9] (if not NULL), a backward kernel reads v_in[n][9] (if not NULL). */
+int neuma_constitutive_svd_cache(neuma_ctx* ctx, float* v_out, const float* v_in);
 int neuma_constitutive_fwd_g2p(neuma_ctx* ctx, int n, int hidden, const void* staged, float alpha, float* F_out,
                                const neuma_mpm_const* c, const float* x, const float* F, const float* clip_bound,
                                const int32_t* enabled, const int32_t* box, const float* grid, float* x2, float* v2,

@@ -109,6 +109,7 @@ SIGNATURES = {
     "neuma_constitutive_fwd_g2p": [_P, _I, _I, _P, _F, _P, _CP] + [_P] * 12,
     "neuma_constitutive_bwd_gather": [_P, _I, _I, _I, _P, _P, _CP] + [_P] * 24,
     "neuma_constitutive_reduce_partials": [_P, _I, _P, _P, _P, _P, _P],
+    "neuma_constitutive_svd_cache": [_P, _P, _P],
     "neuma_bind_spmm": [_P, _I, _I, _P, _P, _P, _I, _P, _P, _I, _P],
     "neuma_particles_to_gaussians": [_P, _I] + [_P] * 15,
     "neuma_gaussians_to_particles": [_P, _I] + [_P] * 8,

@@ -32,6 +32,9 @@ struct neuma_ctx {
   RasterState* raster;
   int attrs_set;  // cudaFuncSetAttribute (opt-in shared memory) is per DEVICE: tracked per ctx
   int rollout_attrs_set;
+  // neuma_constitutive_svd_cache: consumed by the NEXT constitutive launch on this ctx
+  float* svd_v_out;        // forward kernels: the right singular vectors of every input row go here
+  const float* svd_v_in;   // backward kernels: read them instead of running the Jacobi iteration
 };
 
 static inline int neuma_fail(neuma_ctx* ctx, const char* what, cudaError_t e) {

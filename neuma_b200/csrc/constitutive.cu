@@ -103,6 +103,30 @@ __device__ __forceinline__ void kinematics(const Mat3& F, bool normalize, Kinema
     for (int j = 0; j < 3; ++j) k.feat[3 + 3 * i + j] = FtF(i, j) - ((i == j) ? sub : 0.0f);
   k.feat[12] = mat3_det(k.F) - sub;
 }
+// The same with the right singular vectors V of F already known (saved by the forward kernel): only
+// the sort-free tail of the SVD (U and sigma from F V by Gram-Schmidt) is left -- the Jacobi sweeps were
+// 16 % of a backward tile's latency.  V is the SORTED V the forward produced, so the tail's column sort is
+// a no-op and U, sigma come out as in the forward.
+__device__ __forceinline__ void kinematics_from_v(const Mat3& F, const float* __restrict__ Vrow, bool normalize,
+                                                  Kinematics& k) {
+  k.F = F;
+  float V[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) V[i][j] = Vrow ? Vrow[3 * i + j] : ((i == j) ? 1.0f : 0.0f);
+  svd3_finish(k.F, V, k.U, k.sig, k.V);
+  k.R = mat3_mul_nt(k.U, k.V);
+  const Mat3 FtF = mat3_mul_tn(k.F, k.F);
+  const float sub = normalize ? 1.0f : 0.0f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) k.feat[i] = k.sig[i] - sub;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) k.feat[3 + 3 * i + j] = FtF(i, j) - ((i == j) ? sub : 0.0f);
+  k.feat[12] = mat3_det(k.F) - sub;
+}
 __device__ __forceinline__ Mat3 load_F_or_identity(const float* __restrict__ F, int p, int n) {
   Mat3 m;
   if (p < n) {
@@ -519,7 +543,8 @@ __device__ __forceinline__ void box_accumulate_warp(const neuma_mpm_const& c, bo
 template <int RT>
 __global__ void __launch_bounds__(fwd_threads<RT>(), 1)
 constitutive_fwd_kernel(int kind, int n, const float* __restrict__ F, const uint8_t* __restrict__ staged,
-                        float alpha, float* __restrict__ out, const FusedP2G fp, const FusedG2P fg) {
+                        float alpha, float* __restrict__ out, const FusedP2G fp, const FusedG2P fg,
+                        float* __restrict__ vsave) {
   constexpr int NS = NS_FWD, NPIPE = NPIPE_FWD, PW = 4 * RT;  // PW = warps per pipeline
   using W = WImg<NS>;
   using P = PipeFwd<NS>;
@@ -601,6 +626,7 @@ constitutive_fwd_kernel(int kind, int n, const float* __restrict__ F, const uint
         if (!have_F) Fin = load_F_or_identity(F, pi, n);
         Kinematics k;
         kinematics(Fin, kind != 2, k);
+        if (vsave && pi < n) mat3_store(vsave + (size_t)pi * 9, k.V);
         kF = k.F;
         kR = k.R;
         float f[KF];
@@ -652,7 +678,8 @@ __global__ void __launch_bounds__(bwd_threads<RT>(), 1)
 constitutive_bwd_kernel(int kind, int n, const float* __restrict__ F, const uint8_t* __restrict__ staged,
                         float alpha, const float* __restrict__ gout, float* __restrict__ gF,
                         float* __restrict__ gW0, float* __restrict__ gW1, float* __restrict__ gW2,
-                        float* __restrict__ gWpart, int accumulate_gF, const FusedScatter fs, const FusedGather fa) {
+                        float* __restrict__ gWpart, int accumulate_gF, const FusedScatter fs, const FusedGather fa,
+                        const float* __restrict__ vin) {
   constexpr int NS = NS_BWD, NPIPE = NPIPE_BWD, PW = 4 * RT;  // PW = warps per pipeline
   using W = WImg<NS>;
   using P = PipeBwd<NS>;
@@ -764,7 +791,11 @@ constitutive_bwd_kernel(int kind, int n, const float* __restrict__ F, const uint
                                            fa.adj, fa.gx, fa.gv, fa.gC, gF, fa.gstress);
       }
       Kinematics k;
-      if (owner) kinematics(load_F_or_identity(F, pi, n), kind != 2, k);
+      if (owner) {
+        // vin: warp-uniform choice (svd3_fast votes across the warp); padding rows take V = I
+        if (vin) kinematics_from_v(load_F_or_identity(F, pi, n), live ? vin + (size_t)pi * 9 : nullptr, kind != 2, k);
+        else kinematics(load_F_or_identity(F, pi, n), kind != 2, k);
+      }
       PHASE(0);
       // FEAT / BIGA were last read by the previous tile's dW0 GEMM
       if (WGRAD && !first) ps.wait_wdone();
@@ -795,6 +826,7 @@ constitutive_bwd_kernel(int kind, int n, const float* __restrict__ F, const uint
       if (owner) {
         if (!fa.grid) prefetch_row(gout, pi, n);
         prefetch_row(F, pi + chains * TP, n);
+        if (vin) prefetch_row(vin, pi + chains * TP, n);
       }
       PHASE(1);
       ps.wait_done();
@@ -1188,12 +1220,14 @@ int launch_fwd(neuma_ctx* ctx, int kind, int n, const float* F, const void* stag
                const FusedP2G& fp, const FusedG2P& fg, cudaStream_t st) {
   const int tiles = (n + TP - 1) / TP;
   const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
+  float* vsave = ctx->svd_v_out;       // neuma_constitutive_svd_cache: consumed by this launch
+  ctx->svd_v_out = nullptr;
   if (row_threads() == 2)
     NEUMA_CUDA(ctx, neuma_launch(constitutive_fwd_kernel<2>, dim3(grid), dim3(fwd_threads<2>()), FWD_SMEM, st, kind, n,
-                                 F, (const uint8_t*)staged, alpha, out, fp, fg));
+                                 F, (const uint8_t*)staged, alpha, out, fp, fg, vsave));
   else
     NEUMA_CUDA(ctx, neuma_launch(constitutive_fwd_kernel<1>, dim3(grid), dim3(fwd_threads<1>()), FWD_SMEM, st, kind, n,
-                                 F, (const uint8_t*)staged, alpha, out, fp, fg));
+                                 F, (const uint8_t*)staged, alpha, out, fp, fg, vsave));
   NEUMA_LAUNCH_CHECK(ctx, "constitutive_fwd_kernel");
   return 0;
 }
@@ -1204,10 +1238,12 @@ int launch_bwd(neuma_ctx* ctx, bool wgrad, int kind, int n, const float* F, cons
   const int tiles = (n + TP - 1) / TP;
   const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
   const uint8_t* sg = (const uint8_t*)staged;
+  const float* vin = ctx->svd_v_in;    // neuma_constitutive_svd_cache: consumed by this launch
+  ctx->svd_v_in = nullptr;
 #define NEUMA_BWD(WG, RTV)                                                                                       \
   NEUMA_CUDA(ctx, neuma_launch(constitutive_bwd_kernel<WG, RTV>, dim3(grid), dim3(bwd_threads<RTV>()),            \
                                bwd_smem<RTV>(), st, kind, n, F, sg, alpha, gout, gF, gW0, gW1, gW2, gWpart,       \
-                               accumulate_gF, fs, fa))
+                               accumulate_gF, fs, fa, vin))
   if (row_threads() == 2) {
     if (wgrad) NEUMA_BWD(true, 2); else NEUMA_BWD(false, 2);
   } else {
@@ -1250,6 +1286,13 @@ int neuma_svd3_bwd(neuma_ctx* ctx, int n, const float* U, const float* sigma, co
 }
 
 int neuma_constitutive_staged_bytes(void) { return (int)STAGED_BYTES; }
+
+int neuma_constitutive_svd_cache(neuma_ctx* ctx, float* v_out, const float* v_in) {
+  if (!ctx) return 2;
+  ctx->svd_v_out = v_out;
+  ctx->svd_v_in = v_in;
+  return 0;
+}
 
 #ifdef NEUMA_PHASE_TIMING
 int neuma_debug_phase_cycles(long long* out_host, int reset) {

@@ -442,6 +442,14 @@ def constitutive_bwd_gather(kind: int, staged, gWpart, c: MPMConstC, x, v, Cm, F
                  ptr(gv), ptr(gC), ptr(gF), ptr(gstress), _stream(x))
 
 
+def constitutive_svd_cache(like: torch.Tensor, v_out: Optional[torch.Tensor] = None,
+                           v_in: Optional[torch.Tensor] = None) -> None:
+    """The NEXT constitutive launch on `like`'s device writes the right singular vectors of its input
+    rows to v_out [n, 3, 3] (forward kernels) / reads them from v_in and skips the Jacobi iteration
+    (backward kernels) -- neuma_constitutive_svd_cache."""
+    _ctx(like).call("neuma_constitutive_svd_cache", ptr(v_out), ptr(v_in))
+
+
 def constitutive_reduce_partials(gWpart, gW0, gW1, gW2, hidden: int = 64) -> None:
     """gW* += sum of the slots; the slots are zeroed."""
     _ctx(gWpart).call("neuma_constitutive_reduce_partials", hidden, ptr(gWpart), ptr(gW0), ptr(gW1), ptr(gW2),

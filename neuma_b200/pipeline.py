@@ -41,7 +41,7 @@ class FusedFrame:
                  elastic_kind: int = ops.KIND_ELASTIC, use_graphs: bool = True, sort: bool = True,
                  compact: bool = True, grid_margin: int = 6, cap_nodes: Optional[int] = None, fuse=True,
                  frames: int = 1, views: Optional[Sequence[RasterSettingsC]] = None, loss: str = "l2",
-                 force_mask_data: bool = False):
+                 force_mask_data: bool = False, save_svd: Optional[bool] = None):
         """frames: rendered frames this engine rolls out before ONE backward over all of them
         (finetune.py:360-414: loss.backward() comes after nsteps = frames x substeps substeps); the state
         of every substep of every frame stays resident.  views: one GaussianRasterizationSettings per
@@ -52,6 +52,11 @@ class FusedFrame:
         load_state() from that state's box widened by `grid_margin` nodes on every side (room for
         the cloud to move / deform over the frames this engine will see), or given as cap_nodes.
         A later box that does not fit is reported by check() -- nothing is written out of bounds.
+        save_svd: the forward constitutive kernels keep the right singular vectors V of their inputs
+        (2 x 36 B per particle and substep) and the backward kernels skip the Jacobi iteration of the SVD
+        (neuma_constitutive_svd_cache).  Measured (profiles/r03s_save_svd_ab.txt): backward -0.045 ms,
+        forward +0.05 ms per frame at 100 k / S = 20 -- the Jacobi sweeps are not on the exposed path -- so
+        it is OFF by default.
         fuse: which MPM stages ride inside the constitutive kernels.  "epilogue" = the two scatters (P2G after
         elasticity, the adjoint scatter after the plasticity backward); "full" = also G2P in front of
         plasticity and the adjoint gather in front of the elasticity backward (three kernels per substep
@@ -93,6 +98,9 @@ class FusedFrame:
         self.F = torch.empty(T + 1, n, 3, 3, **f)
         self.stress = torch.empty(T, n, 3, 3, **f)
         self.Ftrial = torch.empty(T, n, 3, 3, **f)
+        self.save_svd = bool(save_svd)
+        self.Ve = torch.empty(T, n, 3, 3, **f) if self.save_svd else None     # V of F[s] (elasticity input)
+        self.Vp = torch.empty(T, n, 3, 3, **f) if self.save_svd else None     # V of F_trial[s] (plasticity input)
         # adjoint buffers (ping-pong) and weight-gradient accumulators
         self.g = [[torch.zeros(n, 3, **f), torch.zeros(n, 3, **f), torch.zeros(n, 3, 3, **f),
                    torch.zeros(n, 3, 3, **f)] for _ in range(2)]
@@ -141,7 +149,7 @@ class FusedFrame:
 
     def memory_bytes_per_substep(self) -> dict:
         """What one substep of the rollout keeps resident for the backward."""
-        particle = 4 * (3 + 3 + 9 + 9 + 9 + 9) * self.n          # x, v, C, F, stress, F_trial
+        particle = 4 * (3 + 3 + 9 + 9 + 9 + 9 + (18 if self.save_svd else 0)) * self.n   # x, v, C, F, stress, F_trial (+ 2 V)
         grid = 0 if self.grid is None else 16 * self.cap_nodes
         return {"particle_state": particle, "grids": grid, "per_particle": (particle + grid) / max(self.n, 1)}
 
@@ -163,10 +171,12 @@ class FusedFrame:
             # [G2P + plasticity] (csrc/constitutive.cu FusedP2G / FusedG2P, mpm_rollout.cu grid_op_box_kernel)
             ops.mpm_box_clear(c, self.box[s0], self.grid[s0], None, None)
             for s in range(s0, s1):
+                self._svd_out(self.Ve, s)
                 ops.constitutive_fwd_p2g(self.kind_e, self.F[s], self.We_st, self.stress[s], c, self.x[s], self.v[s],
                                          self.C[s], self.vol, self.rho, self.enabled, self.grid[s], box=self.box[s])
                 ops.mpm_grid_op_box(c, self.box[s], self.grid[s], None,
                                     next_grid=self.grid[s + 1] if s + 1 < s1 else None, box_reset=self.box[s + 1])
+                self._svd_out(self.Vp, s)
                 ops.constitutive_fwd_g2p(self.Wp_st, self.alpha, self.F[s + 1], c, self.x[s], self.F[s], self.clip,
                                          self.enabled, self.grid[s],
                                          (self.x[s + 1], self.v[s + 1], self.C[s + 1], self.Ftrial[s]),
@@ -174,6 +184,7 @@ class FusedFrame:
             return
         ops.mpm_box_clear(c, self.box[s0], self.grid[s0], None, self.box[s0 + 1])
         for s in range(s0, s1):
+            self._svd_out(self.Ve, s)
             if self.fuse_fwd:
                 # elasticity + P2G in ONE kernel: the particle is scattered by the thread that just
                 # computed its stress (csrc/constitutive.cu, FusedP2G)
@@ -193,9 +204,18 @@ class FusedFrame:
                 self._side.wait_stream(main)
                 with torch.cuda.stream(self._side):
                     ops.mpm_box_clear(c, self.box[s + 1], self.grid[s + 1], None, self.box[s + 2])
+            self._svd_out(self.Vp, s)
             ops.constitutive_fwd_staged(ops.KIND_PLASTIC, self.Ftrial[s], self.Wp_st, self.alpha, self.F[s + 1])
             if s + 1 < s1:
                 main.wait_stream(self._side)
+
+    def _svd_out(self, buf, s: int) -> None:
+        if buf is not None:
+            ops.constitutive_svd_cache(self.x, v_out=buf[s])
+
+    def _svd_in(self, buf, s: int) -> None:
+        if buf is not None:
+            ops.constitutive_svd_cache(self.x, v_in=buf[s])
 
     def _sim_backward(self, frame: int = 0) -> None:
         """Consumes self.g[0] = dL/d(state after frame `frame`); leaves dL/d(state at its start) in
@@ -218,6 +238,7 @@ class FusedFrame:
                 with torch.cuda.stream(self._side):
                     ops.mpm_box_clear(c, self.box[s - 1], adjs[(s - 1) & 1], None, None)
             # plasticity: F[s+1] = P(Ftrial[s]); then adj(G2P) scatters dL/dv_node into adj
+            self._svd_in(self.Vp, s)
             if self.fuse_bwd:
                 ops.constitutive_bwd_scatter(self.Ftrial[s], self.Wp_st, self.alpha, gF_next, self.gFtrial,
                                              self.gWp_part, c, self.x[s], self.F[s], self.clip, self.enabled,
@@ -230,6 +251,7 @@ class FusedFrame:
             if full:
                 # [node pass] [adjoint gather + elasticity backward]
                 ops.mpm_bwd_node(c, self.grid[s], adj, self.box[s])
+                self._svd_in(self.Ve, s)
                 ops.constitutive_bwd_gather(self.kind_e, self.We_st, self.gWe_part, c, self.x[s], self.v[s], self.C[s],
                                             self.F[s], self.stress[s], self.vol, self.rho, self.clip, self.enabled,
                                             self.v[s + 1], self.C[s + 1], gx2, gv2, gC2, self.gFtrial, self.grid[s],
@@ -248,6 +270,7 @@ class FusedFrame:
                 with torch.cuda.stream(self._side):
                     ops.mpm_box_clear(c, self.box[s - 1], self.adj, None, None)
             # elasticity: stress[s] = E(F[s]);  dL/dF[s] += E'(F[s])^T gstress
+            self._svd_in(self.Ve, s)
             ops.constitutive_bwd_partials(self.kind_e, self.F[s], self.We_st, 0.0, self.gstress, gF,
                                           self.gWe_part, accumulate_gF=True)
             if s > s0:

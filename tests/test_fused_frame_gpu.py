@@ -88,6 +88,30 @@ def test_fuse_modes_agree(cuda_dev, compact):
             assert rel_err(a, b) < 1e-4, fuse
 
 
+def test_saved_singular_vectors_equal_recomputed_svd(cuda_dev):
+    """save_svd: the backward kernels read the forward's right singular vectors and run only the
+    Gram-Schmidt tail of the SVD -- same U, sigma, V, so the same gradients as the full recompute."""
+    from neuma_b200.pipeline import FusedFrame
+    spec, cc, d, W, alpha, settings, bind, gs, F0, gt, kxyz = _setup(cuda_dev, n=4000)
+    runs = {}
+    for save in (False, True):
+        for fuse in (True, False):
+            eng = FusedFrame(spec["n"], cc, (d["vol"], d["rho"], d["clip"], d["enabled"]), W["elastic"], W["plastic"],
+                             alpha, 4, cuda_dev, bind=bind, gaussians=gs, settings=settings, use_graphs=False,
+                             save_svd=save, fuse=fuse)
+            eng.load_state(d["x"], d["v"], d["C"], F0)
+            eng.zero_weight_grads()
+            loss, g0 = eng.frame_fwd_bwd(gt, d["x"].clone(), kxyz)
+            runs[(save, fuse)] = (loss.clone(), [t.clone() for t in g0], [t.clone() for t in eng.gWe + eng.gWp])
+    ref = runs[(False, False)]
+    for key, (loss, g0, gW) in runs.items():
+        assert float(loss) == float(ref[0]), key                # the forward is untouched
+        for a, b in zip(g0, ref[1]):
+            assert rel_err(a, b) < 1e-4, key
+        for a, b in zip(gW, ref[2]):
+            assert rel_err(a, b) < 1e-4, key
+
+
 def test_full_fusion_flags_a_particle_crossing_more_than_a_cell(cuda_dev):
     """fuse="full" clears the next grid slot over the current box dilated by ONE node; a particle that
     leaves that region in one substep must raise check() instead of scattering into stale nodes."""
