@@ -28,8 +28,10 @@ def _views(IM, eyes, bg=1.0):
     return cs, os_
 
 
-@pytest.mark.parametrize("loss,mask,graphs", [("l2", False, True), ("l1", False, False), ("l2", True, True)])
-def test_rollout_views_weights_exclusion_against_oracle(cuda_dev, loss, mask, graphs):
+@pytest.mark.parametrize("loss,mask,graphs,fuse", [("l2", False, True, True), ("l1", False, False, True),
+                                                   ("l2", True, True, True), ("l2", False, True, "full"),
+                                                   ("l1", False, False, "epilogue")])
+def test_rollout_views_weights_exclusion_against_oracle(cuda_dev, loss, mask, graphs, fuse):
     from neuma_b200.pipeline import FusedFrame
     from oracle import mpm_oracle as MO, pipeline_oracle as PO
     n, G, IM, Ssub, frames = 1500, 32, 48, 2, 3
@@ -44,7 +46,7 @@ def test_rollout_views_weights_exclusion_against_oracle(cuda_dev, loss, mask, gr
     weights = [1.0, 0.8, 0.64]                           # decay_rate ** ((cur_step - 1) // decay_steps)
     eng = FusedFrame(n, cc, (d["vol"], d["rho"], d["clip"], d["enabled"]), W["elastic"], W["plastic"], alpha, Ssub,
                      cuda_dev, bind=bind, gaussians=gs, views=views, center=center, size=size, frames=frames,
-                     loss=loss, force_mask_data=mask, use_graphs=graphs)
+                     loss=loss, force_mask_data=mask, use_graphs=graphs, fuse=fuse, save_svd=(fuse == "full"))
     dev_gts = [None if g is None else [t.to(cuda_dev) for t in g] for g in gts]
     for rep in range(2):                                 # the second epoch replays the captured graphs
         eng.load_state(d["x"], d["v"], d["C"], F0)
