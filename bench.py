@@ -477,15 +477,21 @@ def dropin_measure(wl, dev, state0, steps: int = 5, warmup: int = 2, cache_merge
     for _ in range(warmup):
         frame()
     torch.cuda.synchronize()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(steps):
-        loss = frame()
-    b.record()
-    b.synchronize()
-    ms = a.elapsed_time(b) / steps
+    # this path is bound by the HOST (Python / autograd launch overhead, ~15 ms per frame): three timed blocks,
+    # the best one is reported and all three are listed -- a busy host core shows up as a slow block
+    blocks = []
+    for _ in range(3):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            loss = frame()
+        b.record()
+        b.synchronize()
+        blocks.append(a.elapsed_time(b) / steps)
+    ms = min(blocks)
     model.check(sim.curr_states)
-    return {"frames_per_s": 1000.0 / ms, "ms_per_frame": ms, "loss": float(loss.detach()), "steps": steps,
+    return {"frames_per_s": 1000.0 / ms, "ms_per_frame": ms, "ms_per_frame_blocks": blocks,
+            "loss": float(loss.detach()), "steps": steps,
             "api": "neuma_b200.sim.MPMCacheDiffSim + material.InvariantFullMeta* (LoRA r16, autograd) + glue."
                    "diff_rasterization: the reference's finetune.py loop with the import swap only"}
 

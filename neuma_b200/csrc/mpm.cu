@@ -59,10 +59,9 @@ grid_op_kernel(neuma_mpm_const c, const float4* __restrict__ grid, float4* __res
 // ------------------------------------------------------------------ G2P
 template <bool LAZY>
 __global__ void __launch_bounds__(256)
-g2p_kernel(neuma_mpm_const c, int n, const float* __restrict__ x, const float* __restrict__ F,
+g2p_kernel(neuma_mpm_const c, int n, const float* x, const float* F,   // x2.. may alias x.. (in-place step)
            const float* __restrict__ clip, const int* __restrict__ enabled,
-           const float4* __restrict__ grid, float* __restrict__ x2, float* __restrict__ v2,
-           float* __restrict__ C2, float* __restrict__ F2) {
+           const float4* __restrict__ grid, float* x2, float* v2, float* C2, float* F2) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
   if (enabled[p] == 0) return;

@@ -294,13 +294,15 @@ __device__ __forceinline__ void p2g_particle(const neuma_mpm_const& c, const Gri
 // ---- G2P: one particle (mpm.py:432-498).  LAZY: the grid holds (mv, m) and grid_op is
 // evaluated per gathered node; otherwise it holds v.  Writes x', v', C', F'; returns x' in nx3 and,
 // when Fret is given, F' in registers (the fused plasticity kernel goes on with it).
+// x2 / F2 MAY ALIAS x / F (MPMForwardSim steps in place, interface.py:133): no __restrict__ on them, and the
+// row of F is read into registers before anything is written.
 template <bool LAZY>
 __device__ __forceinline__ void g2p_particle(const neuma_mpm_const& c, const GridMap& gm, int p,
-                                             const float* __restrict__ x, const float* __restrict__ F,
+                                             const float* x, const float* F,
                                              const float* __restrict__ clip,
-                                             const float4* __restrict__ grid, float* __restrict__ x2,
-                                             float* __restrict__ v2, float* __restrict__ C2,
-                                             float* __restrict__ F2, float nx3[3], float* Fret = nullptr) {
+                                             const float4* __restrict__ grid, float* x2,
+                                             float* v2, float* C2,
+                                             float* F2, float nx3[3], float* Fret = nullptr) {
   const float px[3] = {x[3 * p], x[3 * p + 1], x[3 * p + 2]};
   const Stencil s = make_stencil(px[0], px[1], px[2], c.inv_dx);
   float nv[3] = {0.f, 0.f, 0.f};
