@@ -32,8 +32,8 @@ bool neuma_pdl_enabled() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("NEUMA_PDL");
-    v = (e && e[0] == '1') ? 1 : 0;  // off by default: measured -1.7 % forward, +3 % backward (profiles/r01s)
-  }
+    v = (e && e[0] == '0') ? 0 : 1;  // on by default since the constitutive kernels stopped triggering early
+  }                                  // (profiles/r03y_pdl_ab.txt: +2.1 % frames/s); NEUMA_PDL=0 turns it off
   return v != 0;
 }
 

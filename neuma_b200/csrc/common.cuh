@@ -65,9 +65,14 @@ static inline int neuma_fail_msg(neuma_ctx* ctx, const char* what) {
 // the stream is scheduled as soon as every CTA of this one has started (launch_dependents at
 // the top), runs its prologue (barrier init, TMEM allocation, index math) while this one
 // drains, and blocks in pdl_wait() until this grid has completed and its writes are visible.
-// Semantics are those of ordinary stream order.  OFF unless NEUMA_PDL=1: on the B200 it bought
-// 1.7 % on the forward graph and cost 3 % on the backward one (early-resident dependents compete
-// with the persistent constitutive CTAs), see profiles/r01s_pdl_ab.txt.
+// Semantics are those of ordinary stream order.  EVERY kernel launched through neuma_launch() must call
+// pdl_wait() (pdl_prologue()) before it touches anything a predecessor wrote.
+// Round 1 had every kernel trigger at its top: +1.7 % on the forward graph, -3 % on the backward one (the
+// kernel after a persistent constitutive kernel then sits resident beside it for its whole duration) -> off.
+// Now the SMALL kernels trigger early and the constitutive kernels do not: a constitutive kernel that
+// follows a small one (plasticity after G2P, elasticity backward after the node pass) runs its prologue
+// (barriers, TMEM allocation) on the SMs the small kernel has already left.  Forward graph -5.7 %,
+// backward -0.4 %, frame +2.1 % (profiles/r03y_pdl_ab.txt): ON by default, NEUMA_PDL=0 disables.
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_launch_dependents() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");

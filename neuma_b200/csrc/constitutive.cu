@@ -428,7 +428,10 @@ __device__ __forceinline__ uint32_t block_setup(Bars* bars, uint32_t* tmem_slot,
                                                 const uint8_t* __restrict__ staged, uint32_t w_bytes,
                                                 uint32_t tmem_cols, uint32_t pipe_threads) {
   const int warp = threadIdx.x >> 5;
-  pdl_launch_dependents();
+  // no early griddepcontrol.launch_dependents here: the kernel that follows a persistent constitutive kernel
+  // would sit resident next to it for its whole duration (measured: +3 % on the backward graph, profiles/r01s);
+  // the small kernels DO trigger early, so that THIS kernel's CTAs run the prologue below on the SMs the
+  // previous kernel has already left
   if (threadIdx.x == 0) {
     umma::mbar_init(umma::smem_u32(&bars->w), 1);
 #pragma unroll
@@ -778,6 +781,10 @@ constitutive_bwd_kernel(int kind, int n, const float* __restrict__ F, const uint
     bool first = true;
     PHASE_T0();
     for (int tile = p * gridDim.x + blockIdx.x; tile < tiles; tile += chains, first = false) {
+      // LATE trigger of the dependent kernel (see common.cuh): when this CTA's first pipeline starts its last
+      // tile -- the small kernel that follows becomes resident during the tail, not during the whole kernel.
+      // Backward only: measured -0.04 ms per frame here, +0.025 ms in the forward kernel (profiles/r03y_pdl_ab.txt)
+      if (tid == 0 && tile + chains >= tiles) pdl_launch_dependents();
       const int pi = tile * TP + r;
       const bool live = pi < n;
       if (owner && fa.grid && live) {

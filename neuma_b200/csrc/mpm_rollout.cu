@@ -170,6 +170,7 @@ p2g_tiled_kernel(neuma_mpm_const c, int n, const float* __restrict__ x, const fl
                  const float* __restrict__ vol, const float* __restrict__ rho,
                  const int* __restrict__ enabled, const int32_t* __restrict__ box,
                  float4* __restrict__ grid) {
+  pdl_prologue();
   __shared__ float4 tile[PT_NODES];
   __shared__ int s_lo[3];
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
