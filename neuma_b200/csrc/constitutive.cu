@@ -1227,8 +1227,9 @@ int launch_fwd(neuma_ctx* ctx, int kind, int n, const float* F, const void* stag
                const FusedP2G& fp, const FusedG2P& fg, cudaStream_t st) {
   const int tiles = (n + TP - 1) / TP;
   const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
-  float* vsave = ctx->svd_v_out;       // neuma_constitutive_svd_cache: consumed by this launch
+  float* vsave = ctx->svd_v_out;       // neuma_constitutive_svd_cache: consumed by this launch (either pointer)
   ctx->svd_v_out = nullptr;
+  ctx->svd_v_in = nullptr;
   if (row_threads() == 2)
     NEUMA_CUDA(ctx, neuma_launch(constitutive_fwd_kernel<2>, dim3(grid), dim3(fwd_threads<2>()), FWD_SMEM, st, kind, n,
                                  F, (const uint8_t*)staged, alpha, out, fp, fg, vsave));
@@ -1245,8 +1246,9 @@ int launch_bwd(neuma_ctx* ctx, bool wgrad, int kind, int n, const float* F, cons
   const int tiles = (n + TP - 1) / TP;
   const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
   const uint8_t* sg = (const uint8_t*)staged;
-  const float* vin = ctx->svd_v_in;    // neuma_constitutive_svd_cache: consumed by this launch
+  const float* vin = ctx->svd_v_in;    // neuma_constitutive_svd_cache: consumed by this launch (either pointer)
   ctx->svd_v_in = nullptr;
+  ctx->svd_v_out = nullptr;
 #define NEUMA_BWD(WG, RTV)                                                                                       \
   NEUMA_CUDA(ctx, neuma_launch(constitutive_bwd_kernel<WG, RTV>, dim3(grid), dim3(bwd_threads<RTV>()),            \
                                bwd_smem<RTV>(), st, kind, n, F, sg, alpha, gout, gF, gW0, gW1, gW2, gWpart,       \
