@@ -249,16 +249,17 @@ class SlabRollout:
 
     Same kernels and per-substep saved grids as neuma_b200.pipeline.FusedFrame, plus the halo
     exchange:
-      halo="fused" (default)  ONE own kernel per exchange (FusedHalo), windowed to the occupied x-y
-                              range; with overlap=True it runs on a side stream while the
-                              particles that do not touch a shared plane go through P2G, grid_op and
-                              G2P (forward) / the adjoint scatter, node pass and gather (backward):
-                              boundary particles first -> exchange || interior -> boundary rest
-                              (overlap="full"), or only the scatter pass is split (overlap="scatter");
+      halo="fused" (default)  ONE own kernel per exchange (FusedHalo), windowed to the box the rank's
+                              particles occupy.  overlap="split" (default): the particles are kept boundary
+                              class first; the boundary range's scatter kernel, then the exchange on a side
+                              stream under the interior range's scatter kernel -- split on a whole number of
+                              tile rounds of the persistent constitutive kernels (split_fwd / split_bwd).
+                              overlap="none": in line.  overlap="scatter" / "full": run-time particle
+                              classes (csrc/mpm_common.cuh::particle_selected), kept as measured alternatives;
       halo="peer"             round 1: push + add/ack kernel pair per neighbour (PeerHalo);
       halo="nccl"             send/recv pairs, eager launches.
-    The classes are decided per particle at run time from its current position (exact under
-    drift), csrc/mpm_common.cuh::particle_selected."""
+    The backward runs [plasticity bwd + adjoint scatter] [exchange] [node pass] [adjoint gather + elasticity
+    bwd] with two adjoint targets in turn (overlap "none" / "split", fuse=True)."""
 
     def __init__(self, G: int, dt: float, We, Wp, alpha: float, substeps: int, device, group=None,
                  bound: int = 1, gravity=(0.0, -9.8, 0.0), eps: float = 6e-7, bc: str = "noslip",
