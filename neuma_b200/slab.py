@@ -244,6 +244,14 @@ class FusedHalo:
         self.ops.halo_exchange(c, lo, hi, box, self.cnt)
 
 
+def split_on_tile_rounds(nb: int, n: int, sms: int, pipelines: int, tile: int = 128) -> int:
+    """Smallest split point >= nb that is a whole number of tile rounds of a persistent constitutive kernel
+    (one CTA per SM, `pipelines` tile pipelines of `tile` particles each), clipped to n: launching [0, split)
+    and [split, n) separately then costs no more rounds than one launch over [0, n)."""
+    rnd = sms * pipelines * tile
+    return min(n, -(-nb // rnd) * rnd)
+
+
 class SlabRollout:
     """S-substep differentiable rollout (elasticity -> MPM -> plasticity) of this rank's slab.
 
@@ -352,8 +360,8 @@ class SlabRollout:
         # point on a whole number of tile ROUNDS costs no extra round, any other point costs one
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
         n_loc = int(loc[0].shape[0]) if loc[0].dim() else 0
-        self.split_fwd = min(n_loc, -(-self.nb // (sms * 3 * 128)) * (sms * 3 * 128))
-        self.split_bwd = min(n_loc, -(-self.nb // (sms * 2 * 128)) * (sms * 2 * 128))
+        self.split_fwd = split_on_tile_rounds(self.nb, n_loc, sms, 3)
+        self.split_bwd = split_on_tile_rounds(self.nb, n_loc, sms, 2)
         loc = [ops.gather_rows(t, perm) if t.shape[0] else t for t in loc]
         self.ids = mine.to(dev)[perm.long()]
         n = self.n = int(loc[0].shape[0])

@@ -106,3 +106,17 @@ def test_halo_exchange_sums_to_global_grid(world):
     for rank, err, total in res:
         assert err < 1e-12, (rank, err)
         assert total == n
+
+
+def test_split_point_sits_on_whole_tile_rounds():
+    """overlap="split": two launches over [0, split) and [split, n) must not cost more tile rounds of the
+    persistent constitutive kernels than one launch over [0, n)."""
+    from neuma_b200.slab import split_on_tile_rounds
+    sms, tile = 148, 128
+    rounds = lambda cnt, pipes: -(-(-(-cnt // tile)) // (sms * pipes))      # ceil(ceil(cnt / tile) / (sms * pipes))
+    for pipes in (2, 3):
+        for n, nb in ((127284, 39251), (500000, 41000), (20000, 7000), (1000, 0), (56832, 56832), (300000, 299999)):
+            s = split_on_tile_rounds(nb, n, sms, pipes, tile)
+            assert nb <= s <= n
+            assert s == n or s % (sms * pipes * tile) == 0
+            assert rounds(s, pipes) + rounds(n - s, pipes) == rounds(n, pipes) or s == n
