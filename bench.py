@@ -498,6 +498,7 @@ def dropin_measure(wl, dev, state0, steps: int = 5, warmup: int = 2, cache_merge
 
 # --------------------------------------------------------------------------- Z-slab mode
 SLAB_WORKLOAD = "block-1m-256"
+SLAB_FUSE_GATHER = False
 
 
 def slab_measure(dev, world: int, rank: int, substeps: int, steps: int, warmup: int, halo: str = "fused",
@@ -517,7 +518,7 @@ def slab_measure(dev, world: int, rank: int, substeps: int, steps: int, warmup: 
 
     def make(standalone: bool, **kw):
         sim = SlabRollout(spec["G"], spec["dt"], w["elastic"], w["plastic"], w["alpha"], substeps, dev,
-                          halo=halo, standalone=standalone, **kw)
+                          halo=halo, standalone=standalone, fuse_gather=SLAB_FUSE_GATHER, **kw)
         sim.distribute(p["x"], p["v"], p["C"], p["F"], p["vol"], p["rho"], p["clip"], p["enabled"])
         g = [torch.randn(sim.n, 3, generator=gen).to(dev), None, None,
              torch.randn(sim.n, 3, 3, generator=gen).to(dev)]
@@ -700,7 +701,7 @@ def run_reference(args):
 
 
 def main():
-    global WORKLOAD, GOLD, SLAB_WORKLOAD
+    global WORKLOAD, GOLD, SLAB_WORKLOAD, SLAB_FUSE_GATHER
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -712,15 +713,17 @@ def main():
                     help="parity-test configs of BASELINE.json for the record; the headline is jellyduck-100k-128")
     ap.add_argument("--no-fuse", action="store_true",
                     help="A/B: every MPM stage its own kernel (same as --fuse none)")
-    ap.add_argument("--fuse", default="best", choices=["best", "full", "epilogue", "none"],
-                    help="A/B: epilogue = P2G / the adjoint scatter ride in the constitutive kernels; full = also G2P "
-                         "and the adjoint gather (3 kernels per substep each way); best (default) = epilogue forward, "
+    ap.add_argument("--fuse", default="epilogue", choices=["epilogue", "full", "backward-full", "none"],
+                    help="A/B: epilogue (default) = P2G / the adjoint scatter ride in the constitutive kernels; full = also "
+                         "G2P and the adjoint gather (3 kernels per substep each way); backward-full = epilogue forward, "
                          "full backward; none = every stage its own kernel")
     ap.add_argument("--save-svd", action="store_true",
                     help="A/B: the forward constitutive kernels save V, the backward ones skip the Jacobi iteration")
     ap.add_argument("--no-dropin", action="store_true", help="skip the drop-in (autograd classes) measurement")
     ap.add_argument("--no-slab", action="store_true", help="skip the Z-slab (config 5) section of the line")
     ap.add_argument("--slab-steps", type=int, default=5, help="timed frames of the Z-slab section")
+    ap.add_argument("--slab-fuse-gather", action="store_true",
+                    help="A/B: slab backward with the adjoint gather inside the elasticity backward's prologue")
     ap.add_argument("--slab-workload", default=SLAB_WORKLOAD, choices=["block-1m-256", "block-250k-256"],
                     help="block-250k-256: development proxy (2 GPUs carry an 8-GPU rank's load each)")
     ap.add_argument("--halo", default="fused", choices=["fused", "peer", "nccl"],
@@ -729,9 +732,10 @@ def main():
     ap.add_argument("--slab", action="store_true",
                     help="BASELINE config 5: 1M particles / 256^3 MPM fwd+bwd, Z-slab sharded over the ranks")
     args = ap.parse_args()
-    args.fuse = False if (args.no_fuse or args.fuse == "none") else (True if args.fuse == "best" else args.fuse)
+    args.fuse = False if (args.no_fuse or args.fuse == "none") else args.fuse
     WORKLOAD = args.workload
     SLAB_WORKLOAD = args.slab_workload
+    SLAB_FUSE_GATHER = args.slab_fuse_gather
     if WORKLOAD.startswith("claycat"):       # plasticine_0300 weights
         GOLD = os.path.join(ROOT, "tests", "golden", "material_plasticine.npz")
     if args.impl == "reference":

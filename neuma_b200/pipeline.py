@@ -57,11 +57,12 @@ class FusedFrame:
         (neuma_constitutive_svd_cache).  Measured (profiles/r03s_save_svd_ab.txt): backward -0.045 ms,
         forward +0.05 ms per frame at 100 k / S = 20 -- the Jacobi sweeps are not on the exposed path -- so
         it is OFF by default.
-        fuse: which MPM stages ride inside the constitutive kernels.  "epilogue" = the two scatters (P2G after
-        elasticity, the adjoint scatter after the plasticity backward); "full" = also G2P in front of
-        plasticity and the adjoint gather in front of the elasticity backward (three kernels per substep
-        each way); True (default) = the measured best of both, "epilogue" forward and "full" backward
-        (profiles/r03_fuse_modes.txt); False = every stage its own kernel."""
+        fuse: which MPM stages ride inside the constitutive kernels.  True (default) | "epilogue" = the two
+        scatters (P2G after elasticity, the adjoint scatter after the plasticity backward); "full" = also G2P in
+        front of plasticity and the adjoint gather in front of the elasticity backward (three kernels per
+        substep each way); False = every stage its own kernel.  Measured (profiles/r03_fuse_modes.txt): with
+        programmatic dependent launch on, "epilogue" wins in both directions; "full" costs the forward 13 %.
+        "backward-full" = epilogue forward + full backward (the best combination before PDL)."""
         self.n, self.S, self.dev = int(n), int(substeps), device
         self.frames = int(frames)
         self.T = self.S * self.frames                   # substeps resident for one backward
@@ -74,11 +75,11 @@ class FusedFrame:
         # statics in the engine's (cell-sorted) particle order; refreshed by load_state()
         self.vol, self.rho, self.clip, self.enabled = [t.clone() for t in self._statics_in]
         self.sort = bool(sort)
-        if fuse not in (True, False, "full", "epilogue"):
-            raise ValueError("fuse must be True, False, 'full' or 'epilogue'")
+        if fuse not in (True, False, "full", "epilogue", "backward-full"):
+            raise ValueError("fuse must be True, False, 'full', 'epilogue' or 'backward-full'")
         self.fuse = fuse                                 # which MPM stages ride inside the constitutive kernels
-        self.fuse_fwd = {True: "epilogue", False: False}.get(fuse, fuse)
-        self.fuse_bwd = {True: "full", False: False}.get(fuse, fuse)
+        self.fuse_fwd = {True: "epilogue", False: False, "backward-full": "epilogue"}.get(fuse, fuse)
+        self.fuse_bwd = {True: "epilogue", False: False, "backward-full": "full"}.get(fuse, fuse)
         self.perm = torch.arange(n, device=device, dtype=torch.int32)   # sorted slot -> caller index
         self.inv = self.perm.clone()                                    # caller index -> sorted slot
         self.We = [w.detach().clone().contiguous() for w in We]     # engine-owned static buffers (set_weights)

@@ -272,7 +272,7 @@ class SlabRollout:
     def __init__(self, G: int, dt: float, We, Wp, alpha: float, substeps: int, device, group=None,
                  bound: int = 1, gravity=(0.0, -9.8, 0.0), eps: float = 6e-7, bc: str = "noslip",
                  halo_k: int = 1, elastic_kind: int = 0, halo: str = "fused", use_graphs: Optional[bool] = None,
-                 overlap="split", standalone: bool = False, fuse: bool = True):
+                 overlap="split", standalone: bool = False, fuse: bool = True, fuse_gather: bool = False):
         from . import ops
         self.ops = ops
         self.G, self.dt, self.S, self.dev, self.group = int(G), float(dt), int(substeps), device, group
@@ -321,6 +321,9 @@ class SlabRollout:
             raise ValueError("overlap must be 'none', 'split', 'scatter' or 'full'")
         self.overlap = overlap if self._fused is not None else "none"
         self.fuse = bool(fuse)      # P2G / adjoint scatter inside the constitutive kernels' epilogues
+        # the adjoint gather inside the elasticity backward's prologue (+ two adjoint targets in turn): the better
+        # backward before programmatic dependent launch was on, the worse one since (profiles/r03_fuse_modes.txt)
+        self.fuse_gather = bool(fuse_gather) and self.fuse
         # graphs need capturable communication: peer memory yes, NCCL send/recv no
         self.use_graphs = (halo != "nccl" or self.world == 1) if use_graphs is None else bool(use_graphs)
         if self.use_graphs and halo == "nccl" and self.world > 1:
@@ -374,7 +377,7 @@ class SlabRollout:
         self.vol, self.rho, self.clip, self.enabled = loc[4:]
         self.grid = torch.zeros(S, nz, G, G, 4, **f)
         self.adj = torch.zeros(nz, G, G, 4, **f)           # adjoint scatter target(s), cleared in the backward
-        self.adj2 = torch.zeros(nz, G, G, 4, **f) if (self.fuse and self.overlap in ("none", "split")) else None
+        self.adj2 = torch.zeros(nz, G, G, 4, **f) if (self.fuse_gather and self.overlap in ("none", "split")) else None
         self.box = torch.zeros(S + 1, 8, device=dev, dtype=torch.int32)
         self.g = [[torch.zeros(n, 3, **f), torch.zeros(n, 3, **f), torch.zeros(n, 3, 3, **f),
                    torch.zeros(n, 3, 3, **f)] for _ in range(2)]
@@ -555,7 +558,7 @@ class SlabRollout:
             if self.world > 1 and not windowed:
                 for vw in self._overlap_views(adj):
                     vw.zero_()
-        if self.fuse and self.overlap in ("none", "split"):
+        if self.fuse_gather and self.overlap in ("none", "split"):
             # [plasticity bwd + adjoint scatter] [exchange] [node pass] [adjoint gather + elasticity bwd]; two
             # scatter targets in turn, so that the clear for substep s - 1 runs beside substep s (as
             # FusedFrame._sim_backward, fuse_bwd = "full").  split: the exchange (and that clear) run on the side

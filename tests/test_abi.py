@@ -48,3 +48,18 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh")):
                 src = open(os.path.join(dp, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_every_module_imports_without_a_gpu():
+    """A syntax error in a module that only the -m gpu tests import must not wait for the GPU box."""
+    import importlib
+    for m in ("neuma_b200.pipeline", "neuma_b200.slab", "neuma_b200.ops", "neuma_b200.material", "neuma_b200.glue",
+              "neuma_b200.rasterizer", "neuma_b200.sim", "neuma_b200.svd", "neuma_b200.synthetic", "neuma_b200.build",
+              "bench", "__graft_entry__"):
+        importlib.import_module(m)
+    import glob
+    import os
+    import py_compile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for f in glob.glob(os.path.join(root, "tools", "*.py")) + glob.glob(os.path.join(root, "tests", "*.py")):
+        py_compile.compile(f, doraise=True)

@@ -65,7 +65,7 @@ def test_fuse_modes_agree(cuda_dev, compact):
     from neuma_b200.pipeline import FusedFrame
     spec, cc, d, W, alpha, settings, bind, gs, F0, gt, kxyz = _setup(cuda_dev, n=4000)
     runs = {}
-    for fuse in (False, "epilogue", "full", True):
+    for fuse in (False, "epilogue", "full", "backward-full", True):
         eng = FusedFrame(spec["n"], cc, (d["vol"], d["rho"], d["clip"], d["enabled"]), W["elastic"], W["plastic"],
                          alpha, 4, cuda_dev, bind=bind, gaussians=gs, settings=settings, use_graphs=False, fuse=fuse,
                          compact=compact)
@@ -76,7 +76,7 @@ def test_fuse_modes_agree(cuda_dev, compact):
         runs[fuse] = (loss.clone(), [t.clone() for t in eng.final_state()], [t.clone() for t in g0],
                       [t.clone() for t in eng.gWe + eng.gWp], eng.box.clone())
     ref = runs[False]
-    for fuse in ("epilogue", "full", True):
+    for fuse in ("epilogue", "full", "backward-full", True):
         loss, st, g0, gW, box = runs[fuse]
         assert torch.equal(box[:, :6], ref[4][:, :6]), fuse            # node boxes of every substep
         assert abs(float(loss) - float(ref[0])) <= 1e-6 * abs(float(ref[0])), fuse

@@ -30,7 +30,7 @@ def _views(IM, eyes, bg=1.0):
 
 @pytest.mark.parametrize("loss,mask,graphs,fuse", [("l2", False, True, True), ("l1", False, False, True),
                                                    ("l2", True, True, True), ("l2", False, True, "full"),
-                                                   ("l1", False, False, "epilogue")])
+                                                   ("l1", False, False, "backward-full")])
 def test_rollout_views_weights_exclusion_against_oracle(cuda_dev, loss, mask, graphs, fuse):
     from neuma_b200.pipeline import FusedFrame
     from oracle import mpm_oracle as MO, pipeline_oracle as PO
