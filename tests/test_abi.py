@@ -63,3 +63,38 @@ def test_every_module_imports_without_a_gpu():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     for f in glob.glob(os.path.join(root, "tools", "*.py")) + glob.glob(os.path.join(root, "tests", "*.py")):
         py_compile.compile(f, doraise=True)
+
+
+def _header_params():
+    """name -> list of parameter type strings, parsed from include/neuma_b200.h"""
+    text = open(os.path.join(ROOT, "include", "neuma_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"//[^\n]*", "", text)
+    out = {}
+    for m in re.finditer(r"\b(neuma_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S):
+        params = [p.strip() for p in m.group(2).replace("\n", " ").split(",")]
+        out[m.group(1)] = [] if params in ([""], ["void"]) else params
+    return out
+
+
+def test_ctypes_signatures_match_the_header():
+    """Argument COUNT and KIND (pointer / integer / float) of every binding against the header: a mismatch
+    would only show up as a crash on the GPU box."""
+    decl = _header_params()
+    for name, argtypes in _lib.SIGNATURES.items():
+        assert name in decl, name
+        params = decl[name]
+        assert len(params) == len(argtypes), (name, len(params), len(argtypes))
+        for p, a in zip(params, argtypes):
+            is_ptr = "*" in p
+            if is_ptr:
+                assert a is ctypes.c_void_p or a is ctypes.c_char_p or hasattr(a, "contents") or \
+                    issubclass(a, ctypes._Pointer), (name, p, a)
+            elif re.search(r"\bfloat\b", p):
+                assert a is ctypes.c_float, (name, p, a)
+            elif re.search(r"\bsize_t\b", p):
+                assert a is ctypes.c_size_t, (name, p, a)
+            elif re.search(r"\blong long\b", p):
+                assert a is ctypes.c_longlong, (name, p, a)
+            else:
+                assert a in (ctypes.c_int, ctypes.c_int32, ctypes.c_uint32, ctypes.c_uint), (name, p, a)
